@@ -1,0 +1,118 @@
+"""Parity of the CUDA path against the reference (golden vectors) and the numpy oracle, through the
+C-ABI `tspws_main` with host buffers -- the call the reference's CLI / MEX gateway make.
+
+Tolerances (BASELINE.json north_star), all as max|a-b| / max|b|:
+    stacked traces (ls, tsPWS)  <= 1e-4        coherence map |PS|/K  <= 1e-5
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import cases as CS, tspws_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL_STACK, TOL_COH = 1e-4, 1e-5
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def gpu_run(pkg, lib, x, dt=1.0, beg=None, **params):
+    p = pkg.default_params(**params)
+    r = pkg.call_tspws_main(lib, x, p, dt=dt, beg=beg)
+    assert r["rc"] == 0, f"tspws_main returned {r['rc']}"
+    n = lib.tspws_b200_get_coherence(None, 0)
+    assert n > 0
+    coh = np.empty(n)
+    assert lib.tspws_b200_get_coherence(coh.ctypes.data_as(C.POINTER(C.c_double)), n) == n
+    st = np.empty(2 * n)
+    ps = np.empty(2 * n)
+    assert lib.tspws_b200_get_stacks(st.ctypes.data_as(C.POINTER(C.c_double)),
+                                     ps.ctypes.data_as(C.POINTER(C.c_double)), n) == n
+    r.update(coherence=coh, st=st[0::2] + 1j * st[1::2], ps=ps[0::2] + 1j * ps[1::2])
+    return r
+
+
+@pytest.mark.parametrize("name", sorted(CS.CASES))
+def test_main_stack_matches_reference_golden(pkg, gpu_lib, name):
+    case = CS.CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    x = CS.make_input(case)
+    r = gpu_run(pkg, gpu_lib, x, dt=case["dt"], beg=case.get("beg"), **case["params"])
+    p = r["params"]
+    np.testing.assert_array_equal(
+        np.array([p.J, p.V, p.s0, p.b0, p.w0, p.fmin, p.fold], dtype=np.float64), g["derived"])
+    K = int(g["K"])
+    assert O.nerr(r["coherence"], np.abs(g["ps"]) / K) <= TOL_COH
+    assert O.nerr(r["ps"], g["ps"]) <= TOL_COH
+    assert O.nerr(r["st"], g["st"]) <= TOL_STACK
+    assert O.nerr(r["ls"], g["ls"]) <= TOL_STACK
+    assert O.nerr(r["tsPWS"], g["tsPWS"]) <= TOL_STACK
+
+
+@pytest.mark.parametrize("fp64_tail", [0, 1])
+def test_two_stage_fp64_tail_option(pkg, gpu_lib, fp64_tail):
+    case = CS.CASES["morlet_two_stage_unbiased_64x4096"]
+    g = np.load(os.path.join(GOLD, "morlet_two_stage_unbiased_64x4096.npz"))
+    gpu_lib.tspws_b200_set_option(pkg.OPT_FP64_TAIL, fp64_tail)
+    try:
+        r = gpu_run(pkg, gpu_lib, CS.make_input(case), **case["params"])
+    finally:
+        gpu_lib.tspws_b200_set_option(pkg.OPT_FP64_TAIL, 0)
+    tol = 1e-9 if fp64_tail else TOL_COH
+    assert O.nerr(r["coherence"], np.abs(g["ps"]) / int(g["K"])) <= tol
+    assert O.nerr(r["tsPWS"], g["tsPWS"]) <= (2e-7 if fp64_tail else TOL_STACK)
+
+
+def test_medium_single_stage_vs_oracle(pkg, gpu_lib):
+    """256 x 8192, Morlet w0=6 (the C2 frame at half length): CUDA vs numpy oracle."""
+    x = O.synthetic_traces(256, 8192, seed=4242)
+    r = gpu_run(pkg, gpu_lib, x, w0=6.0, w0set=4, lrm=1)
+    o = O.tspws_main(O.Params(w0=6.0, w0set=4, lrm=1), x)
+    assert O.nerr(r["coherence"], o["coherence"]) <= TOL_COH
+    assert O.nerr(r["ls"], o["ls"]) <= TOL_STACK
+    assert O.nerr(r["tsPWS"], o["tsPWS"]) <= TOL_STACK
+
+
+def test_medium_two_stage_vs_oracle(pkg, gpu_lib):
+    """1024 x 16384 headline frame (Morlet, 44 scales), two-stage Kmax=10 unbiased, rm + fold."""
+    x = O.synthetic_traces(1024, 16384, seed=777)
+    kw = dict(Kmax=10, unbiased=1, lrm=1, fold=1)
+    r = gpu_run(pkg, gpu_lib, x, **kw)
+    o = O.tspws_main(O.Params(**kw), x)
+    assert r["params"].J == 11 and r["params"].V == 4
+    assert O.nerr(r["coherence"], o["coherence"]) <= TOL_COH
+    assert O.nerr(r["ls"], o["ls"]) <= TOL_STACK
+    assert O.nerr(r["tsPWS"], o["tsPWS"]) <= TOL_STACK
+
+
+def test_repeated_calls_and_plan_cache(pkg, gpu_lib):
+    x = O.synthetic_traces(16, 1024, seed=5)
+    a = gpu_run(pkg, gpu_lib, x, lrm=1)
+    b = gpu_run(pkg, gpu_lib, x, lrm=1)
+    np.testing.assert_array_equal(a["tsPWS"], b["tsPWS"])      # deterministic
+    c = gpu_run(pkg, gpu_lib, x, lrm=1, type=-3)
+    assert not np.array_equal(a["tsPWS"], c["tsPWS"])
+    d = gpu_run(pkg, gpu_lib, x, lrm=1)
+    np.testing.assert_array_equal(a["tsPWS"], d["tsPWS"])
+
+
+def test_writeback_option_mutates_input_like_reference(pkg, gpu_lib):
+    x = O.synthetic_traces(12, 600, seed=9)
+    ref = x.copy()
+    O.fold_inplace(ref)
+    O.remove_mean_inplace(ref)
+    gpu_lib.tspws_b200_set_option(pkg.OPT_WRITEBACK, 1)
+    try:
+        for kmax in (0, 4):
+            r = gpu_run(pkg, gpu_lib, x, lrm=1, fold=1, Kmax=kmax)
+            np.testing.assert_array_equal(r["sigall"], ref)    # bit-exact fp32 mutation
+    finally:
+        gpu_lib.tspws_b200_set_option(pkg.OPT_WRITEBACK, 0)
+
+
+def test_launch_counter_moves(pkg, gpu_lib):
+    n0 = gpu_lib.tspws_b200_kernel_launches()
+    gpu_run(pkg, gpu_lib, O.synthetic_traces(8, 512, seed=1))
+    assert gpu_lib.tspws_b200_kernel_launches() > n0

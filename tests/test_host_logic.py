@@ -1,0 +1,123 @@
+"""Host logic through the C-ABI (no GPU): parameter derivation, frame geometry and filters,
+resampling plans -- against the numpy oracle (and the compiled reference when present)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from oracle import tspws_oracle as O
+
+CASES = [
+    # (type, N, dt, extra t_tsPWS fields)
+    (-1, 16384, 1.0, {}),
+    (-1, 16384, 1.0, dict(w0=6.0, w0set=4)),
+    (-3, 16384, 1.0, {}),
+    (-1, 32768, 1.0, {}),
+    (-1, 8192, 1.0, {}),
+    (-1, 16501, 4.0, {}),
+    (-1, 16501, 4.0, dict(fmin=0.004, J=3)),
+    (-1, 16501, 4.0, dict(fmin=0.004)),
+    (-2, 1000, 1.0, {}),
+    (-1, 1000, 1.0, dict(Q=4.0, w0set=1)),
+    (-1, 1000, 1.0, dict(cycle=3.0, w0set=2)),
+    (-1, 1000, 1.0, dict(w0=3.0, w0set=4)),            # b0 truncates to 0 -> undecimated frame
+    (-1, 1001, 1.0, dict(J=8, V=6, s0=4.0, lVfix=1, ls0fix=1)),
+    (-3, 777, 1.0, dict(uni=1, J=4)),
+    (-1, 1000, 1.0, dict(fmin=1e-9)),                  # fmin too low -> reset to default
+]
+
+
+@pytest.mark.parametrize("typ,N,dt,kw", CASES)
+def test_params_and_frame_match_oracle(pkg, lib, typ, N, dt, kw):
+    p = pkg.default_params(type=typ, **kw)
+    assert lib.tspws_b200_derive_params(C.byref(p), N, dt) == 0
+    po = O.derive_params(O.Params(type=typ, **kw), N, dt)
+    assert (p.J, p.V) == (po.J, po.V)
+    assert p.s0 == po.s0 and p.b0 == po.b0 and p.w0 == po.w0 and p.fmin == po.fmin
+
+    fr = lib.tspws_b200_frame_create(p.type, p.J, p.V, N, p.s0, p.b0, p.w0, p.uni)
+    assert fr
+    try:
+        d = pkg.frame_to_dict(fr)
+    finally:
+        lib.tspws_b200_frame_destroy(fr)
+    fo = O.frame_from_params(po, N)
+    assert d["S"] == fo.S and d["ncoef"] == fo.ncoef
+    np.testing.assert_array_equal(d["L"], fo.L)
+    np.testing.assert_array_equal(d["center"], fo.center)
+    np.testing.assert_array_equal(d["D"], fo.D)
+    np.testing.assert_array_equal(d["Ns"], fo.Ns)
+    np.testing.assert_allclose(d["scale"], fo.scale, rtol=0, atol=0)
+    assert abs(d["Cpsi"] - fo.Cpsi) <= 1e-15 * abs(fo.Cpsi)
+    wo = np.concatenate(fo.w)
+    assert np.max(np.abs(d["w"] - wo)) <= 2e-14 * np.max(np.abs(wo))
+
+
+def test_geometry_of_baseline_configs(pkg, lib):
+    """SURVEY.md Appendix B table (probed with the reference's CreateWaveletFamily)."""
+    expect = {  # (type, N, w0) -> (V, J, scales, ncoef, ntaps)
+        (-1, 16384, None): (4, 11, 44, 65504, 172907),
+        (-1, 16384, 6.0): (5, 11, 55, 81880, 218177),
+        (-3, 16384, None): (2, 10, 20, 98176, 24750),
+        (-1, 32768, None): (4, 12, 48, 131040, 345853),
+        (-1, 8192, None): (4, 10, 40, 32736, 86431),
+    }
+    for (typ, N, w0), (V, J, S, ncoef, ntaps) in expect.items():
+        kw = dict(w0=w0, w0set=4) if w0 else {}
+        p = pkg.default_params(type=typ, **kw)
+        lib.tspws_b200_derive_params(C.byref(p), N, 1.0)
+        assert (p.V, p.J) == (V, J)
+        fr = lib.tspws_b200_frame_create(p.type, p.J, p.V, N, p.s0, p.b0, p.w0, p.uni)
+        f = fr.contents
+        assert (f.S, f.ncoef, f.ntaps) == (S, ncoef, ntaps)
+        lib.tspws_b200_frame_destroy(fr)
+
+
+def test_frame_rejects_bad_type(lib):
+    assert not lib.tspws_b200_frame_create(0, 3, 4, 100, 2.0, 1.0, 5.0, 0)
+    assert not lib.tspws_b200_frame_create(2, 3, 4, 100, 2.0, 1.0, 5.0, 0)
+    assert not lib.tspws_b200_frame_create(-4, 3, 4, 100, 2.0, 1.0, 5.0, 0)
+
+
+def test_subsampling_plan_counts(lib):
+    for J, K in [(10, 3), (10, 5), (10, 8), (499, 250), (7, 7), (7, 0)]:
+        buf = C.create_string_buffer(J)
+        assert lib.tspws_b200_subsampling_plan(buf, J, K) == 0
+        sel = np.frombuffer(buf.raw, dtype=np.int8, count=J)
+        assert set(np.unique(sel)) <= {0, 1} and sel.sum() == K
+    assert lib.tspws_b200_subsampling_plan(None, 4, 2) == 1
+    assert lib.tspws_b200_subsampling_plan(C.create_string_buffer(4), 4, 5) == 2
+
+
+def test_subsampling_plan_follows_reference_rand_sequence(lib):
+    """Same rand() consumption as reference SubsamplingPlan: with both libraries in one process
+    sharing libc's rand(), re-seeding and drawing must give identical plans."""
+    from oracle import ref_lib as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built")
+    libc = C.CDLL(None)
+    ref = R.load()
+    for J, K in [(40, 10), (40, 30), (499, 250), (9, 4)]:
+        a, b = C.create_string_buffer(J), C.create_string_buffer(J)
+        libc.srand(1234)
+        ref.SubsamplingPlan(a, J, K)
+        libc.srand(1234)
+        lib.tspws_b200_subsampling_plan(b, J, K)
+        assert a.raw == b.raw
+
+
+def test_jackknife_plans_match_oracle(lib):
+    day = 86400
+    t0 = 946684800  # 2000-01-01
+    times = np.array([t0 + day * (3 * i) for i in range(200)], dtype=np.int64)
+    for n, d in [(12, 2), (6, 1), (5, 3)]:
+        Cn = math.comb(n, d)
+        buf = C.create_string_buffer(Cn * len(times))
+        rc = lib.tspws_b200_jackknife_plans(buf, times.ctypes.data_as(C.POINTER(C.c_long)), len(times), d, n, Cn)
+        assert rc == 0
+        sel = np.frombuffer(buf.raw, dtype=np.int8).reshape(Cn, len(times))
+        np.testing.assert_array_equal(sel, O.jackknife_plans(times, n, d))
+    assert lib.tspws_b200_jackknife_plans(None, None, 3, 1, 2, 2) == 1
+    z = np.zeros(3, dtype=np.int64)
+    assert lib.tspws_b200_jackknife_plans(C.create_string_buffer(6), z.ctypes.data_as(C.POINTER(C.c_long)), 3, 1, 2, 2) == -2

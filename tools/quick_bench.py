@@ -1,0 +1,36 @@
+"""Scratch timing of the device-resident plan API (not the official bench)."""
+import ctypes as C, sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tests.conftest import load_pkg
+B = load_pkg(); lib = B.load_library()
+
+def run(name, mtr, n, reps=5, **kw):
+    p = B.default_params(**kw)
+    lib.tspws_b200_derive_params(C.byref(p), n, 1.0)
+    x = torch.randn(mtr, n, device="cuda", dtype=torch.float32)
+    ls = torch.empty(n, device="cuda"); ts = torch.empty(n, device="cuda")
+    plan = lib.tspws_b200_plan_create(C.byref(p), n, mtr, mtr, 0)
+    assert plan
+    stream = torch.cuda.current_stream().cuda_stream
+    def step():
+        rc = lib.tspws_b200_plan_stack(plan, x.data_ptr(), ls.data_ptr(), ts.data_ptr(), stream)
+        assert rc == 0, rc
+    for _ in range(2): step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        step(); ev[i + 1].record()
+    torch.cuda.synchronize()
+    ts_ = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+    best = min(ts_)
+    print(f"{name}: {mtr}x{n} J={p.J} V={p.V} best {best*1e3:.1f} us  median {sorted(ts_)[len(ts_)//2]*1e3:.1f} us  "
+          f"{mtr*n/best/1e6:.3f} Gsamples/s  {mtr*n*4/best/1e6:.1f} GB/s", flush=True)
+    lib.tspws_b200_plan_destroy(plan)
+
+if __name__ == "__main__":
+    run("two-stage morlet rm", 8192, 16384, Kmax=10, unbiased=1, lrm=1)
+    run("two-stage morlet", 8192, 16384, Kmax=10, unbiased=1)
+    run("two-stage mexhat rm", 8192, 16384, type=-3, Kmax=10, unbiased=1, lrm=1)
+    run("single-stage morlet w0=6 (512 traces)", 512, 16384, reps=3, w0=6.0, w0set=4, lrm=1)

@@ -1,0 +1,263 @@
+/*
+ * tspws_main.c -- the drop-in boundary: int tspws_main(t_tsPWS*, t_tsPWS_out*, t_data*)
+ * with the reference's semantics (reference src/ts_pws1f_lib.c:48-352), host buffers in and
+ * out, all arithmetic on the GPU.  Also the small amount of library state behind the additive
+ * exports of include/tspws_b200.h.
+ *
+ * No CPU fallback: when CUDA is unusable the call fails with TSPWS_ERR_CUDA.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cuda_runtime_api.h>
+
+#include "tspws_internal.h"
+
+/* from tspws_plan.c */
+const tspws_frame_t *tspws_plan_frame(tspws_plan_t *pl);
+const tspws_devframe_t *tspws_plan_devframe(tspws_plan_t *pl);
+/* from tspws_resample.c */
+int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
+                       unsigned int mtr, int max, const char *sel_override, unsigned int selM,
+                       cudaStream_t stream);
+int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
+                          unsigned int mtr, int max, cudaStream_t stream);
+
+static struct {
+    long          opt_writeback, opt_fp64_tail, opt_device;
+    int           cuda_state;              /* 0 unknown, 1 ok, -1 unusable */
+    cudaStream_t  stream;
+    /* cached plan of the last main stack */
+    tspws_plan_t *plan;
+    t_tsPWS       plan_key;
+    int           plan_max;
+    unsigned int  plan_mtr;
+    long          plan_fp64;
+    /* cached device buffers */
+    float        *d_x;   size_t d_x_cap;
+    float        *d_out; size_t d_out_cap;
+    /* explicit resampling selection */
+    char         *sel;   unsigned int selM, selmtr;
+} G;
+
+const char *tspws_b200_version(void) { return "tspws_b200 0.1 (sm_100a)"; }
+unsigned long tspws_b200_kernel_launches(void) { return tspws_cu_launch_count(); }
+
+int tspws_b200_set_option(int option, long value)
+{
+    switch (option) {
+    case TSPWS_OPT_WRITEBACK: G.opt_writeback = value; return 0;
+    case TSPWS_OPT_FP64_TAIL: G.opt_fp64_tail = value; return 0;
+    case TSPWS_OPT_DEVICE:    G.opt_device = value; G.cuda_state = 0; return 0;
+    default: return TSPWS_ERR_ARG;
+    }
+}
+long tspws_b200_get_option(int option)
+{
+    switch (option) {
+    case TSPWS_OPT_WRITEBACK: return G.opt_writeback;
+    case TSPWS_OPT_FP64_TAIL: return G.opt_fp64_tail;
+    case TSPWS_OPT_DEVICE:    return G.opt_device;
+    default: return -1;
+    }
+}
+
+int tspws_b200_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return -(int)e; }
+    return n;
+}
+
+static int ensure_cuda(void)
+{
+    if (G.cuda_state == 1) return 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        fprintf(stderr, "tspws_b200: no usable CUDA device (%s); this library has no CPU path\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        G.cuda_state = -1;
+        return TSPWS_ERR_CUDA;
+    }
+    if (G.opt_device < 0 || G.opt_device >= n) {
+        fprintf(stderr, "tspws_b200: device %ld out of range (0..%d)\n", G.opt_device, n - 1);
+        return TSPWS_ERR_CUDA;
+    }
+    if (cudaSetDevice((int)G.opt_device) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (!G.stream && cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking) != cudaSuccess) return TSPWS_ERR_CUDA;
+    G.cuda_state = 1;
+    return 0;
+}
+
+static void drop_plan(void)
+{
+    if (G.plan) { tspws_b200_plan_destroy(G.plan); G.plan = NULL; }
+}
+
+void tspws_b200_shutdown(void)
+{
+    drop_plan();
+    if (G.d_x)   { cudaFree(G.d_x);   G.d_x = NULL;   G.d_x_cap = 0; }
+    if (G.d_out) { cudaFree(G.d_out); G.d_out = NULL; G.d_out_cap = 0; }
+    if (G.stream) { cudaStreamDestroy(G.stream); G.stream = NULL; }
+    free(G.sel); G.sel = NULL; G.selM = G.selmtr = 0;
+    G.cuda_state = 0;
+}
+
+int tspws_b200_set_selection(const char *sel, unsigned int M, unsigned int mtr)
+{
+    free(G.sel); G.sel = NULL; G.selM = G.selmtr = 0;
+    if (!sel) return 0;
+    if (!M || !mtr) return TSPWS_ERR_ARG;
+    G.sel = (char *)malloc((size_t)M * mtr);
+    if (!G.sel) return TSPWS_ERR_ALLOC;
+    memcpy(G.sel, sel, (size_t)M * mtr);
+    G.selM = M; G.selmtr = mtr;
+    return 0;
+}
+
+static int grow(float **buf, size_t *cap, size_t need)
+{
+    if (*cap >= need) return 0;
+    if (*buf) { cudaFree(*buf); *buf = NULL; *cap = 0; }
+    if (cudaMalloc((void **)buf, need * sizeof(float)) != cudaSuccess) { cudaGetLastError(); return TSPWS_ERR_ALLOC; }
+    *cap = need;
+    return 0;
+}
+
+/* the fields of t_tsPWS that shape a plan */
+static int same_plan_key(const t_tsPWS *a, const t_tsPWS *b)
+{
+    return a->type == b->type && a->uni == b->uni && a->J == b->J && a->V == b->V &&
+           a->s0 == b->s0 && a->b0 == b->b0 && a->w0 == b->w0 && a->wu == b->wu &&
+           a->lrm == b->lrm && a->fold == b->fold && a->unbiased == b->unbiased && a->Kmax == b->Kmax;
+}
+
+long tspws_b200_get_stacks(double *st, double *ps, size_t ncoef)
+{
+    if (!G.plan) return TSPWS_ERR_NULL;
+    const size_t n = tspws_b200_plan_ncoef(G.plan);
+    if (!st && !ps) return (long)n;
+    if (ncoef < n) return TSPWS_ERR_ARG;
+    const void *d_st, *d_ps; unsigned int K; int f64;
+    tspws_b200_plan_stacks_ptr(G.plan, &d_st, &d_ps, &K, &f64);
+    const size_t esz = f64 ? sizeof(double) : sizeof(float);
+    void *tmp = malloc(2 * n * esz);
+    if (!tmp) return TSPWS_ERR_ALLOC;
+    for (int which = 0; which < 2; which++) {
+        double *dst = which ? ps : st;
+        if (!dst) continue;
+        if (cudaMemcpy(tmp, which ? d_ps : d_st, 2 * n * esz, cudaMemcpyDeviceToHost) != cudaSuccess) { free(tmp); return TSPWS_ERR_CUDA; }
+        if (f64) memcpy(dst, tmp, 2 * n * sizeof(double));
+        else for (size_t i = 0; i < 2 * n; i++) dst[i] = (double)((float *)tmp)[i];
+    }
+    free(tmp);
+    return (long)n;
+}
+
+long tspws_b200_get_coherence(double *coh, size_t ncap)
+{
+    if (!G.plan) return TSPWS_ERR_NULL;
+    const size_t n = tspws_b200_plan_ncoef(G.plan);
+    if (!coh) return (long)n;
+    if (ncap < n) return TSPWS_ERR_ARG;
+    double *ps = (double *)malloc(2 * n * sizeof(double));
+    if (!ps) return TSPWS_ERR_ALLOC;
+    long rc = tspws_b200_get_stacks(NULL, ps, n);
+    if (rc >= 0) {
+        unsigned int K = 1;
+        tspws_b200_plan_stacks_ptr(G.plan, NULL, NULL, &K, NULL);
+        for (size_t i = 0; i < n; i++) coh[i] = hypot(ps[2 * i], ps[2 * i + 1]) / (double)K;
+    }
+    free(ps);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
+{
+    if (tspws == NULL || out == NULL || in == NULL) { printf("tspws_main: NULL input\n"); return -1; }
+
+    t_hdr *hdr = &in->hdr;
+    const int max = hdr->max;
+    unsigned int mtr = tspws->Nmax ? tspws->Nmax : hdr->mtr;     /* src/ts_pws1f_lib.c:65 */
+    if (mtr > hdr->mtr) mtr = hdr->mtr;                           /* never read past the input */
+    const unsigned int nsamp = (unsigned int)max;
+    int nerr = 0;
+
+    /* fold only when the lag axis is symmetric (src/ts_pws1f_lib.c:71-75) */
+    if (tspws->fold && !tspws_fold_allowed(hdr->beg, hdr->dt, max)) {
+        printf("Warning: Folding ignored. B = %f, E = %f, nsamp = %u\n", hdr->beg, hdr->beg + (max - 1) * hdr->dt, nsamp);
+        tspws->fold = 0;
+    }
+    tspws_b200_derive_params(tspws, nsamp, hdr->dt);
+    if (tspws->verbose) tspws_print_params(tspws, nsamp, hdr->dt);
+    if (max <= 0 || !mtr) return 0;                               /* nothing to stack (src/ts_pws1f_lib.c:194) */
+    if (!in->sigall || !out->ls || !out->tsPWS) { printf("tspws_main: NULL input\n"); return -1; }
+    if (tspws->type > -1 || tspws->type < -3 || !tspws->V) {
+        printf("Error: CreateWaveletFamily: Complex wavelet not defined.\n");
+        return TSPWS_ERR_ARG;
+    }
+
+    if ((nerr = ensure_cuda())) return nerr;
+    cudaStream_t st = G.stream;
+
+    /* ---- traces to the device ---- */
+    const size_t nelem = (size_t)mtr * (size_t)max;
+    if (grow(&G.d_x, &G.d_x_cap, nelem) || grow(&G.d_out, &G.d_out_cap, 2 * (size_t)max)) {
+        fprintf(stderr, "tspws_b200: out of device memory\n");
+        return TSPWS_ERR_ALLOC;
+    }
+    if (cudaMemcpyAsync(G.d_x, in->sigall, nelem * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) goto cuda_fail;
+
+    const int resampling  = (tspws->subsmpl_N > 0 && tspws->subsmpl_p > 0) || (tspws->jackknife_n > 0 && tspws->jackknife_d > 0);
+    const int two_stage   = tspws->Kmax && tspws->Kmax <= mtr;
+    /* Later passes (resampling, convergence, write-back) need the cleaned traces themselves; the
+     * plain two-stage stack does not and folds / de-means its Kmax group sums instead. */
+    const int exact_prep  = two_stage && (tspws->fold || tspws->lrm) &&
+                            (resampling || tspws->convergence || G.opt_writeback);
+    t_tsPWS pp = *tspws;
+    if (exact_prep) {
+        if (tspws_cu_prep(G.d_x, (int)mtr, max, tspws->fold, tspws->lrm, st)) goto cuda_fail;
+        pp.fold = 0; pp.lrm = 0;
+    }
+
+    /* ---- main stack ---- */
+    if (!G.plan || !same_plan_key(&G.plan_key, &pp) || G.plan_max != max || G.plan_mtr != mtr ||
+        G.plan_fp64 != G.opt_fp64_tail) {
+        drop_plan();
+        G.plan = tspws_b200_plan_create(&pp, max, mtr, mtr, 0);
+        if (!G.plan) { fprintf(stderr, "tspws_b200: cannot create the stacking plan\n"); return TSPWS_ERR_ALLOC; }
+        G.plan_key = pp; G.plan_max = max; G.plan_mtr = mtr; G.plan_fp64 = G.opt_fp64_tail;
+    }
+    if ((nerr = tspws_b200_plan_stack(G.plan, G.d_x, G.d_out, G.d_out + max, st))) goto cuda_fail;
+    if (cudaMemcpyAsync(out->ls, G.d_out, (size_t)max * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) goto cuda_fail;
+    if (cudaMemcpyAsync(out->tsPWS, G.d_out + max, (size_t)max * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) goto cuda_fail;
+    if (G.opt_writeback && (tspws->fold || tspws->lrm))
+        if (cudaMemcpyAsync(in->sigall, G.d_x, nelem * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) goto cuda_fail;
+    if (cudaStreamSynchronize(st) != cudaSuccess) goto cuda_fail;
+
+    /* ---- convergence curves (src/ts_pws1f_lib.c:247-314) ---- */
+    if (tspws->convergence) {
+        int e = tspws_convergence_run(tspws, out, in, G.d_x, mtr, max, st);
+        if (e) return e;
+    }
+    /* ---- resampling (src/ts_pws1f_lib.c:324-345) ---- */
+    if (resampling) {
+        int e = tspws_resample_run(tspws, out, in, G.d_x, mtr, max, G.sel,
+                                   (G.sel && G.selmtr == mtr) ? G.selM : 0, st);
+        if (e) return e;
+    }
+    return 0;
+
+cuda_fail:
+    {
+        cudaError_t e = cudaGetLastError();
+        fprintf(stderr, "tspws_b200: CUDA failure in tspws_main (%s)\n", cudaGetErrorString(e));
+    }
+    return TSPWS_ERR_CUDA;
+}

@@ -1,0 +1,347 @@
+/*
+ * tspws_plan.c -- device-resident stacking plans (C host code over the CUDA runtime API).
+ *
+ * A plan owns the frame (filter bank) on the device, the work lists of the kernels and every
+ * workspace, so that a stack is a fixed sequence of kernel launches on one stream with no
+ * allocation, no host round trip and no synchronisation:
+ *
+ *   two-stage (Kmax groups, reference src/ts_pws1f_lib.c:212-222):
+ *     reduce : colsum -> [rowmean] -> finalize                  => exchange = fp64 group sums
+ *     finish : group_post(fold, fp32) -> forward(Kmax traces) -> reduce+weight -> inverse
+ *   single-stage (reference src/ts_pws1f_lib.c:209-211):
+ *     reduce : prep(fold, rm, in place) -> forward(all traces) -> reduce+weight
+ *                                                                => exchange = PS | ST sums
+ *     finish : [weight again if ranks were summed] -> inverse
+ *
+ * Between reduce and finish the exchange block may be all-reduced (sum) across ranks that hold
+ * disjoint trace shards of the same stack.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cuda_runtime_api.h>
+
+#include "tspws_internal.h"
+
+struct tspws_plan {
+    t_tsPWS      p;
+    int          N;
+    unsigned int mtr_local, mtr_total, offset;
+    int          two_stage;
+    unsigned int K;                 /* divisor of the phase stack: Kmax or mtr_total */
+    int          acc64;             /* transforms in fp64                            */
+    size_t       csz;               /* sizeof(complex of the transform type)         */
+    tspws_frame_t    *fr;
+    tspws_devframe_t  dev;
+    tspws_weight_t    rule, *d_rule;
+    /* two-stage */
+    int    ncs, rowpart_ld, rowpart_n;
+    tspws_csum_item_t *d_cs;
+    int    *d_slot_off, *d_grp_t0;
+    double *d_part, *d_meancorr, *d_gsum;
+    float  *d_rowpart, *d_gsum32;
+    /* forward / weights / inverse */
+    int    chunk, nchunk, ntr_fwd;
+    void  *d_pps, *d_pst, *d_exch, *d_zout, *d_invscratch;
+    int    summed_across_ranks;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "tspws_b200: CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    goto fail; } } while (0)
+
+static long env_long(const char *name, long dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atol(v) : dflt;
+}
+
+static int pow2_floor(int v) { int r = 1; while (2 * r <= v) r *= 2; return r; }
+
+/* ---- device frame: scale records, filters (fp32 [+fp64]), forward items, inverse groups ---- */
+static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64)
+{
+    memset(d, 0, sizeof(*d));
+    const int S = (int)f->S;
+    d->S = S; d->N = (int)f->N; d->ncoef = (int)f->ncoef; d->ntaps = (int)f->ntaps;
+    tspws_scale_t    *sc    = (tspws_scale_t *)calloc(S ? S : 1, sizeof(*sc));
+    float            *w32   = (float *)malloc((f->ntaps ? f->ntaps : 1) * 2 * sizeof(float));
+    tspws_fwd_item_t *items = NULL;
+    tspws_inv_group_t *grp  = NULL;
+    int nitems = 0, ok = 0;
+    if (!sc || !w32) goto done;
+
+    const long work = env_long("TSPWS_FWD_WORK", 4096);    /* taps x coefficients per warp item */
+    for (int pass = 0; pass < 2; pass++) {
+        nitems = 0;
+        for (int s = 0; s < S; s++) {
+            const int L = (int)f->L[s], Ns = (int)f->Ns[s];
+            int G = pow2_floor(L / 8 > 0 ? L / 8 : 1);
+            if (G > 32) G = 32;
+            const int opp = 32 / G;
+            long run = work / L;
+            run -= run % opp;
+            if (run < opp) run = opp;
+            if (!pass) {
+                sc[s].L = L; sc[s].c = f->center[s]; sc[s].D = (int)f->D[s]; sc[s].Ns = Ns;
+                sc[s].coef_off = (int)f->coef_off[s]; sc[s].tap_off = (int)f->tap_off[s];
+                sc[s].G = G;
+                sc[s].gain = log(2.) / (2 * f->Cpsi * f->V * f->scale[s]) * (double)f->D[s];
+            }
+            for (int m0 = 0; m0 < Ns; m0 += (int)run) {
+                if (pass) {
+                    items[nitems].s = s; items[nitems].m0 = m0;
+                    items[nitems].nout = (Ns - m0 < run) ? Ns - m0 : (int)run;
+                }
+                nitems++;
+            }
+        }
+        if (!pass) {
+            items = (tspws_fwd_item_t *)calloc(nitems ? nitems : 1, sizeof(*items));
+            if (!items) goto done;
+        }
+    }
+    for (size_t i = 0; i < 2 * f->ntaps; i++) w32[i] = (float)f->w[i];
+
+    /* inverse: split the scales into groups of about equal taps per output sample */
+    {
+        int want = (int)env_long("TSPWS_INV_GROUPS", 8);
+        if (want > S) want = S;
+        if (want < 1) want = 1;
+        grp = (tspws_inv_group_t *)calloc(want, sizeof(*grp));
+        if (!grp) goto done;
+        double total = 0, cum = 0;
+        for (int s = 0; s < S; s++) total += ceil((double)f->L[s] / f->D[s]);
+        int ng = 0, prev = -1;
+        for (int s = 0; s < S; s++) {
+            int gi = total > 0 ? (int)(cum / total * want) : 0;
+            if (gi >= want) gi = want - 1;
+            if (gi != prev) { grp[ng].s0 = s; ng++; prev = gi; }
+            grp[ng - 1].s1 = s + 1;
+            cum += ceil((double)f->L[s] / f->D[s]);
+        }
+        d->ninv = ng;
+    }
+
+    if (cudaMalloc((void **)&d->d_scale, (S ? S : 1) * sizeof(*sc)) != cudaSuccess) goto done;
+    if (cudaMalloc(&d->d_w32, (f->ntaps ? f->ntaps : 1) * 2 * sizeof(float)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&d->d_items, (nitems ? nitems : 1) * sizeof(*items)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&d->d_invgrp, (d->ninv ? d->ninv : 1) * sizeof(*grp)) != cudaSuccess) goto done;
+    if (cudaMemcpy(d->d_scale, sc, S * sizeof(*sc), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMemcpy(d->d_w32, w32, f->ntaps * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMemcpy(d->d_items, items, nitems * sizeof(*items), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMemcpy(d->d_invgrp, grp, d->ninv * sizeof(*grp), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (want64) {
+        if (cudaMalloc(&d->d_w64, (f->ntaps ? f->ntaps : 1) * 2 * sizeof(double)) != cudaSuccess) goto done;
+        if (cudaMemcpy(d->d_w64, f->w, f->ntaps * 2 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    }
+    d->nitems = nitems;
+    ok = 1;
+done:
+    free(sc); free(w32); free(items); free(grp);
+    return ok ? 0 : -1;
+}
+
+static void devframe_free(tspws_devframe_t *d)
+{
+    cudaFree(d->d_scale); cudaFree(d->d_w32); cudaFree(d->d_w64);
+    cudaFree(d->d_items); cudaFree(d->d_invgrp);
+    memset(d, 0, sizeof(*d));
+}
+
+/* group of global trace itr: reference src/ts_pws1f_lib.c:876 (unsigned product, double division) */
+static unsigned int group_of(unsigned int itr, unsigned int K, unsigned int mtr)
+{
+    return (unsigned int)floor((double)(itr * K) / (double)mtr);
+}
+
+/* ---- two-stage work lists ---- */
+static int twostage_build(tspws_plan_t *pl)
+{
+    const unsigned int K = pl->K, n = pl->mtr_local;
+    const int ntiles = (pl->N + 1023) / 1024;
+    int target_items = (int)(env_long("TSPWS_CS_CTAS", 148 * 8 * 2) / ntiles);
+    if (target_items < 1) target_items = 1;
+    int chunk = (int)((n + target_items - 1) / target_items);
+    if (chunk < 8) chunk = 8;
+
+    int *grp_t0   = (int *)calloc(K + 1, sizeof(int));
+    int *slot_off = (int *)calloc(K + 1, sizeof(int));
+    tspws_csum_item_t *it = (tspws_csum_item_t *)calloc((size_t)n / chunk + 2 * K + 2, sizeof(*it));
+    int ni = 0, rc = -1;
+    if (!grp_t0 || !slot_off || !it) goto done;
+    {
+        unsigned int t = 0;
+        for (unsigned int g = 0; g < K; g++) {
+            grp_t0[g] = (int)t;
+            slot_off[g] = ni;
+            while (t < n && group_of(pl->offset + t, K, pl->mtr_total) == g) t++;
+            for (int a = grp_t0[g]; a < (int)t; a += chunk) {
+                it[ni].t0 = a; it[ni].t1 = (a + chunk < (int)t) ? a + chunk : (int)t;
+                it[ni].group = (int)g; it[ni].slot = ni;
+                ni++;
+            }
+        }
+        grp_t0[K] = (int)t; slot_off[K] = ni;
+        if (t != n) { fprintf(stderr, "tspws_b200: internal error, group runs do not cover the shard\n"); goto done; }
+    }
+    pl->ncs = ni;
+    pl->rowpart_n  = ntiles * 8;
+    pl->rowpart_ld = pl->rowpart_n;
+    const size_t N = (size_t)pl->N;
+    if (cudaMalloc((void **)&pl->d_cs, (ni ? ni : 1) * sizeof(*it)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_slot_off, (K + 1) * sizeof(int)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_grp_t0, (K + 1) * sizeof(int)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_part, (ni ? ni : 1) * N * sizeof(double)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_meancorr, K * sizeof(double)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_gsum, K * N * sizeof(double)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_gsum32, K * N * sizeof(float)) != cudaSuccess) goto done;
+    if (pl->p.lrm && cudaMalloc((void **)&pl->d_rowpart, (size_t)(n ? n : 1) * pl->rowpart_ld * sizeof(float)) != cudaSuccess) goto done;
+    if (cudaMemcpy(pl->d_cs, it, ni * sizeof(*it), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMemcpy(pl->d_slot_off, slot_off, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMemcpy(pl->d_grp_t0, grp_t0, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    rc = 0;
+done:
+    free(grp_t0); free(slot_off); free(it);
+    return rc;
+}
+
+void tspws_b200_plan_destroy(tspws_plan_t *pl)
+{
+    if (!pl) return;
+    devframe_free(&pl->dev);
+    cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
+    cudaFree(pl->d_part); cudaFree(pl->d_meancorr); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
+    cudaFree(pl->d_rowpart); cudaFree(pl->d_pps); cudaFree(pl->d_pst); cudaFree(pl->d_exch);
+    cudaFree(pl->d_zout); cudaFree(pl->d_invscratch);
+    tspws_b200_frame_destroy(pl->fr);
+    free(pl);
+}
+
+tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr_local,
+                                     unsigned int mtr_total, unsigned int trace_offset)
+{
+    if (!p || max <= 0 || !mtr_total || mtr_local > mtr_total) return NULL;
+    tspws_plan_t *pl = (tspws_plan_t *)calloc(1, sizeof(*pl));
+    if (!pl) return NULL;
+    pl->p = *p; pl->N = max;
+    pl->mtr_local = mtr_local; pl->mtr_total = mtr_total; pl->offset = trace_offset;
+    pl->two_stage = (p->Kmax && p->Kmax <= mtr_total);            /* src/ts_pws1f_lib.c:209 */
+    pl->K     = pl->two_stage ? p->Kmax : mtr_total;
+    pl->acc64 = pl->two_stage && tspws_b200_get_option(TSPWS_OPT_FP64_TAIL) != 0;
+    pl->csz   = pl->acc64 ? 2 * sizeof(double) : 2 * sizeof(float);
+    pl->rule  = tspws_weight_rule(p->wu, p->unbiased, pl->K, mtr_total);
+
+    pl->fr = tspws_b200_frame_create(p->type, p->J, p->V, (unsigned int)max, p->s0, p->b0, p->w0, (int)p->uni);
+    if (!pl->fr) { fprintf(stderr, "tspws_b200: cannot build the wavelet frame\n"); free(pl); return NULL; }
+    for (unsigned int s = 0; s < pl->fr->S; s++)
+        if (pl->fr->L[s] > (unsigned int)max) goto fail;          /* cannot happen: L is capped at N */
+    if (devframe_build(&pl->dev, pl->fr, pl->acc64)) goto fail;
+
+    CK(cudaMalloc((void **)&pl->d_rule, sizeof(tspws_weight_t)));
+    CK(cudaMemcpy(pl->d_rule, &pl->rule, sizeof(tspws_weight_t), cudaMemcpyHostToDevice));
+
+    const size_t ncoef = pl->fr->ncoef ? pl->fr->ncoef : 1;
+    if (pl->two_stage) {
+        if (twostage_build(pl)) goto fail;
+        pl->ntr_fwd = (int)pl->K;
+        pl->chunk   = (int)env_long("TSPWS_TAIL_CHUNK", 2);
+    } else {
+        pl->ntr_fwd = (int)mtr_local;
+        long c = env_long("TSPWS_FWD_CHUNK", 0);
+        if (c <= 0) { c = (mtr_local + 127) / 128; if (c < 4) c = 4; }
+        pl->chunk = (int)c;
+    }
+    if (pl->chunk < 1) pl->chunk = 1;
+    pl->nchunk = (pl->ntr_fwd + pl->chunk - 1) / pl->chunk;
+    if (pl->nchunk < 1) pl->nchunk = 1;
+    CK(cudaMalloc(&pl->d_pps, (size_t)pl->nchunk * ncoef * pl->csz));
+    CK(cudaMalloc(&pl->d_pst, (size_t)pl->nchunk * ncoef * pl->csz));
+    CK(cudaMalloc(&pl->d_exch, 2 * ncoef * pl->csz));
+    CK(cudaMalloc(&pl->d_zout, ncoef * pl->csz));
+    CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.ninv ? pl->dev.ninv : 1) * max * (pl->csz / 2)));
+    CK(cudaMemset(pl->d_exch, 0, 2 * ncoef * pl->csz));
+    return pl;
+fail:
+    tspws_b200_plan_destroy(pl);
+    return NULL;
+}
+
+static void *plan_ps(tspws_plan_t *pl) { return pl->d_exch; }
+static void *plan_st(tspws_plan_t *pl) { return (char *)pl->d_exch + (size_t)pl->fr->ncoef * pl->csz; }
+
+int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
+{
+    if (!pl || (!d_sigall && pl->mtr_local)) return TSPWS_ERR_NULL;
+    int e;
+    pl->summed_across_ranks = 0;
+    if (pl->two_stage) {
+        if ((e = tspws_cu_colsum(d_sigall, pl->N, pl->d_cs, pl->ncs, pl->d_part,
+                                 pl->p.lrm ? pl->d_rowpart : NULL, pl->rowpart_ld, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_colsum_finalize(pl->d_part, pl->d_slot_off, (int)pl->K, pl->N,
+                                          pl->p.lrm ? pl->d_rowpart : NULL, pl->rowpart_ld, pl->rowpart_n,
+                                          pl->d_grp_t0, pl->d_meancorr, pl->d_gsum, stream))) return TSPWS_ERR_CUDA;
+        return 0;
+    }
+    if ((e = tspws_cu_prep(d_sigall, (int)pl->mtr_local, pl->N, pl->p.fold, pl->p.lrm, stream))) return TSPWS_ERR_CUDA;
+    if ((e = tspws_cu_forward(&pl->dev, d_sigall, 0, 0, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+    if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, 0, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
+                                    plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+    return 0;
+}
+
+void *tspws_b200_plan_exchange_ptr(tspws_plan_t *pl)
+{
+    if (!pl) return NULL;
+    pl->summed_across_ranks = 1;          /* the caller is about to all-reduce it */
+    return pl->two_stage ? (void *)pl->d_gsum : pl->d_exch;
+}
+size_t tspws_b200_plan_exchange_bytes(tspws_plan_t *pl)
+{
+    if (!pl) return 0;
+    return pl->two_stage ? (size_t)pl->K * pl->N * sizeof(double) : 2 * pl->fr->ncoef * pl->csz;
+}
+int tspws_b200_plan_exchange_is_f64(tspws_plan_t *pl) { return pl && pl->two_stage; }
+
+int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *stream)
+{
+    if (!pl || !d_ls || !d_tspws) return TSPWS_ERR_NULL;
+    int e;
+    if (pl->two_stage) {
+        if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, (int)pl->K, pl->N, pl->p.fold, stream))) return TSPWS_ERR_CUDA;
+        const void *x = pl->acc64 ? (const void *)pl->d_gsum : (const void *)pl->d_gsum32;
+        if ((e = tspws_cu_forward(&pl->dev, x, pl->acc64, pl->acc64, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, pl->acc64, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
+                                        plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+    } else if (pl->summed_across_ranks) {
+        if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), 0, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+    }
+    if ((e = tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), pl->acc64, 1, pl->d_rule, pl->d_invscratch,
+                              d_tspws, d_ls, stream))) return TSPWS_ERR_CUDA;
+    return 0;
+}
+
+int tspws_b200_plan_stack(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
+{
+    int e = tspws_b200_plan_reduce(pl, d_sigall, stream);
+    if (e) return e;
+    return tspws_b200_plan_finish(pl, d_ls, d_tspws, stream);
+}
+
+int tspws_b200_plan_stacks_ptr(tspws_plan_t *pl, const void **d_st, const void **d_ps, unsigned int *K, int *is_f64)
+{
+    if (!pl) return TSPWS_ERR_NULL;
+    if (d_st) *d_st = plan_st(pl);
+    if (d_ps) *d_ps = plan_ps(pl);
+    if (K) *K = pl->K;
+    if (is_f64) *is_f64 = pl->acc64;
+    return 0;
+}
+
+size_t tspws_b200_plan_ncoef(tspws_plan_t *pl) { return pl ? pl->fr->ncoef : 0; }
+
+/* internal accessors used by tspws_main.c */
+const tspws_frame_t *tspws_plan_frame(tspws_plan_t *pl) { return pl->fr; }
+const tspws_devframe_t *tspws_plan_devframe(tspws_plan_t *pl) { return &pl->dev; }
