@@ -216,6 +216,10 @@ int tspws_b200_plan_stack(tspws_plan_t *plan, float *d_sigall, float *d_ls, floa
 int tspws_b200_plan_stacks_ptr(tspws_plan_t *plan, const void **d_st, const void **d_ps,
                                unsigned int *K, int *is_f64);
 size_t tspws_b200_plan_ncoef(tspws_plan_t *plan);
+/* Host copies (double, interleaved re,im, [2*ncoef]) of the last ST / PS of a plan (either may
+ * be NULL); returns ncoef.  K = divisor of the coherence |PS|/K. */
+long tspws_b200_plan_get_stacks(tspws_plan_t *plan, double *st, double *ps, size_t ncoef);
+unsigned int tspws_b200_plan_K(tspws_plan_t *plan);
 
 /* ------------------------------------------------------------------------- */
 /* ABI checks against the reference layout (probed with the reference header) */

@@ -19,6 +19,7 @@ CASES = {
                                               params=dict(type=-3, Kmax=10, unbiased=1, lrm=1, fold=1)),
     "morlet_two_stage_unbiased_64x4096": dict(mtr=64, n=4096, dt=1.0, seed=6,
                                               params=dict(Kmax=10, unbiased=1, lrm=1)),
+    "morlet_two_stage_plain_48x2048": dict(mtr=48, n=2048, dt=1.0, seed=22, params=dict(Kmax=6, unbiased=1)),
     "morlet_two_stage_biased_37x1024": dict(mtr=37, n=1024, dt=1.0, seed=7, params=dict(Kmax=7, fold=1)),
     # example.sh configurations 2 and 3 in miniature: odd N, dt=4, fmin -> s0=7.89, D = 7/15/31
     "fmin_J3_oddN_25x1501": dict(mtr=25, n=1501, dt=4.0, seed=8, params=dict(fmin=0.004, J=3, lrm=1, fold=1)),

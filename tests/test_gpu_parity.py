@@ -53,16 +53,55 @@ def test_main_stack_matches_reference_golden(pkg, gpu_lib, name):
 
 @pytest.mark.parametrize("fp64_tail", [0, 1])
 def test_two_stage_fp64_tail_option(pkg, gpu_lib, fp64_tail):
-    case = CS.CASES["morlet_two_stage_unbiased_64x4096"]
-    g = np.load(os.path.join(GOLD, "morlet_two_stage_unbiased_64x4096.npz"))
+    """TSPWS_OPT_FP64_TAIL runs the Kmax transforms in double like the reference does."""
+    name = "morlet_two_stage_plain_48x2048"
+    case = CS.CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
     gpu_lib.tspws_b200_set_option(pkg.OPT_FP64_TAIL, fp64_tail)
     try:
         r = gpu_run(pkg, gpu_lib, CS.make_input(case), **case["params"])
     finally:
         gpu_lib.tspws_b200_set_option(pkg.OPT_FP64_TAIL, 0)
-    tol = 1e-9 if fp64_tail else TOL_COH
-    assert O.nerr(r["coherence"], np.abs(g["ps"]) / int(g["K"])) <= tol
+    assert O.nerr(r["coherence"], np.abs(g["ps"]) / int(g["K"])) <= (1e-11 if fp64_tail else TOL_COH)
+    assert O.nerr(r["st"], g["st"]) <= (1e-12 if fp64_tail else TOL_STACK)
     assert O.nerr(r["tsPWS"], g["tsPWS"]) <= (2e-7 if fp64_tail else TOL_STACK)
+
+
+def _plan_stack(pkg, lib, x, mtr_total=None, offset=0, **params):
+    """Device-resident plan API on torch memory: returns ls, tsPWS, coherence."""
+    import torch
+    p = pkg.default_params(**params)
+    n = x.shape[1]
+    lib.tspws_b200_derive_params(C.byref(p), n, 1.0)
+    dx = torch.from_numpy(x).cuda()
+    ls = torch.empty(n, device="cuda")
+    ts = torch.empty(n, device="cuda")
+    plan = lib.tspws_b200_plan_create(C.byref(p), n, x.shape[0], mtr_total or x.shape[0], offset)
+    assert plan
+    try:
+        stream = torch.cuda.current_stream().cuda_stream
+        assert lib.tspws_b200_plan_stack(plan, dx.data_ptr(), ls.data_ptr(), ts.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
+        nc = lib.tspws_b200_plan_ncoef(plan)
+        ps = np.empty(2 * nc)
+        assert lib.tspws_b200_plan_get_stacks(plan, None, ps.ctypes.data_as(C.POINTER(C.c_double)), nc) == nc
+        coh = np.hypot(ps[0::2], ps[1::2]) / lib.tspws_b200_plan_K(plan)
+        return ls.cpu().numpy(), ts.cpu().numpy(), coh
+    finally:
+        lib.tspws_b200_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("kw", [dict(Kmax=10, unbiased=1, lrm=1, fold=1), dict(Kmax=10, unbiased=1, lrm=1),
+                                dict(type=-3, Kmax=8, fold=1), dict(lrm=1, fold=1)])
+def test_device_plan_api_fused_mean_and_fold(pkg, gpu_lib, kw):
+    """The device-resident API de-means / folds the Kmax group sums instead of every trace
+    (linear, so equal up to fp32 rounding of the reference's per-sample subtraction)."""
+    x = O.synthetic_traces(200, 2048, seed=31) + np.float32(0.25)      # non-zero mean on purpose
+    ls, ts, coh = _plan_stack(pkg, gpu_lib, x, **kw)
+    o = O.tspws_main(O.Params(**kw), x)
+    assert O.nerr(coh, o["coherence"]) <= TOL_COH
+    assert O.nerr(ls, o["ls"]) <= TOL_STACK
+    assert O.nerr(ts, o["tsPWS"]) <= TOL_STACK
 
 
 def test_medium_single_stage_vs_oracle(pkg, gpu_lib):

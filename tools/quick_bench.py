@@ -2,8 +2,11 @@
 import ctypes as C, sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from tests.conftest import load_pkg
-B = load_pkg(); lib = B.load_library()
+import importlib.util
+_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_spec = importlib.util.spec_from_file_location("ts_pws_b200", os.path.join(_root, "ts-pws_b200", "__init__.py"))
+B = importlib.util.module_from_spec(_spec); sys.modules["ts_pws_b200"] = B; _spec.loader.exec_module(B)
+lib = B.load_library()
 
 def run(name, mtr, n, reps=5, **kw):
     p = B.default_params(**kw)

@@ -161,6 +161,10 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_plan_stacks_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_void_p), C.POINTER(C.c_uint),
                                                C.POINTER(C.c_int)]
+    lib.tspws_b200_plan_get_stacks.restype = C.c_long
+    lib.tspws_b200_plan_get_stacks.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_size_t]
+    lib.tspws_b200_plan_K.restype = C.c_uint
+    lib.tspws_b200_plan_K.argtypes = [C.c_void_p]
     lib.tspws_b200_plan_ncoef.restype = C.c_size_t
     lib.tspws_b200_plan_ncoef.argtypes = [C.c_void_p]
     return lib
@@ -174,7 +178,7 @@ EXPORTS = [
     "tspws_b200_kernel_launches", "tspws_b200_plan_create", "tspws_b200_plan_destroy",
     "tspws_b200_plan_reduce", "tspws_b200_plan_exchange_ptr", "tspws_b200_plan_exchange_bytes",
     "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
-    "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef",
+    "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",
 ]
 
 

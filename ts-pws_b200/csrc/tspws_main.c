@@ -139,24 +139,7 @@ static int same_plan_key(const t_tsPWS *a, const t_tsPWS *b)
 
 long tspws_b200_get_stacks(double *st, double *ps, size_t ncoef)
 {
-    if (!G.plan) return TSPWS_ERR_NULL;
-    const size_t n = tspws_b200_plan_ncoef(G.plan);
-    if (!st && !ps) return (long)n;
-    if (ncoef < n) return TSPWS_ERR_ARG;
-    const void *d_st, *d_ps; unsigned int K; int f64;
-    tspws_b200_plan_stacks_ptr(G.plan, &d_st, &d_ps, &K, &f64);
-    const size_t esz = f64 ? sizeof(double) : sizeof(float);
-    void *tmp = malloc(2 * n * esz);
-    if (!tmp) return TSPWS_ERR_ALLOC;
-    for (int which = 0; which < 2; which++) {
-        double *dst = which ? ps : st;
-        if (!dst) continue;
-        if (cudaMemcpy(tmp, which ? d_ps : d_st, 2 * n * esz, cudaMemcpyDeviceToHost) != cudaSuccess) { free(tmp); return TSPWS_ERR_CUDA; }
-        if (f64) memcpy(dst, tmp, 2 * n * sizeof(double));
-        else for (size_t i = 0; i < 2 * n; i++) dst[i] = (double)((float *)tmp)[i];
-    }
-    free(tmp);
-    return (long)n;
+    return tspws_b200_plan_get_stacks(G.plan, st, ps, ncoef);
 }
 
 long tspws_b200_get_coherence(double *coh, size_t ncap)
@@ -169,8 +152,7 @@ long tspws_b200_get_coherence(double *coh, size_t ncap)
     if (!ps) return TSPWS_ERR_ALLOC;
     long rc = tspws_b200_get_stacks(NULL, ps, n);
     if (rc >= 0) {
-        unsigned int K = 1;
-        tspws_b200_plan_stacks_ptr(G.plan, NULL, NULL, &K, NULL);
+        const unsigned int K = tspws_b200_plan_K(G.plan);
         for (size_t i = 0; i < n; i++) coh[i] = hypot(ps[2 * i], ps[2 * i + 1]) / (double)K;
     }
     free(ps);
@@ -216,10 +198,11 @@ int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
 
     const int resampling  = (tspws->subsmpl_N > 0 && tspws->subsmpl_p > 0) || (tspws->jackknife_n > 0 && tspws->jackknife_d > 0);
     const int two_stage   = tspws->Kmax && tspws->Kmax <= mtr;
-    /* Later passes (resampling, convergence, write-back) need the cleaned traces themselves; the
-     * plain two-stage stack does not and folds / de-means its Kmax group sums instead. */
-    const int exact_prep  = two_stage && (tspws->fold || tspws->lrm) &&
-                            (resampling || tspws->convergence || G.opt_writeback);
+    /* The host path always cleans the traces themselves, bit-faithfully to the reference's fp32
+     * in-place fold / mean removal: it costs one extra pass over HBM, which is hidden behind the
+     * PCIe copy, and later passes (resampling, convergence, write-back) need the cleaned traces.
+     * (The device-resident plan API instead folds / de-means the Kmax group sums, see tspws_plan.c.) */
+    const int exact_prep  = two_stage && (tspws->fold || tspws->lrm);
     t_tsPWS pp = *tspws;
     if (exact_prep) {
         if (tspws_cu_prep(G.d_x, (int)mtr, max, tspws->fold, tspws->lrm, st)) goto cuda_fail;

@@ -342,6 +342,31 @@ int tspws_b200_plan_stacks_ptr(tspws_plan_t *pl, const void **d_st, const void *
 
 size_t tspws_b200_plan_ncoef(tspws_plan_t *pl) { return pl ? pl->fr->ncoef : 0; }
 
+/* Host copies (double, interleaved re,im) of the last ST / PS of a plan; returns ncoef. */
+long tspws_b200_plan_get_stacks(tspws_plan_t *pl, double *st, double *ps, size_t ncoef)
+{
+    if (!pl) return TSPWS_ERR_NULL;
+    const size_t n = pl->fr->ncoef;
+    if (!st && !ps) return (long)n;
+    if (ncoef < n) return TSPWS_ERR_ARG;
+    const size_t esz = pl->acc64 ? sizeof(double) : sizeof(float);
+    void *tmp = malloc(2 * n * esz + 8);
+    if (!tmp) return TSPWS_ERR_ALLOC;
+    for (int which = 0; which < 2; which++) {
+        double *dst = which ? ps : st;
+        if (!dst) continue;
+        if (cudaMemcpy(tmp, which ? plan_ps(pl) : plan_st(pl), 2 * n * esz, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            free(tmp);
+            return TSPWS_ERR_CUDA;
+        }
+        if (pl->acc64) memcpy(dst, tmp, 2 * n * sizeof(double));
+        else for (size_t i = 0; i < 2 * n; i++) dst[i] = (double)((float *)tmp)[i];
+    }
+    free(tmp);
+    return (long)n;
+}
+unsigned int tspws_b200_plan_K(tspws_plan_t *pl) { return pl ? pl->K : 0; }
+
 /* internal accessors used by tspws_main.c */
 const tspws_frame_t *tspws_plan_frame(tspws_plan_t *pl) { return pl->fr; }
 const tspws_devframe_t *tspws_plan_devframe(tspws_plan_t *pl) { return &pl->dev; }
