@@ -33,6 +33,12 @@ def run(name, mtr, n, reps=5, **kw):
     lib.tspws_b200_plan_destroy(plan)
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "ts":
+        run("two-stage morlet rm", 8192, 16384, reps=2, Kmax=10, unbiased=1, lrm=1)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ss":
+        run("single-stage morlet w0=6 (256 traces)", 256, 16384, reps=1, w0=6.0, w0set=4, lrm=1)
+        sys.exit(0)
     run("two-stage morlet rm", 8192, 16384, Kmax=10, unbiased=1, lrm=1)
     run("two-stage morlet", 8192, 16384, Kmax=10, unbiased=1)
     run("two-stage mexhat rm", 8192, 16384, type=-3, Kmax=10, unbiased=1, lrm=1)

@@ -21,18 +21,34 @@ typedef struct {
     int   Ns;        /* coefficients = ceil(N/D)                      */
     int   coef_off;  /* offset in a ragged coefficient array          */
     int   tap_off;   /* offset in the tap array                       */
-    int   G;         /* lanes cooperating on one coefficient (pow2)   */
+    int   G;         /* generic kernel: lanes cooperating on one coefficient (pow2) */
+    /* polyphase (register-tiled) kernel: x[(m-A+q)D + rho] * g[qD + rho], q < Qs, rho < D */
+    int   lg;        /* log2(lanes over phases): 0..4 when D = 2^lg < 32, 5 when D >= 32, -1: generic kernel */
+    int   A;         /* ceil(c / D)                                   */
+    int   Qs;        /* taps per phase = ceil((A*D - c + L) / D)      */
+    int   g_off;     /* offset of the padded conjugated filter g      */
+    int   nsplit;    /* partial-Y slots (phase splits) in per-trace mode */
+    int   ypart_off; /* offset of this scale in the partial-Y scratch (per unit of K traces) */
     int   pad;
     double gain;     /* synthesis gain ln2/(2 Cpsi V scale) * D       */
 } tspws_scale_t;
 
-/* ---- forward-transform work item: a run of coefficients of one scale ---- */
+/* ---- forward-transform work item of the generic kernel: a run of coefficients of one scale ---- */
 typedef struct {
     int s;           /* scale                           */
     int m0;          /* first coefficient of the run    */
     int nout;        /* coefficients in the run         */
     int pad;
 } tspws_fwd_item_t;
+
+/* ---- work item of the polyphase kernel: one warp, one register tile ---- */
+typedef struct {
+    int s;           /* scale                                              */
+    int m0;          /* first coefficient                                  */
+    int pb0, pb1;    /* blocks of 32 phases [pb0,pb1) (D >= 32), else 0,1  */
+    int split;       /* partial-Y slot written in per-trace mode           */
+    int pad[3];
+} tspws_fwd2_item_t;
 
 /* ---- inverse-transform work split: scales [s0,s1) ---- */
 typedef struct { int s0, s1; } tspws_inv_group_t;
@@ -50,8 +66,18 @@ typedef struct {
     tspws_scale_t     *d_scale;   /* [S]            */
     void              *d_w32;     /* float2[ntaps]  */
     void              *d_w64;     /* double2[ntaps] (NULL unless the fp64 tail is enabled) */
-    tspws_fwd_item_t  *d_items;   /* [nitems]       */
+    void              *d_g32;     /* float2[ng]: conjugated, phase-padded filters of the polyphase kernel */
+    tspws_fwd_item_t  *d_items;   /* [nitems]  generic kernel: all scales   */
     int                nitems;
+    tspws_fwd_item_t  *d_items_gen; /* [nitems_gen] generic kernel: only scales with lg < 0 */
+    int                nitems_gen;
+    tspws_fwd2_item_t *d_items2;  /* [nitems2] polyphase kernel              */
+    int                nitems2;
+    int                fw_lg_begin[7]; /* items2 are sorted by lg: items of lg are [begin[lg], begin[lg+1]) */
+    int                fw_smem_per_warp; /* floats of warp-private staging smem of the polyphase kernel */
+    int                per_trace; /* item list built for per-trace (partial-Y) mode */
+    int                ypart_len; /* partial-Y scratch length per trace (complex)   */
+    int                max_Ns;
     tspws_inv_group_t *d_invgrp;  /* [ninv]         */
     int                ninv;
 } tspws_devframe_t;
@@ -90,16 +116,30 @@ int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t *d_items, i
 int tspws_cu_colsum_finalize(const double *d_part, const int *d_slot_off /*[G+1]*/, int G, int N,
                              const float *d_rowpart, int rowpart_ld, int rowpart_n,
                              const int *d_grp_t0 /*[G+1] local trace range of each group*/,
-                             double *d_meancorr /*[G] scratch*/, double *d_gsum /*[G][N]*/,
+                             int ntr, float *d_mean /*[ntr] scratch*/, double *d_gsum /*[G][N]*/,
                              tspws_stream_t st);
 /* Fold the group sums (linear) and emit the fp32 copy read by the fp32 transform. */
 int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N, int do_fold, tspws_stream_t st);
 
-/* Forward frame transform + phasor / linear accumulation over chunks of traces.
+/* Forward frame transform + phasor / linear accumulation over chunks of traces (generic kernel,
+ * any geometry, float or double).
  *   x: [ntr][N] (float, or double when in64), chunk c covers traces [c*chunk, min(ntr,(c+1)*chunk))
  *   part_ps / part_st: [nchunk][ncoef] complex (float2, or double2 when acc64). */
 int tspws_cu_forward(const tspws_devframe_t *f, const void *d_x, int in64, int acc64,
                      int ntr, int chunk, void *d_part_ps, void *d_part_st, tspws_stream_t st);
+/* fp32 fast path: polyphase register-tiled kernel for the scales it covers + generic kernel for the
+ * rest.  Chunk-accumulate mode (f->per_trace == 0): same outputs as tspws_cu_forward. */
+int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, int chunk,
+                          void *d_part_ps, void *d_part_st, tspws_stream_t st);
+/* Per-trace mode (f->per_trace == 1): raw coefficients of each of the ntr traces (split over
+ * phase ranges for coarse scales) go to d_ypart [f->ypart_len * ntr] complex fp32 ... */
+int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, void *d_ypart,
+                              tspws_stream_t st);
+/* ... and are combined here: for segment g (ntr = nseg*seg traces), PS = sum phasor(Y), ST = sum Y,
+ * Zout = ST * weight(PS).  Outputs [nseg][ncoef] complex fp32. */
+int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_ypart, int nseg, int seg,
+                            const tspws_weight_t *d_rules, void *d_ps, void *d_st, void *d_zout,
+                            tspws_stream_t st);
 /* Sum the chunk partials in segments of `seg` chunks -> PS, ST per segment, and the weighted
  * coefficients Zout = ST * weight(PS).  nseg segments; outputs [nseg][ncoef] complex. */
 int tspws_cu_reduce_weight(const void *d_part_ps, const void *d_part_st, int acc64, int ncoef,

@@ -196,53 +196,56 @@ extern "C" int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t 
     return 0;
 }
 
-/* Mean correction of each group: sum over its traces of (double)(float)(rowsum/N)
- * (the reference subtracts the float-cast mean from every sample, src/ts_pws1f_lib.c:166-167;
- * the sum of those subtractions over a group is this constant).  grid = groups. */
+/* Per-trace mean, float-cast like the reference (src/ts_pws1f_lib.c:165-166): one warp per trace
+ * sums the row partials left by colsum_kernel. */
 __global__ void __launch_bounds__(256)
-rowmean_kernel(const float *__restrict__ rowpart, int rowpart_ld, int rowpart_n,
-               const int *__restrict__ grp_t0 /*[G+1] local trace ranges*/, int N,
-               double *__restrict__ meancorr)
+rowmean_kernel(const float *__restrict__ rowpart, int rowpart_ld, int rowpart_n, int ntr, int N,
+               float *__restrict__ mean)
 {
-    __shared__ double sh[33];
-    const int g = blockIdx.x;
-    double acc = 0.0;
-    for (int t = grp_t0[g] + threadIdx.x; t < grp_t0[g + 1]; t += blockDim.x) {
-        const float *r = rowpart + (size_t)t * rowpart_ld;
-        double s = 0.0;
-        for (int j = 0; j < rowpart_n; j++) s += (double)r[j];
-        acc += (double)(float)(s / (double)(unsigned int)N);
-    }
-    acc = block_sum(acc, sh);
-    if (threadIdx.x == 0) meancorr[g] = acc;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= ntr) return;
+    const float *r = rowpart + (size_t)t * rowpart_ld;
+    double s = 0.0;
+    for (int j = threadIdx.x & 31; j < rowpart_n; j += 32) s += (double)r[j];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) mean[t] = (float)(s / (double)(unsigned int)N);
 }
 
-/* gsum[g][n] = sum over the group's partial slots - meancorr[g]. grid = (n tiles, G). */
+/* gsum[g][n] = sum over the group's partial slots - sum over the group's traces of their mean
+ * (the reference subtracts the float-cast mean from every sample, :167; summed over a group that
+ * is this constant).  grid = (n tiles, G). */
 __global__ void __launch_bounds__(256)
 colsum_finalize_kernel(const double *__restrict__ part, const int *__restrict__ slot_off, int N,
-                       const double *__restrict__ meancorr, double *__restrict__ gsum)
+                       const float *__restrict__ mean, const int *__restrict__ grp_t0,
+                       double *__restrict__ gsum)
 {
+    __shared__ double sh[33];
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
+    double corr = 0.0;
+    if (mean) {
+        double m = 0.0;
+        for (int t = grp_t0[g] + threadIdx.x; t < grp_t0[g + 1]; t += blockDim.x) m += (double)mean[t];
+        corr = block_sum(m, sh);
+    }
     if (n >= N) return;
     double a = 0.0;
     for (int s = slot_off[g]; s < slot_off[g + 1]; s++) a += part[(size_t)s * N + n];
-    if (meancorr) a -= meancorr[g];
-    gsum[(size_t)g * N + n] = a;
+    gsum[(size_t)g * N + n] = a - corr;
 }
 
 extern "C" int tspws_cu_colsum_finalize(const double *d_part, const int *d_slot_off, int G, int N,
                                         const float *d_rowpart, int rowpart_ld, int rowpart_n,
-                                        const int *d_grp_t0, double *d_meancorr, double *d_gsum,
+                                        const int *d_grp_t0, int ntr, float *d_mean, double *d_gsum,
                                         tspws_stream_t st)
 {
     cudaStream_t s = (cudaStream_t)st;
-    if (d_rowpart) {
-        rowmean_kernel<<<G, 256, 0, s>>>(d_rowpart, rowpart_ld, rowpart_n, d_grp_t0, N, d_meancorr);
+    if (d_rowpart && ntr > 0) {
+        rowmean_kernel<<<(ntr + 7) / 8, 256, 0, s>>>(d_rowpart, rowpart_ld, rowpart_n, ntr, N, d_mean);
         TSPWS_LAUNCHED();
     }
     dim3 grid((N + 255) / 256, G);
-    colsum_finalize_kernel<<<grid, 256, 0, s>>>(d_part, d_slot_off, N, d_rowpart ? d_meancorr : nullptr, d_gsum);
+    colsum_finalize_kernel<<<grid, 256, 0, s>>>(d_part, d_slot_off, N, d_rowpart ? d_mean : nullptr, d_grp_t0, d_gsum);
     TSPWS_LAUNCHED();
     return 0;
 }
@@ -399,6 +402,373 @@ extern "C" int tspws_cu_forward(const tspws_devframe_t *f, const void *d_x, int 
 }
 
 /* ===================================================================================== */
+/* polyphase register-tiled forward transform (fp32 fast path)                           */
+/*                                                                                       */
+/*   With c = A D - e (0 <= e < D) and the conjugated filter padded by e leading zeros,  */
+/*   g[t] = conj(w[t - e]):                                                              */
+/*       Y[m] = sum_{rho<D} sum_{q<Qs} x[((m - A + q) D + rho) mod N] * g[q D + rho]     */
+/*   i.e. D short correlations (Qs ~ 11..19 taps) of the polyphase components of x.      */
+/*   A lane owns one phase rho and FW_R = 16 consecutive coefficients: it slides a       */
+/*   register window of R+Qs-1 samples (stride D) past Qs filter taps -> 2 R Qs FMAs for */
+/*   R+Qs-1 + Qs loads.  Lanes of a warp cover                                           */
+/*     D = 2^lg < 32 : D phases x 32/D coefficient tiles; x is staged in (skewed,        */
+/*                     bank-conflict-free) shared memory, warp-private;                  */
+/*     D >= 32       : 32 consecutive phases of one tile; x is read from global/L1       */
+/*                     (consecutive lanes = consecutive samples), looping over blocks of */
+/*                     32 phases.                                                        */
+/*   The per-lane partial sums (over phases) are combined with a transposing butterfly   */
+/*   (log2 steps, halving the live values each step) that leaves every lane holding      */
+/*   complete coefficients, which go straight into the phasor epilogue.                  */
+/* ===================================================================================== */
+#define FW_R 16
+#define FW_WARPS 8
+
+__device__ __forceinline__ double weight_factor(const tspws_weight_t r, double pr, double pi);
+
+__device__ __forceinline__ void phasor_fast(float re, float im, float &pr, float &pi)
+{
+    const float s = re * re + im * im;
+    if (s > 1e-30f && s < 1e30f) {            /* no under/overflow in the square: one MUFU */
+        const float inv = rsqrtf(s);
+        pr = re * inv; pi = im * inv;
+    } else {                                  /* tiny, huge, zero or non-finite: careful path */
+        const float a = hypotf(re, im);
+        if (a > 0.f && a <= 3.0e38f) { pr = re / a; pi = im / a; }
+        else { pr = 0.f; pi = 0.f; }          /* skipped like src/ts_pws1f_lib.c:492 */
+    }
+}
+
+template <int LGR>
+__device__ __forceinline__ void lane_transpose_reduce(float (&v)[2 * FW_R], const int lane)
+{
+#pragma unroll
+    for (int b = LGR - 1; b >= 0; b--) {
+        const int  half = 16 >> (LGR - 1 - b);
+        const bool up   = (lane >> b) & 1;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            const float send = up ? v[i] : v[i + half];
+            const float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1 << b);
+        }
+    }
+}
+
+/* One pass: R coefficients x Qs taps of one phase.  LOADX(j) returns window sample j. */
+#define FW_TAPLOOP(LOADX, GPTR, GSTRIDE, ACTIVE)                                          \
+    {                                                                                     \
+        float win[2 * FW_R - 1];                                                          \
+        _Pragma("unroll")                                                                 \
+        for (int j = 0; j < FW_R - 1; j++) win[j] = LOADX(j);                             \
+        for (int qb = 0; qb < Qs; qb += FW_R) {                                           \
+            _Pragma("unroll")                                                             \
+            for (int qq = 0; qq < FW_R; qq++) {                                           \
+                if (qb + qq < Qs) {                                                       \
+                    win[qq + FW_R - 1] = LOADX(qb + qq + FW_R - 1);                       \
+                    float2 gv = make_float2(0.f, 0.f);                                    \
+                    if (ACTIVE) gv = __ldg((GPTR) + (size_t)(qb + qq) * (GSTRIDE));       \
+                    _Pragma("unroll")                                                     \
+                    for (int r = 0; r < FW_R; r++) {                                      \
+                        v[2 * r]     = fmaf(win[r + qq], gv.x, v[2 * r]);                 \
+                        v[2 * r + 1] = fmaf(win[r + qq], gv.y, v[2 * r + 1]);             \
+                    }                                                                     \
+                }                                                                         \
+            }                                                                             \
+            _Pragma("unroll")                                                             \
+            for (int j = 0; j < FW_R - 1; j++) win[j] = win[j + FW_R];                    \
+        }                                                                                 \
+    }
+
+template <int LG, bool PER_TRACE>
+__device__ __forceinline__ void
+fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__restrict__ g_all,
+          const float *__restrict__ x, const int N, const int k_begin, const int k_end,
+          const int ncoef, const int chunk_idx, float2 *__restrict__ part_ps, float2 *__restrict__ part_st,
+          float2 *__restrict__ ypart, const int ypart_len, float *xs, const int lane)
+{
+    constexpr int LGR  = LG;                       /* lane bits that index phases            */
+    constexpr int NVAL = 32 >> LGR;                /* floats of complete coefficients / lane */
+    const int D = sc.D, Qs = sc.Qs;
+    const float2 *__restrict__ g = g_all + sc.g_off;
+    float ps[NVAL], st[NVAL];
+#pragma unroll
+    for (int i = 0; i < NVAL; i++) { ps[i] = 0.f; st[i] = 0.f; }
+
+    long long b0 = ((long long)(it.m0 - sc.A) * D) % N;
+    if (b0 < 0) b0 += N;
+    const int base = (int)b0;                      /* sample of (tile 0, tap 0, phase 0)     */
+
+    for (int k = k_begin; k < k_end; k++) {
+        const float *__restrict__ xk = x + (size_t)k * N;
+        float v[2 * FW_R];
+#pragma unroll
+        for (int i = 0; i < 2 * FW_R; i++) v[i] = 0.f;
+
+        if (LG < 5) {
+            /* ---- D = 2^LG phases x (32 >> LG) tiles; stage the window in skewed smem ---- */
+            constexpr int LP = 1 << LG, TILES = 32 >> LG, PITCH = (FW_R + 1) * LP;
+            const int a = lane >> LG, rho = lane & (LP - 1);
+            const int W = (TILES * FW_R + Qs - 1) * LP;
+            __syncwarp();
+            for (int i = lane; i < W; i += 32) {
+                int pos = base + i;
+                if (pos >= N) pos -= N;
+                xs[i + (i >> (4 + LG)) * LP] = xk[pos];
+            }
+            __syncwarp();
+            const float *xw = xs + a * PITCH + rho;
+#define FW_LDS(j) xw[((j) >> 4) * PITCH + ((j) & 15) * LP]
+            FW_TAPLOOP(FW_LDS, g + rho, LP, true)
+#undef FW_LDS
+        } else {
+            /* ---- D >= 32: 32 consecutive phases per block, samples straight from global ---- */
+            for (int pb = it.pb0; pb < it.pb1; pb++) {
+                const int  rho = pb * 32 + lane;
+                const bool act = rho < D;
+                int pos0 = base + (act ? rho : 0);
+                if (pos0 >= N) pos0 -= N;
+                int pos = pos0;
+                /* window samples are consumed strictly in order j = 0,1,2,...: load, then step by D */
+#define FW_LDG(j) ({ const float t_ = xk[pos]; pos += D; if (pos >= N) pos -= N; t_; })
+                FW_TAPLOOP(FW_LDG, g + rho, D, act)
+#undef FW_LDG
+            }
+        }
+
+        lane_transpose_reduce<LGR>(v, lane);
+
+        if (NVAL >= 2) {
+            const int a = lane >> LG, rho = lane & ((1 << LG) - 1);
+            const int m_first = it.m0 + a * FW_R + (rho * NVAL) / 2;
+#pragma unroll
+            for (int i = 0; i < NVAL / 2; i++) {
+                const float re = v[2 * i], im = v[2 * i + 1];
+                if (PER_TRACE) {
+                    const int m = m_first + i;
+                    if (m < sc.Ns)
+                        ypart[(size_t)k * ypart_len + sc.ypart_off + (size_t)it.split * sc.Ns + m] = make_float2(re, im);
+                } else {
+                    float pr, pi;
+                    phasor_fast(re, im, pr, pi);
+                    ps[2 * i] += pr; ps[2 * i + 1] += pi;
+                    st[2 * i] += re; st[2 * i + 1] += im;
+                }
+            }
+        } else {
+            /* one float per lane: even lanes hold Re, odd lanes Im of coefficient lane/2 */
+            const float mine  = v[0];
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const bool  odd   = lane & 1;
+            if (PER_TRACE) {
+                const int m = it.m0 + (lane >> 1);
+                if (m < sc.Ns) {
+                    float *o = reinterpret_cast<float *>(ypart + (size_t)k * ypart_len + sc.ypart_off + (size_t)it.split * sc.Ns + m);
+                    o[odd] = mine;
+                }
+            } else {
+                float pr, pi;
+                phasor_fast(odd ? other : mine, odd ? mine : other, pr, pi);
+                ps[0] += odd ? pi : pr;
+                st[0] += mine;
+            }
+        }
+    }
+
+    if (!PER_TRACE) {
+        const size_t obase = (size_t)chunk_idx * ncoef + sc.coef_off;
+        if (NVAL >= 2) {
+            const int a = lane >> LG, rho = lane & ((1 << LG) - 1);
+            const int m_first = it.m0 + a * FW_R + (rho * NVAL) / 2;
+#pragma unroll
+            for (int i = 0; i < NVAL / 2; i++) {
+                const int m = m_first + i;
+                if (m < sc.Ns) {
+                    part_ps[obase + m] = make_float2(ps[2 * i], ps[2 * i + 1]);
+                    part_st[obase + m] = make_float2(st[2 * i], st[2 * i + 1]);
+                }
+            }
+        } else {
+            const int m = it.m0 + (lane >> 1);
+            if (m < sc.Ns) {
+                reinterpret_cast<float *>(part_ps + obase + m)[lane & 1] = ps[0];
+                reinterpret_cast<float *>(part_st + obase + m)[lane & 1] = st[0];
+            }
+        }
+    }
+}
+
+/* chunk-accumulate mode: one instantiation per LG (register budgets differ); items of that LG
+ * are [item_begin, item_end).  grid = (ceil(items / 8 warps), chunks). */
+template <int LG>
+__global__ void __launch_bounds__(FW_WARPS * 32)
+fwd2_acc_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
+                const tspws_fwd2_item_t *__restrict__ items, int item_begin, int item_end,
+                const float *__restrict__ x, int N, int ntr, int chunk, int ncoef,
+                float2 *__restrict__ part_ps, float2 *__restrict__ part_st, int smem_per_warp)
+{
+    extern __shared__ float fw_smem[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = item_begin + blockIdx.x * FW_WARPS + w;
+    if (idx >= item_end) return;
+    const tspws_fwd2_item_t it = items[idx];
+    const tspws_scale_t sc = scales[it.s];
+    const int k0 = blockIdx.y * chunk, k1 = min(ntr, k0 + chunk);
+    fwd2_body<LG, false>(sc, it, g_all, x, N, k0, k1, ncoef, blockIdx.y, part_ps, part_st, nullptr, 0,
+                         fw_smem + (size_t)w * smem_per_warp, lane);
+}
+
+/* per-trace mode: one kernel for all LG (no accumulators -> one register budget fits all).
+ * grid = (ceil(items / 8 warps), traces). */
+__global__ void __launch_bounds__(FW_WARPS * 32)
+fwd2_pertrace_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
+                     const tspws_fwd2_item_t *__restrict__ items, int nitems,
+                     const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len,
+                     int smem_per_warp)
+{
+    extern __shared__ float fw_smem[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * FW_WARPS + w;
+    if (idx >= nitems) return;
+    const tspws_fwd2_item_t it = items[idx];
+    const tspws_scale_t sc = scales[it.s];
+    const int k = blockIdx.y;
+    float *xs = fw_smem + (size_t)w * smem_per_warp;
+    switch (sc.lg) {
+    case 0: fwd2_body<0, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
+    case 1: fwd2_body<1, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
+    case 2: fwd2_body<2, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
+    case 3: fwd2_body<3, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
+    case 4: fwd2_body<4, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
+    default: fwd2_body<5, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
+    }
+}
+
+/* generic kernel in per-trace mode, for the scales the polyphase kernel does not cover */
+__global__ void __launch_bounds__(FWD_WARPS * 32)
+fwd_pertrace_generic_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ wall,
+                            const tspws_fwd_item_t *__restrict__ items, int nitems,
+                            const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len)
+{
+    const int witem = blockIdx.x * FWD_WARPS + (threadIdx.x >> 5);
+    if (witem >= nitems) return;
+    const tspws_fwd_item_t it = items[witem];
+    const tspws_scale_t sc = scales[it.s];
+    const int lane = threadIdx.x & 31;
+    const int G = sc.G, g = lane & (G - 1), og = lane / G, opp = 32 / G;
+    const float2 *__restrict__ w = wall + sc.tap_off;
+    const float *__restrict__ xk = x + (size_t)blockIdx.y * N;
+    for (int mb = 0; mb < it.nout; mb += opp) {
+        const bool valid = (mb + og) < it.nout;
+        const int  m     = it.m0 + (valid ? mb + og : it.nout - 1);
+        long long pll = ((long long)m * sc.D - sc.c + g) % N;
+        if (pll < 0) pll += N;
+        int p = (int)pll;
+        float ar = 0.f, ai = 0.f;
+#pragma unroll 4
+        for (int l = g; l < sc.L; l += G) {
+            const float2 wv = w[l];
+            const float  xv = xk[p];
+            ar = fmaf(xv, wv.x, ar);
+            ai = fmaf(-xv, wv.y, ai);
+            p += G;
+            if (p >= N) p -= N;
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, o);
+            ai += __shfl_xor_sync(0xffffffffu, ai, o);
+        }
+        if (g == 0 && valid)
+            ypart[(size_t)blockIdx.y * ypart_len + sc.ypart_off + m] = make_float2(ar, ai);
+    }
+}
+
+extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, int chunk,
+                                     void *d_part_ps, void *d_part_st, tspws_stream_t st)
+{
+    if (ntr <= 0) return 0;
+    if (f->per_trace) return (int)cudaErrorInvalidValue;
+    if (chunk < 1) chunk = 1;
+    cudaStream_t s = (cudaStream_t)st;
+    const int nchunk = (ntr + chunk - 1) / chunk;
+    const size_t smem = (size_t)f->fw_smem_per_warp * FW_WARPS * sizeof(float);
+#define FW_ACC_LAUNCH(LGV)                                                                              \
+    if (f->fw_lg_begin[LGV + 1] > f->fw_lg_begin[LGV]) {                                                \
+        const int nb = f->fw_lg_begin[LGV + 1] - f->fw_lg_begin[LGV];                                   \
+        dim3 grid((nb + FW_WARPS - 1) / FW_WARPS, nchunk);                                              \
+        if (smem > 48 * 1024)                                                                           \
+            cudaFuncSetAttribute(fwd2_acc_kernel<LGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        fwd2_acc_kernel<LGV><<<grid, FW_WARPS * 32, (LGV < 5 ? smem : 0), s>>>(f->d_scale, (const float2 *)f->d_g32, \
+            f->d_items2, f->fw_lg_begin[LGV], f->fw_lg_begin[LGV + 1], d_x, f->N, ntr, chunk, f->ncoef,  \
+            (float2 *)d_part_ps, (float2 *)d_part_st, f->fw_smem_per_warp);                              \
+        TSPWS_LAUNCHED();                                                                               \
+    }
+    FW_ACC_LAUNCH(0) FW_ACC_LAUNCH(1) FW_ACC_LAUNCH(2) FW_ACC_LAUNCH(3) FW_ACC_LAUNCH(4) FW_ACC_LAUNCH(5)
+#undef FW_ACC_LAUNCH
+    if (f->nitems_gen > 0) {
+        dim3 grid((f->nitems_gen + FWD_WARPS - 1) / FWD_WARPS, nchunk);
+        if (chunk >= 4)
+            fwd_kernel<float, float, 4><<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
+                f->nitems_gen, d_x, f->N, ntr, chunk, f->ncoef, (float2 *)d_part_ps, (float2 *)d_part_st);
+        else
+            fwd_kernel<float, float, 1><<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
+                f->nitems_gen, d_x, f->N, ntr, chunk, f->ncoef, (float2 *)d_part_ps, (float2 *)d_part_st);
+        TSPWS_LAUNCHED();
+    }
+    return 0;
+}
+
+extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, void *d_ypart,
+                                         tspws_stream_t st)
+{
+    if (ntr <= 0) return 0;
+    if (!f->per_trace) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)st;
+    if (f->nitems2 > 0) {
+        const size_t smem = (size_t)f->fw_smem_per_warp * FW_WARPS * sizeof(float);
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(fwd2_pertrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid((f->nitems2 + FW_WARPS - 1) / FW_WARPS, ntr);
+        fwd2_pertrace_kernel<<<grid, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, f->d_items2,
+            f->nitems2, d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp);
+        TSPWS_LAUNCHED();
+    }
+    if (f->nitems_gen > 0) {
+        dim3 grid((f->nitems_gen + FWD_WARPS - 1) / FWD_WARPS, ntr);
+        fwd_pertrace_generic_kernel<<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
+            f->nitems_gen, d_x, f->N, (float2 *)d_ypart, f->ypart_len);
+        TSPWS_LAUNCHED();
+    }
+    return 0;
+}
+
+/* per-trace coefficients -> PS, ST, Zout.  grid = (tiles over Ns, scales, segments). */
+__global__ void __launch_bounds__(256)
+phasor_combine_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ ypart, int ypart_len,
+                      int ncoef, int seg, const tspws_weight_t *__restrict__ rules,
+                      float2 *__restrict__ ps, float2 *__restrict__ st, float2 *__restrict__ zout)
+{
+    const tspws_scale_t sc = scales[blockIdx.y];
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= sc.Ns) return;
+    const int sg = blockIdx.z;
+    float pr = 0.f, pi = 0.f;
+    double sr = 0.0, si = 0.0;
+    for (int k = 0; k < seg; k++) {
+        const float2 *yp = ypart + (size_t)(sg * seg + k) * ypart_len + sc.ypart_off + m;
+        float re = 0.f, im = 0.f;
+        for (int sp = 0; sp < sc.nsplit; sp++) { const float2 y = yp[(size_t)sp * sc.Ns]; re += y.x; im += y.y; }
+        float a, b;
+        phasor_fast(re, im, a, b);
+        pr += a; pi += b; sr += (double)re; si += (double)im;
+    }
+    const double f = weight_factor(rules[sg], (double)pr, (double)pi);
+    const size_t o = (size_t)sg * ncoef + sc.coef_off + m;
+    ps[o]   = make_float2(pr, pi);
+    st[o]   = make_float2((float)sr, (float)si);
+    zout[o] = make_float2((float)(sr * f), (float)(si * f));
+}
+
+/* ===================================================================================== */
 /* chunk reduction + coherence weighting                                                 */
 /*   segment sg sums chunks [sg*seg, (sg+1)*seg) -> PS, ST; Zout = ST * weight(|PS|)     */
 /* ===================================================================================== */
@@ -465,6 +835,20 @@ extern "C" int tspws_cu_weight(const void *d_ps, const void *d_st, int acc64, in
     /* in-place re-reduction with one chunk per segment: PS/ST are rewritten with themselves */
     return tspws_cu_reduce_weight(d_ps, d_st, acc64, ncoef, nseg, 1, d_rules,
                                   (void *)d_ps, (void *)d_st, d_zout, st);
+}
+
+extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_ypart, int nseg, int seg,
+                                       const tspws_weight_t *d_rules, void *d_ps, void *d_st, void *d_zout,
+                                       tspws_stream_t st)
+{
+    if (nseg <= 0 || f->S <= 0) return 0;
+    int maxNs = (f->N + 0);               /* Ns <= N */
+    dim3 grid((maxNs + 255) / 256, f->S, nseg);
+    if (f->max_Ns > 0) grid.x = (f->max_Ns + 255) / 256;
+    phasor_combine_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(f->d_scale, (const float2 *)d_ypart, f->ypart_len,
+        f->ncoef, seg, d_rules, (float2 *)d_ps, (float2 *)d_st, (float2 *)d_zout);
+    TSPWS_LAUNCHED();
+    return 0;
 }
 
 /* ===================================================================================== */

@@ -40,11 +40,11 @@ struct tspws_plan {
     int    ncs, rowpart_ld, rowpart_n;
     tspws_csum_item_t *d_cs;
     int    *d_slot_off, *d_grp_t0;
-    double *d_part, *d_meancorr, *d_gsum;
-    float  *d_rowpart, *d_gsum32;
+    double *d_part, *d_gsum;
+    float  *d_rowpart, *d_gsum32, *d_mean;
     /* forward / weights / inverse */
     int    chunk, nchunk, ntr_fwd;
-    void  *d_pps, *d_pst, *d_exch, *d_zout, *d_invscratch;
+    void  *d_pps, *d_pst, *d_exch, *d_zout, *d_invscratch, *d_ypart;
     int    summed_across_ranks;
 };
 
@@ -61,16 +61,19 @@ static long env_long(const char *name, long dflt)
 static int pow2_floor(int v) { int r = 1; while (2 * r <= v) r *= 2; return r; }
 
 /* ---- device frame: scale records, filters (fp32 [+fp64]), forward items, inverse groups ---- */
-static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64)
+static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64, int per_trace)
 {
     memset(d, 0, sizeof(*d));
     const int S = (int)f->S;
     d->S = S; d->N = (int)f->N; d->ncoef = (int)f->ncoef; d->ntaps = (int)f->ntaps;
     tspws_scale_t    *sc    = (tspws_scale_t *)calloc(S ? S : 1, sizeof(*sc));
     float            *w32   = (float *)malloc((f->ntaps ? f->ntaps : 1) * 2 * sizeof(float));
-    tspws_fwd_item_t *items = NULL;
+    tspws_fwd_item_t *items = NULL, *items_gen = NULL;
+    tspws_fwd2_item_t *items2 = NULL;
     tspws_inv_group_t *grp  = NULL;
-    int nitems = 0, ok = 0;
+    float *g32 = NULL;
+    int nitems = 0, nitems_gen = 0, nitems2 = 0, ok = 0;
+    size_t ng = 0;
     if (!sc || !w32) goto done;
 
     const long work = env_long("TSPWS_FWD_WORK", 4096);    /* taps x coefficients per warp item */
@@ -105,6 +108,99 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
     }
     for (size_t i = 0; i < 2 * f->ntaps; i++) w32[i] = (float)f->w[i];
 
+    /* ---- polyphase (register-tiled) kernel: which scales it covers, padded filters, items ---- */
+    {
+        const int N = (int)f->N;
+        const int pbmax = (int)env_long("TSPWS_FW_PB", 4);       /* blocks of 32 phases per per-trace item */
+        const int nofast = (int)env_long("TSPWS_NO_FAST", 0);
+        d->per_trace = per_trace;
+        d->fw_smem_per_warp = 0;
+        d->max_Ns = 0;
+        int ypart = 0;
+        for (int s = 0; s < S; s++) {
+            const int L = sc[s].L, c = sc[s].c, D = sc[s].D, Ns = sc[s].Ns;
+            const int e = (D - c % D) % D;
+            sc[s].A  = (c + e) / D;
+            sc[s].Qs = (e + L + D - 1) / D;
+            sc[s].lg = -1;
+            sc[s].nsplit = 1;
+            if (Ns > d->max_Ns) d->max_Ns = Ns;
+            if (!nofast && D <= N) {
+                if (D >= 32) sc[s].lg = 5;
+                else if ((D & (D - 1)) == 0) {
+                    int lg = 0; while ((1 << lg) < D) lg++;
+                    const int tiles = 32 >> lg;
+                    const long W = ((long)tiles * 16 + sc[s].Qs - 1) * D;
+                    const long need = W + (W / (16 * D) + 1) * D;
+                    if (W <= N && sc[s].Qs <= 96 && need * 8 * 4 <= 200 * 1024) {
+                        sc[s].lg = lg;
+                        if (need > d->fw_smem_per_warp) d->fw_smem_per_warp = (int)need;
+                    }
+                }
+            }
+            if (sc[s].lg >= 0) { sc[s].g_off = (int)ng; ng += (size_t)sc[s].Qs * D; }
+            if (sc[s].lg == 5 && per_trace) {
+                const int nblk = (D + 31) / 32;
+                sc[s].nsplit = (nblk + pbmax - 1) / pbmax;
+            }
+            sc[s].ypart_off = ypart;
+            ypart += sc[s].nsplit * Ns;
+        }
+        d->ypart_len = ypart;
+        g32 = (float *)calloc((ng ? ng : 1) * 2, sizeof(float));
+        if (!g32) goto done;
+        for (int s = 0; s < S; s++) {
+            if (sc[s].lg < 0) continue;
+            const int e = sc[s].A * sc[s].D - sc[s].c;
+            const double *w = f->w + 2 * f->tap_off[s];
+            float *g = g32 + 2 * (size_t)sc[s].g_off;
+            for (int l = 0; l < sc[s].L; l++) {           /* g[t] = conj(w[t - e]) */
+                g[2 * (e + l)]     = (float)w[2 * l];
+                g[2 * (e + l) + 1] = (float)(-w[2 * l + 1]);
+            }
+        }
+        for (int pass = 0; pass < 2; pass++) {
+            nitems2 = 0; nitems_gen = 0;
+            for (int lg = 0; lg <= 5; lg++) {
+                d->fw_lg_begin[lg] = nitems2;
+                for (int s = 0; s < S; s++) {
+                    if (sc[s].lg != lg) continue;
+                    const int per_item = (lg < 5) ? (512 >> lg) : 16;
+                    const int nblk = (lg < 5) ? 1 : (sc[s].D + 31) / 32;
+                    const int nsp = sc[s].nsplit;
+                    for (int m0 = 0; m0 < sc[s].Ns; m0 += per_item)
+                        for (int sp = 0; sp < nsp; sp++) {
+                            if (pass) {
+                                tspws_fwd2_item_t *it = &items2[nitems2];
+                                it->s = s; it->m0 = m0; it->split = sp;
+                                it->pb0 = (lg < 5) ? 0 : (int)((long)nblk * sp / nsp);
+                                it->pb1 = (lg < 5) ? 1 : (int)((long)nblk * (sp + 1) / nsp);
+                            }
+                            nitems2++;
+                        }
+                }
+            }
+            d->fw_lg_begin[6] = nitems2;
+            for (int s = 0; s < S; s++) {
+                if (sc[s].lg >= 0) continue;
+                const int L = sc[s].L, Ns = sc[s].Ns, opp = 32 / sc[s].G;
+                long run = work / L; run -= run % opp; if (run < opp) run = opp;
+                for (int m0 = 0; m0 < Ns; m0 += (int)run) {
+                    if (pass) {
+                        items_gen[nitems_gen].s = s; items_gen[nitems_gen].m0 = m0;
+                        items_gen[nitems_gen].nout = (Ns - m0 < run) ? Ns - m0 : (int)run;
+                    }
+                    nitems_gen++;
+                }
+            }
+            if (!pass) {
+                items2    = (tspws_fwd2_item_t *)calloc(nitems2 ? nitems2 : 1, sizeof(*items2));
+                items_gen = (tspws_fwd_item_t *)calloc(nitems_gen ? nitems_gen : 1, sizeof(*items_gen));
+                if (!items2 || !items_gen) goto done;
+            }
+        }
+    }
+
     /* inverse: split the scales into groups of about equal taps per output sample */
     {
         int want = (int)env_long("TSPWS_INV_GROUPS", 8);
@@ -133,6 +229,13 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
     if (cudaMemcpy(d->d_w32, w32, f->ntaps * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_items, items, nitems * sizeof(*items), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_invgrp, grp, d->ninv * sizeof(*grp), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMalloc(&d->d_g32, (ng ? ng : 1) * 2 * sizeof(float)) != cudaSuccess) goto done;
+    if (cudaMemcpy(d->d_g32, g32, (ng ? ng : 1) * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&d->d_items2, (nitems2 ? nitems2 : 1) * sizeof(*items2)) != cudaSuccess) goto done;
+    if (cudaMemcpy(d->d_items2, items2, nitems2 * sizeof(*items2), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&d->d_items_gen, (nitems_gen ? nitems_gen : 1) * sizeof(*items_gen)) != cudaSuccess) goto done;
+    if (cudaMemcpy(d->d_items_gen, items_gen, nitems_gen * sizeof(*items_gen), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    d->nitems2 = nitems2; d->nitems_gen = nitems_gen;
     if (want64) {
         if (cudaMalloc(&d->d_w64, (f->ntaps ? f->ntaps : 1) * 2 * sizeof(double)) != cudaSuccess) goto done;
         if (cudaMemcpy(d->d_w64, f->w, f->ntaps * 2 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
@@ -140,7 +243,7 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
     d->nitems = nitems;
     ok = 1;
 done:
-    free(sc); free(w32); free(items); free(grp);
+    free(sc); free(w32); free(items); free(grp); free(items2); free(items_gen); free(g32);
     return ok ? 0 : -1;
 }
 
@@ -148,6 +251,7 @@ static void devframe_free(tspws_devframe_t *d)
 {
     cudaFree(d->d_scale); cudaFree(d->d_w32); cudaFree(d->d_w64);
     cudaFree(d->d_items); cudaFree(d->d_invgrp);
+    cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen);
     memset(d, 0, sizeof(*d));
 }
 
@@ -195,7 +299,7 @@ static int twostage_build(tspws_plan_t *pl)
     if (cudaMalloc((void **)&pl->d_slot_off, (K + 1) * sizeof(int)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&pl->d_grp_t0, (K + 1) * sizeof(int)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&pl->d_part, (ni ? ni : 1) * N * sizeof(double)) != cudaSuccess) goto done;
-    if (cudaMalloc((void **)&pl->d_meancorr, K * sizeof(double)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_mean, (size_t)(n ? n : 1) * sizeof(float)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&pl->d_gsum, K * N * sizeof(double)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&pl->d_gsum32, K * N * sizeof(float)) != cudaSuccess) goto done;
     if (pl->p.lrm && cudaMalloc((void **)&pl->d_rowpart, (size_t)(n ? n : 1) * pl->rowpart_ld * sizeof(float)) != cudaSuccess) goto done;
@@ -213,9 +317,9 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     if (!pl) return;
     devframe_free(&pl->dev);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
-    cudaFree(pl->d_part); cudaFree(pl->d_meancorr); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
+    cudaFree(pl->d_part); cudaFree(pl->d_mean); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
     cudaFree(pl->d_rowpart); cudaFree(pl->d_pps); cudaFree(pl->d_pst); cudaFree(pl->d_exch);
-    cudaFree(pl->d_zout); cudaFree(pl->d_invscratch);
+    cudaFree(pl->d_zout); cudaFree(pl->d_invscratch); cudaFree(pl->d_ypart);
     tspws_b200_frame_destroy(pl->fr);
     free(pl);
 }
@@ -238,7 +342,7 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     if (!pl->fr) { fprintf(stderr, "tspws_b200: cannot build the wavelet frame\n"); free(pl); return NULL; }
     for (unsigned int s = 0; s < pl->fr->S; s++)
         if (pl->fr->L[s] > (unsigned int)max) goto fail;          /* cannot happen: L is capped at N */
-    if (devframe_build(&pl->dev, pl->fr, pl->acc64)) goto fail;
+    if (devframe_build(&pl->dev, pl->fr, pl->acc64, pl->two_stage && !pl->acc64)) goto fail;
 
     CK(cudaMalloc((void **)&pl->d_rule, sizeof(tspws_weight_t)));
     CK(cudaMemcpy(pl->d_rule, &pl->rule, sizeof(tspws_weight_t), cudaMemcpyHostToDevice));
@@ -257,8 +361,12 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     if (pl->chunk < 1) pl->chunk = 1;
     pl->nchunk = (pl->ntr_fwd + pl->chunk - 1) / pl->chunk;
     if (pl->nchunk < 1) pl->nchunk = 1;
-    CK(cudaMalloc(&pl->d_pps, (size_t)pl->nchunk * ncoef * pl->csz));
-    CK(cudaMalloc(&pl->d_pst, (size_t)pl->nchunk * ncoef * pl->csz));
+    if (pl->dev.per_trace) {
+        CK(cudaMalloc(&pl->d_ypart, (size_t)(pl->dev.ypart_len ? pl->dev.ypart_len : 1) * pl->K * 2 * sizeof(float)));
+    } else {
+        CK(cudaMalloc(&pl->d_pps, (size_t)pl->nchunk * ncoef * pl->csz));
+        CK(cudaMalloc(&pl->d_pst, (size_t)pl->nchunk * ncoef * pl->csz));
+    }
     CK(cudaMalloc(&pl->d_exch, 2 * ncoef * pl->csz));
     CK(cudaMalloc(&pl->d_zout, ncoef * pl->csz));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.ninv ? pl->dev.ninv : 1) * max * (pl->csz / 2)));
@@ -282,11 +390,11 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
                                  pl->p.lrm ? pl->d_rowpart : NULL, pl->rowpart_ld, stream))) return TSPWS_ERR_CUDA;
         if ((e = tspws_cu_colsum_finalize(pl->d_part, pl->d_slot_off, (int)pl->K, pl->N,
                                           pl->p.lrm ? pl->d_rowpart : NULL, pl->rowpart_ld, pl->rowpart_n,
-                                          pl->d_grp_t0, pl->d_meancorr, pl->d_gsum, stream))) return TSPWS_ERR_CUDA;
+                                          pl->d_grp_t0, (int)pl->mtr_local, pl->d_mean, pl->d_gsum, stream))) return TSPWS_ERR_CUDA;
         return 0;
     }
     if ((e = tspws_cu_prep(d_sigall, (int)pl->mtr_local, pl->N, pl->p.fold, pl->p.lrm, stream))) return TSPWS_ERR_CUDA;
-    if ((e = tspws_cu_forward(&pl->dev, d_sigall, 0, 0, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+    if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
     if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, 0, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
                                     plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     return 0;
@@ -311,10 +419,15 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     int e;
     if (pl->two_stage) {
         if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, (int)pl->K, pl->N, pl->p.fold, stream))) return TSPWS_ERR_CUDA;
-        const void *x = pl->acc64 ? (const void *)pl->d_gsum : (const void *)pl->d_gsum32;
-        if ((e = tspws_cu_forward(&pl->dev, x, pl->acc64, pl->acc64, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
-        if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, pl->acc64, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
-                                        plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+        if (pl->dev.per_trace) {
+            if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule,
+                                             plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+        } else {
+            if ((e = tspws_cu_forward(&pl->dev, pl->d_gsum, 1, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, 1, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
+                                            plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+        }
     } else if (pl->summed_across_ranks) {
         if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), 0, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     }
