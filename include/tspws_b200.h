@@ -181,6 +181,11 @@ int  tspws_b200_device_count(void);          /* <0: CUDA unusable               
 void tspws_b200_shutdown(void);              /* frees cached plans / device workspaces  */
 const char *tspws_b200_version(void);
 unsigned long tspws_b200_kernel_launches(void); /* kernels launched by this library so far */
+/* Optional in-stream timing of every kernel with CUDA events (used by bench.py for the roofline
+ * line): enable, run, then read "kernel_name launches total_ms" lines.  Off by default. */
+int tspws_b200_profile(int enable);
+int tspws_b200_profile_reset(void);
+int tspws_b200_profile_read(char *buf, int cap);
 
 /* ---- device-resident API (inputs already in HBM; used by bench.py and multi-GPU) ---- */
 typedef struct tspws_plan tspws_plan_t;

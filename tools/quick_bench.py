@@ -28,6 +28,12 @@ def run(name, mtr, n, reps=5, **kw):
     torch.cuda.synchronize()
     ts_ = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
     best = min(ts_)
+    if os.environ.get("PROF"):
+        lib.tspws_b200_profile(1); lib.tspws_b200_profile_reset()
+        for i in range(reps): step()
+        torch.cuda.synchronize()
+        prof = B.read_profile(lib); lib.tspws_b200_profile(0)
+        print("   " + "  ".join(f"{k}={v[1]/max(v[0],1)*1e3:.1f}us(x{v[0]//reps})" for k, v in prof.items()))
     print(f"{name}: {mtr}x{n} J={p.J} V={p.V} best {best*1e3:.1f} us  median {sorted(ts_)[len(ts_)//2]*1e3:.1f} us  "
           f"{mtr*n/best/1e6:.3f} Gsamples/s  {mtr*n*4/best/1e6:.1f} GB/s", flush=True)
     lib.tspws_b200_plan_destroy(plan)
@@ -35,6 +41,9 @@ def run(name, mtr, n, reps=5, **kw):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ts":
         run("two-stage morlet rm", 8192, 16384, reps=2, Kmax=10, unbiased=1, lrm=1)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ss64":
+        run("single-stage morlet w0=6 (64 traces)", 64, 16384, reps=1, w0=6.0, w0set=4, lrm=1)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ss":
         run("single-stage morlet w0=6 (256 traces)", 256, 16384, reps=1, w0=6.0, w0set=4, lrm=1)

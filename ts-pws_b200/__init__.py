@@ -141,6 +141,8 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_shutdown.restype = None
     lib.tspws_b200_version.restype = C.c_char_p
     lib.tspws_b200_kernel_launches.restype = C.c_ulong
+    lib.tspws_b200_profile.argtypes = [C.c_int]
+    lib.tspws_b200_profile_read.argtypes = [C.c_char_p, C.c_int]
     lib.tspws_b200_plan_create.restype = C.c_void_p
     lib.tspws_b200_plan_create.argtypes = [C.POINTER(TsPWS), C.c_int, C.c_uint, C.c_uint, C.c_uint]
     lib.tspws_b200_plan_destroy.restype = None
@@ -175,7 +177,7 @@ EXPORTS = [
     "tspws_b200_subsampling_plan", "tspws_b200_jackknife_plans", "tspws_b200_get_coherence",
     "tspws_b200_get_stacks", "tspws_b200_set_selection", "tspws_b200_set_option",
     "tspws_b200_get_option", "tspws_b200_device_count", "tspws_b200_shutdown", "tspws_b200_version",
-    "tspws_b200_kernel_launches", "tspws_b200_plan_create", "tspws_b200_plan_destroy",
+    "tspws_b200_kernel_launches", "tspws_b200_profile", "tspws_b200_profile_reset", "tspws_b200_profile_read", "tspws_b200_plan_create", "tspws_b200_plan_destroy",
     "tspws_b200_plan_reduce", "tspws_b200_plan_exchange_ptr", "tspws_b200_plan_exchange_bytes",
     "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
     "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",
@@ -280,6 +282,17 @@ def call_tspws_main(lib: C.CDLL, sigall: np.ndarray, params: TsPWS, dt: float = 
     rc = lib.tspws_main(C.byref(p), C.byref(out), C.byref(dat))
     res.update(rc=rc, ls=ls, tsPWS=ts, params=p, sigall=x, M=M)
     return res
+
+
+def read_profile(lib) -> dict:
+    """Per-kernel in-stream timings collected since the last reset: name -> (launches, total_ms)."""
+    buf = C.create_string_buffer(8192)
+    lib.tspws_b200_profile_read(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 def frame_to_dict(fr) -> dict:

@@ -156,6 +156,10 @@ int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, const void *
                      float *d_out_ts, float *d_out_ls, tspws_stream_t st);
 
 unsigned long tspws_cu_launch_count(void);
+void tspws_cu_profile_mark(tspws_stream_t st);
+int  tspws_cu_profile_enable(int on);
+int  tspws_cu_profile_reset(void);
+int  tspws_cu_profile_read(char *buf, int cap);
 
 #ifdef __cplusplus
 }

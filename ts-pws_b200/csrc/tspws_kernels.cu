@@ -19,14 +19,89 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <stdio.h>
+#include <string.h>
 
 #include "tspws_internal.h"
 
 static unsigned long g_launches = 0;
 extern "C" unsigned long tspws_cu_launch_count(void) { return g_launches; }
 
-#define TSPWS_LAUNCHED()                              \
+/* ---- optional per-kernel timing with CUDA events on the launching stream: an event is recorded
+ * after every launch (and at tspws_cu_profile_mark), and a kernel is charged the time since the
+ * previous event -- warm, in-stream durations including launch gaps (ncu's are cold-cache and
+ * serialised).  Off by default: zero cost. ---- */
+#define PROF_MAX_KERNELS 32
+#define PROF_MAX_EVENTS  2048
+static struct {
+    int         on, nk, nev, created;
+    const char *name[PROF_MAX_KERNELS];
+    double      ms[PROF_MAX_KERNELS];
+    long        count[PROF_MAX_KERNELS];
+    cudaEvent_t ev[PROF_MAX_EVENTS];
+    int         evk[PROF_MAX_EVENTS];       /* kernel index, -1 for a bare mark */
+} g_prof;
+
+static void prof_flush(void)
+{
+    for (int i = 1; i < g_prof.nev; i++) {
+        if (g_prof.evk[i] < 0) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(g_prof.ev[i]) == cudaSuccess &&
+            cudaEventElapsedTime(&ms, g_prof.ev[i - 1], g_prof.ev[i]) == cudaSuccess) {
+            g_prof.ms[g_prof.evk[i]] += ms;
+            g_prof.count[g_prof.evk[i]]++;
+        }
+    }
+    g_prof.nev = 0;
+}
+
+static void prof_record(const char *name, cudaStream_t s)
+{
+    if (g_prof.nev >= PROF_MAX_EVENTS) {
+        prof_flush();
+        if (name) return;                    /* lost its start marker: skip this one */
+    }
+    int k = -1;
+    if (name) {
+        for (k = 0; k < g_prof.nk; k++) if (!strcmp(g_prof.name[k], name)) break;
+        if (k == g_prof.nk) { if (k >= PROF_MAX_KERNELS) return; g_prof.name[k] = name; g_prof.nk++; }
+        if (g_prof.nev == 0) return;         /* no preceding event to measure from */
+    }
+    const int i = g_prof.nev;
+    if (i >= g_prof.created) { cudaEventCreate(&g_prof.ev[i]); g_prof.created = i + 1; }
+    g_prof.evk[i] = k;
+    cudaEventRecord(g_prof.ev[i], s);
+    g_prof.nev = i + 1;
+}
+
+extern "C" void tspws_cu_profile_mark(tspws_stream_t st) { if (g_prof.on) prof_record(nullptr, (cudaStream_t)st); }
+extern "C" int tspws_cu_profile_enable(int on)
+{
+    if (!on) prof_flush();
+    g_prof.on = on;
+    return 0;
+}
+extern "C" int tspws_cu_profile_reset(void)
+{
+    prof_flush();
+    for (int k = 0; k < g_prof.nk; k++) { g_prof.ms[k] = 0; g_prof.count[k] = 0; }
+    return 0;
+}
+/* Writes "name count total_ms\n" lines; returns the number of bytes written. */
+extern "C" int tspws_cu_profile_read(char *buf, int cap)
+{
+    prof_flush();
+    int off = 0;
+    if (cap > 0) buf[0] = 0;
+    for (int k = 0; k < g_prof.nk && off < cap - 1; k++)
+        off += snprintf(buf + off, cap - off, "%s %ld %.6f\n", g_prof.name[k], g_prof.count[k], g_prof.ms[k]);
+    return off;
+}
+
+#define TSPWS_LAUNCHED_N(name, stream)                \
     do {                                              \
+        if (g_prof.on) prof_record(name, stream);     \
         g_launches++;                                 \
         cudaError_t e__ = cudaGetLastError();         \
         if (e__ != cudaSuccess) return (int)e__;      \
@@ -99,7 +174,7 @@ extern "C" int tspws_cu_prep(float *d_x, int ntr, int N, int do_fold, int do_rm,
 {
     if (ntr <= 0 || (!do_fold && !do_rm)) return 0;
     prep_kernel<<<ntr, 256, 0, (cudaStream_t)st>>>(d_x, N, do_fold, do_rm);
-    TSPWS_LAUNCHED();
+    TSPWS_LAUNCHED_N("prep_kernel", (cudaStream_t)st);
     return 0;
 }
 
@@ -192,7 +267,7 @@ extern "C" int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t 
         if (d_rowpart) colsum_kernel<false, true><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_rowpart, rowpart_ld);
         else           colsum_kernel<false, false><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_rowpart, rowpart_ld);
     }
-    TSPWS_LAUNCHED();
+    TSPWS_LAUNCHED_N("colsum_kernel", s);
     return 0;
 }
 
@@ -242,11 +317,11 @@ extern "C" int tspws_cu_colsum_finalize(const double *d_part, const int *d_slot_
     cudaStream_t s = (cudaStream_t)st;
     if (d_rowpart && ntr > 0) {
         rowmean_kernel<<<(ntr + 7) / 8, 256, 0, s>>>(d_rowpart, rowpart_ld, rowpart_n, ntr, N, d_mean);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("rowmean_kernel", s);
     }
     dim3 grid((N + 255) / 256, G);
     colsum_finalize_kernel<<<grid, 256, 0, s>>>(d_part, d_slot_off, N, d_rowpart ? d_mean : nullptr, d_grp_t0, d_gsum);
-    TSPWS_LAUNCHED();
+    TSPWS_LAUNCHED_N("colsum_finalize_kernel", s);
     return 0;
 }
 
@@ -271,7 +346,7 @@ extern "C" int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N
 {
     dim3 grid(((N + 1) / 2 + 255) / 256, G);
     group_post_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(d_gsum, d_gsum32, N, do_fold);
-    TSPWS_LAUNCHED();
+    TSPWS_LAUNCHED_N("group_post_kernel", (cudaStream_t)st);
     return 0;
 }
 
@@ -382,7 +457,7 @@ static int fwd_launch(const tspws_devframe_t *f, const void *d_x, int ntr, int c
     else
         fwd_kernel<TIN, T, 1><<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, w, f->d_items, f->nitems,
             (const TIN *)d_x, f->N, ntr, chunk, f->ncoef, (T2 *)d_pps, (T2 *)d_pst);
-    TSPWS_LAUNCHED();
+    TSPWS_LAUNCHED_N("fwd_kernel", s);
     return 0;
 }
 
@@ -454,41 +529,86 @@ __device__ __forceinline__ void lane_transpose_reduce(float (&v)[2 * FW_R], cons
     }
 }
 
-/* One pass: R coefficients x Qs taps of one phase.  LOADX(j) returns window sample j. */
-#define FW_TAPLOOP(LOADX, GPTR, GSTRIDE, ACTIVE)                                          \
-    {                                                                                     \
-        float win[2 * FW_R - 1];                                                          \
-        _Pragma("unroll")                                                                 \
-        for (int j = 0; j < FW_R - 1; j++) win[j] = LOADX(j);                             \
-        for (int qb = 0; qb < Qs; qb += FW_R) {                                           \
-            _Pragma("unroll")                                                             \
-            for (int qq = 0; qq < FW_R; qq++) {                                           \
-                if (qb + qq < Qs) {                                                       \
-                    win[qq + FW_R - 1] = LOADX(qb + qq + FW_R - 1);                       \
-                    float2 gv = make_float2(0.f, 0.f);                                    \
-                    if (ACTIVE) gv = __ldg((GPTR) + (size_t)(qb + qq) * (GSTRIDE));       \
-                    _Pragma("unroll")                                                     \
-                    for (int r = 0; r < FW_R; r++) {                                      \
-                        v[2 * r]     = fmaf(win[r + qq], gv.x, v[2 * r]);                 \
-                        v[2 * r + 1] = fmaf(win[r + qq], gv.y, v[2 * r + 1]);             \
-                    }                                                                     \
-                }                                                                         \
-            }                                                                             \
-            _Pragma("unroll")                                                             \
-            for (int j = 0; j < FW_R - 1; j++) win[j] = win[j + FW_R];                    \
-        }                                                                                 \
+/* ---- cp.async helpers (Ampere+ LDGSTS; fine on sm_100a) ---- */
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
+
+/* One pass: 16 coefficients x Qs taps of one phase.
+ *   loadx(j): window sample j (called with strictly increasing j), loadg(q): filter tap q.
+ * The window lives in a 24-register ring (slot = j mod 24) so that every index is static after
+ * unrolling 24 taps; each slot is refilled right after its last use, i.e. 8 taps (256 FMAs) before
+ * it is needed again, and filter taps are refilled 8 taps ahead -- loads never stall the FMAs. */
+#define FW_WS 24
+template <typename LoadX, typename LoadG>
+__device__ __forceinline__ void fw_taps(float (&v)[2 * FW_R], const int Qs, LoadX loadx, LoadG loadg)
+{
+    float  win[FW_WS];
+    float2 gq[8];
+#pragma unroll
+    for (int j = 0; j < FW_WS; j++) win[j] = loadx(j);
+#pragma unroll
+    for (int q = 0; q < 8; q++) gq[q] = loadg(q);
+    for (int t0 = 0; t0 < Qs; t0 += FW_WS) {
+#pragma unroll
+        for (int tt = 0; tt < FW_WS; tt++) {
+            const int t = t0 + tt;
+            if (t < Qs) {
+                const float2 gv = gq[tt & 7];
+#pragma unroll
+                for (int r = 0; r < FW_R; r++) {
+                    const float xv = win[(tt + r) % FW_WS];
+                    v[2 * r]     = fmaf(xv, gv.x, v[2 * r]);
+                    v[2 * r + 1] = fmaf(xv, gv.y, v[2 * r + 1]);
+                }
+                win[tt]     = loadx(t + FW_WS);
+                gq[tt & 7] = loadg(t + 8);
+            }
+        }
     }
+}
+
+/* Stage the window [base, base+W) (circular) of one trace into a warp-private, skewed smem buffer:
+ * sample i goes to i + (i / (16 D)) D, i.e. tiles of 16 D samples at a pitch of 17 D floats, which
+ * makes the compute-side accesses of lanes (tile a, phase rho) bank-conflict free. */
+template <int LG>
+__device__ __forceinline__ void fw_stage(float *buf, const float *__restrict__ xk, const int base,
+                                         const int W, const int N, const int lane, const bool vec_ok)
+{
+    constexpr int LP  = 1 << LG;
+    constexpr int CPF = LP >= 4 ? 4 : LP;             /* floats per copy: 16 B when D >= 4 */
+    if (vec_ok) {
+        for (int i = lane * CPF; i < W; i += 32 * CPF) {
+            int pos = base + i;
+            if (pos >= N) pos -= N;
+            cp_async<CPF * 4>(buf + i + (i >> (4 + LG)) * LP, xk + pos);
+        }
+    } else {
+        for (int i = lane; i < W; i += 32) {
+            int pos = base + i;
+            if (pos >= N) pos -= N;
+            cp_async<4>(buf + i + (i >> (4 + LG)) * LP, xk + pos);
+        }
+    }
+}
 
 template <int LG, bool PER_TRACE>
 __device__ __forceinline__ void
 fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__restrict__ g_all,
           const float *__restrict__ x, const int N, const int k_begin, const int k_end,
           const int ncoef, const int chunk_idx, float2 *__restrict__ part_ps, float2 *__restrict__ part_st,
-          float2 *__restrict__ ypart, const int ypart_len, float *xs, const int lane)
+          float2 *__restrict__ ypart, const int ypart_len, float *xs, const int xs_half, const int lane)
 {
     constexpr int LGR  = LG;                       /* lane bits that index phases            */
     constexpr int NVAL = 32 >> LGR;                /* floats of complete coefficients / lane */
     const int D = sc.D, Qs = sc.Qs;
+    const int jmax = FW_R + Qs - 2;                /* last window sample a pass needs        */
     const float2 *__restrict__ g = g_all + sc.g_off;
     float ps[NVAL], st[NVAL];
 #pragma unroll
@@ -498,6 +618,16 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
     if (b0 < 0) b0 += N;
     const int base = (int)b0;                      /* sample of (tile 0, tap 0, phase 0)     */
 
+    /* LG < 5: D = 2^LG phases x (32 >> LG) tiles; window staged by cp.async, double buffered */
+    constexpr int LP = 1 << (LG < 5 ? LG : 0), TILES = 32 >> (LG < 5 ? LG : 0);
+    const int  W      = (TILES * FW_R + Qs - 1) * LP;
+    const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (LG < 5) {
+        __syncwarp();
+        fw_stage<(LG < 5 ? LG : 0)>(xs, x + (size_t)k_begin * N, base, W, N, lane, vec_ok);
+        cp_async_commit();
+    }
+
     for (int k = k_begin; k < k_end; k++) {
         const float *__restrict__ xk = x + (size_t)k * N;
         float v[2 * FW_R];
@@ -505,33 +635,36 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
         for (int i = 0; i < 2 * FW_R; i++) v[i] = 0.f;
 
         if (LG < 5) {
-            /* ---- D = 2^LG phases x (32 >> LG) tiles; stage the window in skewed smem ---- */
-            constexpr int LP = 1 << LG, TILES = 32 >> LG, PITCH = (FW_R + 1) * LP;
-            const int a = lane >> LG, rho = lane & (LP - 1);
-            const int W = (TILES * FW_R + Qs - 1) * LP;
-            __syncwarp();
-            for (int i = lane; i < W; i += 32) {
-                int pos = base + i;
-                if (pos >= N) pos -= N;
-                xs[i + (i >> (4 + LG)) * LP] = xk[pos];
+            float *cur = xs + ((k - k_begin) & 1) * xs_half;
+            if (k + 1 < k_end) {                   /* next trace's window flies in during the FMAs */
+                fw_stage<(LG < 5 ? LG : 0)>(xs + (((k - k_begin) & 1) ^ 1) * xs_half, xk + N, base, W, N, lane, vec_ok);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
             __syncwarp();
-            const float *xw = xs + a * PITCH + rho;
-#define FW_LDS(j) xw[((j) >> 4) * PITCH + ((j) & 15) * LP]
-            FW_TAPLOOP(FW_LDS, g + rho, LP, true)
-#undef FW_LDS
+            const int a = lane >> (LG < 5 ? LG : 0), rho = lane & (LP - 1);
+            const float *xw = cur + a * ((FW_R + 1) * LP) + rho;
+            fw_taps(v, Qs,
+                    [&](const int j) { return j <= jmax ? xw[(j + (j >> 4)) << (LG < 5 ? LG : 0)] : 0.f; },
+                    [&](const int q) { return q < Qs ? __ldg(g + q * LP + rho) : make_float2(0.f, 0.f); });
+            __syncwarp();
         } else {
-            /* ---- D >= 32: 32 consecutive phases per block, samples straight from global ---- */
+            /* D >= 32: 32 consecutive phases per block, samples straight from global / L1 */
             for (int pb = it.pb0; pb < it.pb1; pb++) {
                 const int  rho = pb * 32 + lane;
                 const bool act = rho < D;
-                int pos0 = base + (act ? rho : 0);
-                if (pos0 >= N) pos0 -= N;
-                int pos = pos0;
-                /* window samples are consumed strictly in order j = 0,1,2,...: load, then step by D */
-#define FW_LDG(j) ({ const float t_ = xk[pos]; pos += D; if (pos >= N) pos -= N; t_; })
-                FW_TAPLOOP(FW_LDG, g + rho, D, act)
-#undef FW_LDG
+                int pos = base + (act ? rho : 0);
+                if (pos >= N) pos -= N;
+                const float2 *__restrict__ gr = g + (act ? rho : 0);
+                fw_taps(v, Qs,
+                        [&](const int j) {
+                            float r = 0.f;
+                            if (j <= jmax) { r = xk[pos]; pos += D; if (pos >= N) pos -= N; }
+                            return r;
+                        },
+                        [&](const int q) { return (q < Qs && act) ? __ldg(gr + (size_t)q * D) : make_float2(0.f, 0.f); });
             }
         }
 
@@ -614,7 +747,7 @@ fwd2_acc_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restri
     const tspws_scale_t sc = scales[it.s];
     const int k0 = blockIdx.y * chunk, k1 = min(ntr, k0 + chunk);
     fwd2_body<LG, false>(sc, it, g_all, x, N, k0, k1, ncoef, blockIdx.y, part_ps, part_st, nullptr, 0,
-                         fw_smem + (size_t)w * smem_per_warp, lane);
+                         fw_smem + (size_t)w * smem_per_warp, smem_per_warp / 2, lane);
 }
 
 /* per-trace mode: one kernel for all LG (no accumulators -> one register budget fits all).
@@ -634,12 +767,12 @@ fwd2_pertrace_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__r
     const int k = blockIdx.y;
     float *xs = fw_smem + (size_t)w * smem_per_warp;
     switch (sc.lg) {
-    case 0: fwd2_body<0, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
-    case 1: fwd2_body<1, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
-    case 2: fwd2_body<2, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
-    case 3: fwd2_body<3, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
-    case 4: fwd2_body<4, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
-    default: fwd2_body<5, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, lane); break;
+    case 0: fwd2_body<0, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 1: fwd2_body<1, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 2: fwd2_body<2, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 3: fwd2_body<3, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 4: fwd2_body<4, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    default: fwd2_body<5, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
     }
 }
 
@@ -700,7 +833,7 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
         fwd2_acc_kernel<LGV><<<grid, FW_WARPS * 32, (LGV < 5 ? smem : 0), s>>>(f->d_scale, (const float2 *)f->d_g32, \
             f->d_items2, f->fw_lg_begin[LGV], f->fw_lg_begin[LGV + 1], d_x, f->N, ntr, chunk, f->ncoef,  \
             (float2 *)d_part_ps, (float2 *)d_part_st, f->fw_smem_per_warp);                              \
-        TSPWS_LAUNCHED();                                                                               \
+        TSPWS_LAUNCHED_N("fwd2_acc_kernel<" #LGV ">", s);                                                                               \
     }
     FW_ACC_LAUNCH(0) FW_ACC_LAUNCH(1) FW_ACC_LAUNCH(2) FW_ACC_LAUNCH(3) FW_ACC_LAUNCH(4) FW_ACC_LAUNCH(5)
 #undef FW_ACC_LAUNCH
@@ -712,7 +845,7 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
         else
             fwd_kernel<float, float, 1><<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
                 f->nitems_gen, d_x, f->N, ntr, chunk, f->ncoef, (float2 *)d_part_ps, (float2 *)d_part_st);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("fwd_kernel", s);
     }
     return 0;
 }
@@ -730,13 +863,13 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
         dim3 grid((f->nitems2 + FW_WARPS - 1) / FW_WARPS, ntr);
         fwd2_pertrace_kernel<<<grid, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, f->d_items2,
             f->nitems2, d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("fwd2_pertrace_kernel", s);
     }
     if (f->nitems_gen > 0) {
         dim3 grid((f->nitems_gen + FWD_WARPS - 1) / FWD_WARPS, ntr);
         fwd_pertrace_generic_kernel<<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
             f->nitems_gen, d_x, f->N, (float2 *)d_ypart, f->ypart_len);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("fwd_pertrace_generic_kernel", s);
     }
     return 0;
 }
@@ -825,7 +958,7 @@ extern "C" int tspws_cu_reduce_weight(const void *d_part_ps, const void *d_part_
     else
         reduce_weight_kernel<float><<<grid, 256, 0, s>>>((const float2 *)d_part_ps, (const float2 *)d_part_st,
             ncoef, seg, d_rules, (float2 *)d_ps, (float2 *)d_st, (float2 *)d_zout);
-    TSPWS_LAUNCHED();
+    TSPWS_LAUNCHED_N("reduce_weight_kernel", s);
     return 0;
 }
 
@@ -847,7 +980,7 @@ extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_
     if (f->max_Ns > 0) grid.x = (f->max_Ns + 255) / 256;
     phasor_combine_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(f->d_scale, (const float2 *)d_ypart, f->ypart_len,
         f->ncoef, seg, d_rules, (float2 *)d_ps, (float2 *)d_st, (float2 *)d_zout);
-    TSPWS_LAUNCHED();
+    TSPWS_LAUNCHED_N("phasor_combine_kernel", (cudaStream_t)st);
     return 0;
 }
 
@@ -937,15 +1070,15 @@ static int inv_launch(const tspws_devframe_t *f, const void *d_zout, const void 
     if (d_st) {
         inv_kernel<T, true><<<grid, 256, 0, s>>>(f->d_scale, w, f->d_invgrp, f->ninv, f->N, f->ncoef,
             (const T2 *)d_zout, (const T2 *)d_st, (T *)d_scratch, nseg);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("inv_kernel", s);
         inv_finish_kernel<T, true><<<gridf, 256, 0, s>>>((const T *)d_scratch, f->ninv, nseg, f->N, d_rules, d_ts, d_ls);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("inv_finish_kernel", s);
     } else {
         inv_kernel<T, false><<<grid, 256, 0, s>>>(f->d_scale, w, f->d_invgrp, f->ninv, f->N, f->ncoef,
             (const T2 *)d_zout, nullptr, (T *)d_scratch, nseg);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("inv_kernel", s);
         inv_finish_kernel<T, false><<<gridf, 256, 0, s>>>((const T *)d_scratch, f->ninv, nseg, f->N, d_rules, d_ts, d_ls);
-        TSPWS_LAUNCHED();
+        TSPWS_LAUNCHED_N("inv_finish_kernel", s);
     }
     return 0;
 }

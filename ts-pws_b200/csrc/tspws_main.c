@@ -42,6 +42,11 @@ static struct {
     char         *sel;   unsigned int selM, selmtr;
 } G;
 
+/* per-kernel timing (CUDA events on the launching stream); see tspws_kernels.cu */
+int tspws_b200_profile(int enable) { return tspws_cu_profile_enable(enable); }
+int tspws_b200_profile_reset(void) { return tspws_cu_profile_reset(); }
+int tspws_b200_profile_read(char *buf, int cap) { return tspws_cu_profile_read(buf, cap); }
+
 const char *tspws_b200_version(void) { return "tspws_b200 0.1 (sm_100a)"; }
 unsigned long tspws_b200_kernel_launches(void) { return tspws_cu_launch_count(); }
 

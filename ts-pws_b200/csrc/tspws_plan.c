@@ -131,8 +131,9 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
                     int lg = 0; while ((1 << lg) < D) lg++;
                     const int tiles = 32 >> lg;
                     const long W = ((long)tiles * 16 + sc[s].Qs - 1) * D;
-                    const long need = W + (W / (16 * D) + 1) * D;
-                    if (W <= N && sc[s].Qs <= 96 && need * 8 * 4 <= 200 * 1024) {
+                    long need = W + (W / (16 * D) + 1) * D + 8;          /* skewed window + copy overrun */
+                    need = 2 * ((need + 3) & ~3L);                       /* double buffered, 16 B aligned */
+                    if (W <= N && need * 8 * 4 <= 200 * 1024) {
                         sc[s].lg = lg;
                         if (need > d->fw_smem_per_warp) d->fw_smem_per_warp = (int)need;
                     }
@@ -163,7 +164,8 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
             nitems2 = 0; nitems_gen = 0;
             for (int lg = 0; lg <= 5; lg++) {
                 d->fw_lg_begin[lg] = nitems2;
-                for (int s = 0; s < S; s++) {
+                for (int si = 0; si < S; si++) {
+                    const int s = S - 1 - si;                  /* coarsest (most phase blocks) first */
                     if (sc[s].lg != lg) continue;
                     const int per_item = (lg < 5) ? (512 >> lg) : 16;
                     const int nblk = (lg < 5) ? 1 : (sc[s].D + 31) / 32;
@@ -385,6 +387,7 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     if (!pl || (!d_sigall && pl->mtr_local)) return TSPWS_ERR_NULL;
     int e;
     pl->summed_across_ranks = 0;
+    tspws_cu_profile_mark(stream);
     if (pl->two_stage) {
         if ((e = tspws_cu_colsum(d_sigall, pl->N, pl->d_cs, pl->ncs, pl->d_part,
                                  pl->p.lrm ? pl->d_rowpart : NULL, pl->rowpart_ld, stream))) return TSPWS_ERR_CUDA;
@@ -417,6 +420,7 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
 {
     if (!pl || !d_ls || !d_tspws) return TSPWS_ERR_NULL;
     int e;
+    tspws_cu_profile_mark(stream);
     if (pl->two_stage) {
         if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, (int)pl->K, pl->N, pl->p.fold, stream))) return TSPWS_ERR_CUDA;
         if (pl->dev.per_trace) {
