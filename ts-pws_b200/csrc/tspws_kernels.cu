@@ -496,7 +496,12 @@ extern "C" int tspws_cu_forward(const tspws_devframe_t *f, const void *d_x, int 
 /*   complete coefficients, which go straight into the phasor epilogue.                  */
 /* ===================================================================================== */
 #define FW_R 16
-#define FW_WARPS 8
+#ifndef FW_WARPS
+#define FW_WARPS 4
+#endif
+#ifndef FW_MINB
+#define FW_MINB 4
+#endif
 
 __device__ __forceinline__ double weight_factor(const tspws_weight_t r, double pr, double pi);
 
@@ -541,34 +546,35 @@ template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
 /* One pass: 16 coefficients x Qs taps of one phase.
- *   loadx(j): window sample j (called with strictly increasing j), loadg(q): filter tap q.
- * The window lives in a 24-register ring (slot = j mod 24) so that every index is static after
- * unrolling 24 taps; each slot is refilled right after its last use, i.e. 8 taps (256 FMAs) before
- * it is needed again, and filter taps are refilled 8 taps ahead -- loads never stall the FMAs. */
+ *   loadx(): next window sample (called once per sample, in order), loadg(q): filter tap q
+ *   (the filter array is zero-padded by 8 taps, the window source by 24 samples: no guards).
+ * The window lives in a 24-slot register ring (slot = j mod 24) so that every index is static after
+ * unrolling 24 taps; a slot is refilled right after its last use, i.e. 8 taps before it is needed
+ * again, and filter taps are refilled 8 taps ahead -- loads never stall the FMAs.
+ * Arithmetic is Blackwell's packed FFMA2 (fma.rn.f32x2): one instruction updates (Re, Im) of a
+ * coefficient, acc2[r] += (x, x) * (g.re, g.im); the window keeps every sample duplicated. */
 #define FW_WS 24
 template <typename LoadX, typename LoadG>
-__device__ __forceinline__ void fw_taps(float (&v)[2 * FW_R], const int Qs, LoadX loadx, LoadG loadg)
+__device__ __forceinline__ void fw_taps(float2 (&acc)[FW_R], const int Qs, LoadX loadx, LoadG loadg)
 {
-    float  win[FW_WS];
+    float2 win[FW_WS];
     float2 gq[8];
 #pragma unroll
-    for (int j = 0; j < FW_WS; j++) win[j] = loadx(j);
+    for (int j = 0; j < FW_WS; j++) { const float t = loadx(); win[j] = make_float2(t, t); }
 #pragma unroll
     for (int q = 0; q < 8; q++) gq[q] = loadg(q);
     for (int t0 = 0; t0 < Qs; t0 += FW_WS) {
 #pragma unroll
         for (int tt = 0; tt < FW_WS; tt++) {
-            const int t = t0 + tt;
-            if (t < Qs) {
+            if (t0 + tt < Qs) {
                 const float2 gv = gq[tt & 7];
 #pragma unroll
-                for (int r = 0; r < FW_R; r++) {
-                    const float xv = win[(tt + r) % FW_WS];
-                    v[2 * r]     = fmaf(xv, gv.x, v[2 * r]);
-                    v[2 * r + 1] = fmaf(xv, gv.y, v[2 * r + 1]);
+                for (int r = 0; r < FW_R; r++) acc[r] = __ffma2_rn(win[(tt + r) % FW_WS], gv, acc[r]);
+                if (t0 + tt + FW_WS - FW_R + 1 < Qs) {      /* sample t+24 is used by taps >= t+9 only */
+                    const float t = loadx();
+                    win[tt] = make_float2(t, t);
                 }
-                win[tt]     = loadx(t + FW_WS);
-                gq[tt & 7] = loadg(t + 8);
+                if (t0 + tt + 8 < Qs) gq[tt & 7] = loadg(t0 + tt + 8);
             }
         }
     }
@@ -607,8 +613,9 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
 {
     constexpr int LGR  = LG;                       /* lane bits that index phases            */
     constexpr int NVAL = 32 >> LGR;                /* floats of complete coefficients / lane */
+    constexpr int LGS  = LG < 5 ? LG : 0;
+    constexpr int LP   = 1 << LGS, TILES = 32 >> LGS;
     const int D = sc.D, Qs = sc.Qs;
-    const int jmax = FW_R + Qs - 2;                /* last window sample a pass needs        */
     const float2 *__restrict__ g = g_all + sc.g_off;
     float ps[NVAL], st[NVAL];
 #pragma unroll
@@ -618,55 +625,55 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
     if (b0 < 0) b0 += N;
     const int base = (int)b0;                      /* sample of (tile 0, tap 0, phase 0)     */
 
-    /* LG < 5: D = 2^LG phases x (32 >> LG) tiles; window staged by cp.async, double buffered */
-    constexpr int LP = 1 << (LG < 5 ? LG : 0), TILES = 32 >> (LG < 5 ? LG : 0);
-    const int  W      = (TILES * FW_R + Qs - 1) * LP;
+    /* LG < 5: D = 2^LG phases x (32 >> LG) tiles; window staged by cp.async, double buffered.
+     * 24 samples more than needed are staged so that the register ring refills need no guard. */
+    const int  W      = (TILES * FW_R + Qs + FW_WS) * LP;
     const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (LG < 5) {
         __syncwarp();
-        fw_stage<(LG < 5 ? LG : 0)>(xs, x + (size_t)k_begin * N, base, W, N, lane, vec_ok);
+        fw_stage<LGS>(xs, x + (size_t)k_begin * N, base, W, N, lane, vec_ok);
         cp_async_commit();
     }
 
     for (int k = k_begin; k < k_end; k++) {
         const float *__restrict__ xk = x + (size_t)k * N;
-        float v[2 * FW_R];
+        float2 acc[FW_R];
 #pragma unroll
-        for (int i = 0; i < 2 * FW_R; i++) v[i] = 0.f;
+        for (int i = 0; i < FW_R; i++) acc[i] = make_float2(0.f, 0.f);
 
         if (LG < 5) {
-            float *cur = xs + ((k - k_begin) & 1) * xs_half;
+            const float *cur = xs + ((k - k_begin) & 1) * xs_half;
             if (k + 1 < k_end) {                   /* next trace's window flies in during the FMAs */
-                fw_stage<(LG < 5 ? LG : 0)>(xs + (((k - k_begin) & 1) ^ 1) * xs_half, xk + N, base, W, N, lane, vec_ok);
+                fw_stage<LGS>(xs + (((k - k_begin) & 1) ^ 1) * xs_half, xk + N, base, W, N, lane, vec_ok);
                 cp_async_commit();
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
             __syncwarp();
-            const int a = lane >> (LG < 5 ? LG : 0), rho = lane & (LP - 1);
-            const float *xw = cur + a * ((FW_R + 1) * LP) + rho;
-            fw_taps(v, Qs,
-                    [&](const int j) { return j <= jmax ? xw[(j + (j >> 4)) << (LG < 5 ? LG : 0)] : 0.f; },
-                    [&](const int q) { return q < Qs ? __ldg(g + q * LP + rho) : make_float2(0.f, 0.f); });
+            const int a = lane >> LGS, rho = lane & (LP - 1);
+            const float  *xw = cur + a * ((FW_R + 1) * LP) + rho;
+            const float2 *gr = g + rho;
+            int j = 0;
+            fw_taps(acc, Qs,
+                    [&]() { const float r = xw[(j + (j >> 4)) << LGS]; j++; return r; },
+                    [&](const int q) { return __ldg(gr + q * LP); });
             __syncwarp();
         } else {
-            /* D >= 32: 32 consecutive phases per block, samples straight from global / L1 */
+            /* D >= 32: 32 consecutive phases per block, samples straight from global / L1; the
+             * filter rows are zero-padded to a multiple of 32 phases, so idle lanes add zeros */
+            const int GS = (D + 31) & ~31;
             for (int pb = it.pb0; pb < it.pb1; pb++) {
-                const int  rho = pb * 32 + lane;
-                const bool act = rho < D;
-                int pos = base + (act ? rho : 0);
+                int pos = base + pb * 32 + lane;
                 if (pos >= N) pos -= N;
-                const float2 *__restrict__ gr = g + (act ? rho : 0);
-                fw_taps(v, Qs,
-                        [&](const int j) {
-                            float r = 0.f;
-                            if (j <= jmax) { r = xk[pos]; pos += D; if (pos >= N) pos -= N; }
-                            return r;
-                        },
-                        [&](const int q) { return (q < Qs && act) ? __ldg(gr + (size_t)q * D) : make_float2(0.f, 0.f); });
+                if (pos >= N) pos -= N;
+                const float2 *gr = g + pb * 32 + lane;
+                fw_taps(acc, Qs,
+                        [&]() { const float r = xk[pos]; pos += D; if (pos >= N) pos -= N; return r; },
+                        [&](const int q) { return __ldg(gr + (size_t)q * GS); });
             }
         }
+        float(&v)[2 * FW_R] = reinterpret_cast<float(&)[2 * FW_R]>(acc);
 
         lane_transpose_reduce<LGR>(v, lane);
 
@@ -733,7 +740,7 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
 /* chunk-accumulate mode: one instantiation per LG (register budgets differ); items of that LG
  * are [item_begin, item_end).  grid = (ceil(items / 8 warps), chunks). */
 template <int LG>
-__global__ void __launch_bounds__(FW_WARPS * 32)
+__global__ void __launch_bounds__(FW_WARPS * 32, FW_MINB)
 fwd2_acc_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
                 const tspws_fwd2_item_t *__restrict__ items, int item_begin, int item_end,
                 const float *__restrict__ x, int N, int ntr, int chunk, int ncoef,
@@ -752,7 +759,7 @@ fwd2_acc_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restri
 
 /* per-trace mode: one kernel for all LG (no accumulators -> one register budget fits all).
  * grid = (ceil(items / 8 warps), traces). */
-__global__ void __launch_bounds__(FW_WARPS * 32)
+__global__ void __launch_bounds__(FW_WARPS * 32, FW_MINB)
 fwd2_pertrace_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
                      const tspws_fwd2_item_t *__restrict__ items, int nitems,
                      const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len,

@@ -130,16 +130,20 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
                 else if ((D & (D - 1)) == 0) {
                     int lg = 0; while ((1 << lg) < D) lg++;
                     const int tiles = 32 >> lg;
-                    const long W = ((long)tiles * 16 + sc[s].Qs - 1) * D;
+                    const long W = ((long)tiles * 16 + sc[s].Qs + 24) * D;   /* + ring over-read */
                     long need = W + (W / (16 * D) + 1) * D + 8;          /* skewed window + copy overrun */
                     need = 2 * ((need + 3) & ~3L);                       /* double buffered, 16 B aligned */
-                    if (W <= N && need * 8 * 4 <= 200 * 1024) {
+                    if (W <= N && need * 4 * 4 * 3 <= 200 * 1024) {
                         sc[s].lg = lg;
                         if (need > d->fw_smem_per_warp) d->fw_smem_per_warp = (int)need;
                     }
                 }
             }
-            if (sc[s].lg >= 0) { sc[s].g_off = (int)ng; ng += (size_t)sc[s].Qs * D; }
+            if (sc[s].lg >= 0) {
+                const int gs = (sc[s].lg == 5) ? ((D + 31) & ~31) : D;     /* phases padded to 32 lanes */
+                sc[s].g_off = (int)ng;
+                ng += (size_t)(sc[s].Qs + 8) * gs;                       /* + 8 zero taps: unguarded prefetch */
+            }
             if (sc[s].lg == 5 && per_trace) {
                 const int nblk = (D + 31) / 32;
                 sc[s].nsplit = (nblk + pbmax - 1) / pbmax;
@@ -155,9 +159,11 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
             const int e = sc[s].A * sc[s].D - sc[s].c;
             const double *w = f->w + 2 * f->tap_off[s];
             float *g = g32 + 2 * (size_t)sc[s].g_off;
-            for (int l = 0; l < sc[s].L; l++) {           /* g[t] = conj(w[t - e]) */
-                g[2 * (e + l)]     = (float)w[2 * l];
-                g[2 * (e + l) + 1] = (float)(-w[2 * l + 1]);
+            const int Ds = sc[s].D, gs = (sc[s].lg == 5) ? ((Ds + 31) & ~31) : Ds;
+            for (int l = 0; l < sc[s].L; l++) {           /* g[q][rho] = conj(w[q D + rho - e]) */
+                const int t = e + l, q = t / Ds, rho = t % Ds;
+                g[2 * ((size_t)q * gs + rho)]     = (float)w[2 * l];
+                g[2 * ((size_t)q * gs + rho) + 1] = (float)(-w[2 * l + 1]);
             }
         }
         for (int pass = 0; pass < 2; pass++) {
