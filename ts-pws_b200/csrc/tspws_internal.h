@@ -107,19 +107,16 @@ typedef void *tspws_stream_t;
 /* fold (src/ts_pws1f_lib.c:76-86) + mean removal (:160-168) in place, bit-faithful fp32. */
 int tspws_cu_prep(float *d_x, int ntr, int N, int do_fold, int do_rm, tspws_stream_t st);
 
-/* Two-stage column sums (src/ts_pws1f_lib.c:866-881): per-item partial sums of fp32 traces into
- * fp64 slots [nslots][N]; optional per-(trace,tile) row partial sums for the mean. */
+/* Two-stage group sums (src/ts_pws1f_lib.c:866-881): fp32 traces -> fp64 [G][N] group sums
+ * (per-item partial slots [nslots][N] combined by the last CTA of each (group, tile), in slot
+ * order) and per-(group, tile) totals gtile [G][ntile], ntile = ceil(N/1024).
+ * d_tickets: [G][ntile] zero-initialised counters (self re-arming). */
 int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t *d_items, int nitems,
-                    double *d_part, float *d_rowpart, int rowpart_ld, tspws_stream_t st);
-/* Combine partial slots into group sums and subtract the per-group mean correction
- * (sum over the group's local traces of the float-cast trace mean) when d_rowpart != NULL. */
-int tspws_cu_colsum_finalize(const double *d_part, const int *d_slot_off /*[G+1]*/, int G, int N,
-                             const float *d_rowpart, int rowpart_ld, int rowpart_n,
-                             const int *d_grp_t0 /*[G+1] local trace range of each group*/,
-                             int ntr, float *d_mean /*[ntr] scratch*/, double *d_gsum /*[G][N]*/,
-                             tspws_stream_t st);
-/* Fold the group sums (linear) and emit the fp32 copy read by the fp32 transform. */
-int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N, int do_fold, tspws_stream_t st);
+                    double *d_part, const int *d_slot_off, unsigned int *d_tickets,
+                    double *d_gsum, double *d_gtile, tspws_stream_t st);
+/* Mean removal + fold of the group sums (both linear) and the fp32 copy for the transform. */
+int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N, const double *d_gtile,
+                        int ntile, int do_rm, int do_fold, tspws_stream_t st);
 
 /* Forward frame transform + phasor / linear accumulation over chunks of traces (generic kernel,
  * any geometry, float or double).
@@ -150,9 +147,10 @@ int tspws_cu_weight(const void *d_ps, const void *d_st, int acc64, int ncoef, in
                     const tspws_weight_t *d_rules, void *d_zout, tspws_stream_t st);
 /* Inverse frame transform of nseg coefficient sets (two per set: Zout -> tsPWS, ST -> ls).
  *   d_out_ts/d_out_ls: float [nseg][N];  ls is divided by rules[seg].T like src/ts_pws1f_lib.c:234.
- *   d_st may be NULL (no linear stack wanted).  d_scratch: [2][ninv][nseg][N] of T. */
+ *   d_st may be NULL (no linear stack wanted).  d_scratch: [2][ninv][nseg][N] of T;
+ *   d_tickets: [nseg][ceil(N/256)] zero-initialised counters (self re-arming). */
 int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, const void *d_st, int acc64,
-                     int nseg, const tspws_weight_t *d_rules, void *d_scratch,
+                     int nseg, const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
                      float *d_out_ts, float *d_out_ls, tspws_stream_t st);
 
 unsigned long tspws_cu_launch_count(void);

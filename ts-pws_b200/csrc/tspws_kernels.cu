@@ -5,7 +5,7 @@
  * ------------------------  -----------------------------------------------------  -------
  * prep_kernel               fold src/ts_pws1f_lib.c:76-86, mean removal :160-168   HBM
  * colsum_kernel             partial_linear_stacks src/ts_pws1f_lib.c:866-881       HBM  (headline)
- * rowmean/finalize/post     mean + fold applied to the Kmax group sums (linear)    tiny
+ * group_post_kernel         mean + fold applied to the Kmax group sums (linear)    tiny
  * fwd_kernel                complex_1D_wavelet_dec src/FWTa/wavelet_v7.c:43-64 ->
  *                           cdotx_dc src/FWTa/cdotx.c:35-72, fused with the phasor
  *                           accumulate of src/ts_pws1f_lib.c:486-494 / :897-904    FP32/LSU
@@ -179,25 +179,33 @@ extern "C" int tspws_cu_prep(float *d_x, int ntr, int N, int do_fold, int do_rm,
 }
 
 /* ===================================================================================== */
-/* colsum: fp32 traces -> fp64 partial column sums per work item (HBM-bound stream)      */
+/* colsum: fp32 traces -> fp64 group sums (HBM-bound stream; the headline kernel)        */
 /*   grid.x = column tiles of 1024 samples, grid.y = items (trace ranges inside a group) */
+/*   Every CTA leaves the partial column sums of its item in a private slot; the LAST    */
+/*   CTA of each (group, tile) to finish -- found with a fence + atomic ticket -- adds   */
+/*   the group's slots in slot order (deterministic, no float atomics) into gsum and     */
+/*   leaves the tile's total in gtile[g][tile] (used for the mean removal).              */
 /* ===================================================================================== */
 #define CS_THREADS 256
 #define CS_TILE    1024
 #define CS_UNROLL  8
 
-template <bool VEC, bool ROWSUM>
+template <bool VEC>
 __global__ void __launch_bounds__(CS_THREADS)
 colsum_kernel(const float *__restrict__ x, int N, const tspws_csum_item_t *__restrict__ items,
-              double *__restrict__ part, float *__restrict__ rowpart, int rowpart_ld)
+              double *part, const int *__restrict__ slot_off, unsigned int *tickets,
+              double *__restrict__ gsum, double *__restrict__ gtile)
 {
+    __shared__ double sh[33];
+    __shared__ int is_last;
     const tspws_csum_item_t it = items[blockIdx.y];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c0, c1, c2, c3;                                   /* the four columns this thread owns */
 
     if (VEC) {
         const int  col    = blockIdx.x * CS_TILE + threadIdx.x * 4;
         const bool active = col < N;                       /* N % 4 == 0 on this path */
+        c0 = col; c1 = col + 1; c2 = col + 2; c3 = col + 3;
         const float *p = x + (size_t)it.t0 * N + (active ? col : 0);
         int t = it.t0;
         for (; t + CS_UNROLL <= it.t1; t += CS_UNROLL) {
@@ -206,146 +214,112 @@ colsum_kernel(const float *__restrict__ x, int N, const tspws_csum_item_t *__res
             for (int j = 0; j < CS_UNROLL; j++) v[j] = ld_stream4(p + (size_t)j * N);
 #pragma unroll
             for (int j = 0; j < CS_UNROLL; j++) {
-                if (!active) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 a0 += (double)v[j].x; a1 += (double)v[j].y; a2 += (double)v[j].z; a3 += (double)v[j].w;
-                if (ROWSUM) {
-                    float r = warp_sum((v[j].x + v[j].y) + (v[j].z + v[j].w));
-                    if (lane == 0) rowpart[(size_t)(t + j) * rowpart_ld + blockIdx.x * (CS_THREADS / 32) + warp] = r;
-                }
             }
             p += (size_t)CS_UNROLL * N;
         }
         for (; t < it.t1; t++) {
-            float4 v = ld_stream4(p);
-            if (!active) v = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v = ld_stream4(p);
             a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
-            if (ROWSUM) {
-                float r = warp_sum((v.x + v.y) + (v.z + v.w));
-                if (lane == 0) rowpart[(size_t)t * rowpart_ld + blockIdx.x * (CS_THREADS / 32) + warp] = r;
-            }
             p += N;
         }
-        if (active) {
-            double *o = part + (size_t)it.slot * N + col;
-            reinterpret_cast<double2 *>(o)[0] = make_double2(a0, a1);
-            reinterpret_cast<double2 *>(o)[1] = make_double2(a2, a3);
-        }
+        if (!active) { a0 = a1 = a2 = a3 = 0.0; }
     } else {
         /* generic path: any N, any alignment; thread owns columns base + j*256 */
         const int base = blockIdx.x * CS_TILE + threadIdx.x;
+        c0 = base; c1 = base + 256; c2 = base + 512; c3 = base + 768;
         for (int t = it.t0; t < it.t1; t++) {
             const float *p = x + (size_t)t * N;
-            float v0 = base < N ? ld_stream1(p + base) : 0.f;
-            float v1 = base + 256 < N ? ld_stream1(p + base + 256) : 0.f;
-            float v2 = base + 512 < N ? ld_stream1(p + base + 512) : 0.f;
-            float v3 = base + 768 < N ? ld_stream1(p + base + 768) : 0.f;
-            a0 += (double)v0; a1 += (double)v1; a2 += (double)v2; a3 += (double)v3;
-            if (ROWSUM) {
-                float r = warp_sum((v0 + v1) + (v2 + v3));
-                if (lane == 0) rowpart[(size_t)t * rowpart_ld + blockIdx.x * (CS_THREADS / 32) + warp] = r;
-            }
+            a0 += c0 < N ? (double)ld_stream1(p + c0) : 0.0;
+            a1 += c1 < N ? (double)ld_stream1(p + c1) : 0.0;
+            a2 += c2 < N ? (double)ld_stream1(p + c2) : 0.0;
+            a3 += c3 < N ? (double)ld_stream1(p + c3) : 0.0;
         }
-        double *o = part + (size_t)it.slot * N;
-        if (base < N)       o[base]       = a0;
-        if (base + 256 < N) o[base + 256] = a1;
-        if (base + 512 < N) o[base + 512] = a2;
-        if (base + 768 < N) o[base + 768] = a3;
     }
+
+    const int s_begin = slot_off[it.group], s_end = slot_off[it.group + 1];
+    if (s_end - s_begin > 1) {
+        /* publish this item's partial, then take a ticket for (group, tile) */
+        double *o = part + (size_t)it.slot * N;
+        if (c0 < N) o[c0] = a0;
+        if (c1 < N) o[c1] = a1;
+        if (c2 < N) o[c2] = a2;
+        if (c3 < N) o[c3] = a3;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int n = atomicAdd(&tickets[it.group * gridDim.x + blockIdx.x], 1u);
+            is_last = (n == (unsigned int)(s_end - s_begin - 1));
+            if (is_last) tickets[it.group * gridDim.x + blockIdx.x] = 0;      /* re-arm for the next launch */
+        }
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        a0 = a1 = a2 = a3 = 0.0;
+        for (int sidx = s_begin; sidx < s_end; sidx++) {   /* fixed order: deterministic */
+            const double *q = part + (size_t)sidx * N;
+            if (c0 < N) a0 += __ldcg(q + c0);
+            if (c1 < N) a1 += __ldcg(q + c1);
+            if (c2 < N) a2 += __ldcg(q + c2);
+            if (c3 < N) a3 += __ldcg(q + c3);
+        }
+    }
+    double *go = gsum + (size_t)it.group * N;
+    if (c0 < N) go[c0] = a0;
+    if (c1 < N) go[c1] = a1;
+    if (c2 < N) go[c2] = a2;
+    if (c3 < N) go[c3] = a3;
+    const double tot = block_sum((a0 + a1) + (a2 + a3), sh);
+    if (threadIdx.x == 0) gtile[it.group * gridDim.x + blockIdx.x] = tot;
 }
 
 extern "C" int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t *d_items, int nitems,
-                               double *d_part, float *d_rowpart, int rowpart_ld, tspws_stream_t st)
+                               double *d_part, const int *d_slot_off, unsigned int *d_tickets,
+                               double *d_gsum, double *d_gtile, tspws_stream_t st)
 {
     if (nitems <= 0) return 0;
     dim3 grid((N + CS_TILE - 1) / CS_TILE, nitems);
     const bool vec = (N % 4 == 0) && (((uintptr_t)d_x & 15) == 0);
     cudaStream_t s = (cudaStream_t)st;
-    if (vec) {
-        if (d_rowpart) colsum_kernel<true, true><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_rowpart, rowpart_ld);
-        else           colsum_kernel<true, false><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_rowpart, rowpart_ld);
-    } else {
-        if (d_rowpart) colsum_kernel<false, true><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_rowpart, rowpart_ld);
-        else           colsum_kernel<false, false><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_rowpart, rowpart_ld);
-    }
+    if (vec) colsum_kernel<true><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_slot_off, d_tickets, d_gsum, d_gtile);
+    else     colsum_kernel<false><<<grid, CS_THREADS, 0, s>>>(d_x, N, d_items, d_part, d_slot_off, d_tickets, d_gsum, d_gtile);
     TSPWS_LAUNCHED_N("colsum_kernel", s);
     return 0;
 }
 
-/* Per-trace mean, float-cast like the reference (src/ts_pws1f_lib.c:165-166): one warp per trace
- * sums the row partials left by colsum_kernel. */
+/* Group post-processing on the (already reduced, possibly all-reduced) group sums:
+ *   mean removal : the reference subtracts every trace's mean from its samples
+ *                  (src/ts_pws1f_lib.c:160-168); summed over a group that is the constant
+ *                  sum_t mean_t = (1/N) sum_n G[n], taken here from the tile totals;
+ *   fold         : 0.5 (G[n] + G[N-1-n]) (src/ts_pws1f_lib.c:76-86), linear as well;
+ * and the fp32 copy the fp32 transform reads.  grid = (tiles over ceil(N/2), G). */
 __global__ void __launch_bounds__(256)
-rowmean_kernel(const float *__restrict__ rowpart, int rowpart_ld, int rowpart_n, int ntr, int N,
-               float *__restrict__ mean)
-{
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= ntr) return;
-    const float *r = rowpart + (size_t)t * rowpart_ld;
-    double s = 0.0;
-    for (int j = threadIdx.x & 31; j < rowpart_n; j += 32) s += (double)r[j];
-    s = warp_sum(s);
-    if ((threadIdx.x & 31) == 0) mean[t] = (float)(s / (double)(unsigned int)N);
-}
-
-/* gsum[g][n] = sum over the group's partial slots - sum over the group's traces of their mean
- * (the reference subtracts the float-cast mean from every sample, :167; summed over a group that
- * is this constant).  grid = (n tiles, G). */
-__global__ void __launch_bounds__(256)
-colsum_finalize_kernel(const double *__restrict__ part, const int *__restrict__ slot_off, int N,
-                       const float *__restrict__ mean, const int *__restrict__ grp_t0,
-                       double *__restrict__ gsum)
-{
-    __shared__ double sh[33];
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = blockIdx.y;
-    double corr = 0.0;
-    if (mean) {
-        double m = 0.0;
-        for (int t = grp_t0[g] + threadIdx.x; t < grp_t0[g + 1]; t += blockDim.x) m += (double)mean[t];
-        corr = block_sum(m, sh);
-    }
-    if (n >= N) return;
-    double a = 0.0;
-    for (int s = slot_off[g]; s < slot_off[g + 1]; s++) a += part[(size_t)s * N + n];
-    gsum[(size_t)g * N + n] = a - corr;
-}
-
-extern "C" int tspws_cu_colsum_finalize(const double *d_part, const int *d_slot_off, int G, int N,
-                                        const float *d_rowpart, int rowpart_ld, int rowpart_n,
-                                        const int *d_grp_t0, int ntr, float *d_mean, double *d_gsum,
-                                        tspws_stream_t st)
-{
-    cudaStream_t s = (cudaStream_t)st;
-    if (d_rowpart && ntr > 0) {
-        rowmean_kernel<<<(ntr + 7) / 8, 256, 0, s>>>(d_rowpart, rowpart_ld, rowpart_n, ntr, N, d_mean);
-        TSPWS_LAUNCHED_N("rowmean_kernel", s);
-    }
-    dim3 grid((N + 255) / 256, G);
-    colsum_finalize_kernel<<<grid, 256, 0, s>>>(d_part, d_slot_off, N, d_rowpart ? d_mean : nullptr, d_grp_t0, d_gsum);
-    TSPWS_LAUNCHED_N("colsum_finalize_kernel", s);
-    return 0;
-}
-
-/* Fold the (already reduced) group sums -- fold is linear, so folding Kmax sums equals summing
- * folded traces -- and emit the fp32 copy the fp32 transform reads. grid = (tiles over ceil(N/2), G). */
-__global__ void __launch_bounds__(256)
-group_post_kernel(double *__restrict__ gsum, float *__restrict__ gsum32, int N, int do_fold)
+group_post_kernel(double *__restrict__ gsum, float *__restrict__ gsum32, int N,
+                  const double *__restrict__ gtile, int ntile, int do_rm, int do_fold)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = (N + 1) / 2;
+    double corr = 0.0;
+    if (do_rm) {
+        for (int i = 0; i < ntile; i++) corr += gtile[blockIdx.y * ntile + i];   /* same order in every thread */
+        corr /= (double)(unsigned int)N;
+    }
     if (n >= half) return;
     double *g = gsum + (size_t)blockIdx.y * N;
     float  *f = gsum32 + (size_t)blockIdx.y * N;
     const int r = N - 1 - n;
-    double a = g[n], b = g[r];
-    if (do_fold && r != n) { a = 0.5 * (a + b); b = a; g[n] = a; g[r] = a; }
+    double a = g[n] - corr, b = g[r] - corr;
+    if (do_fold && r != n) { a = 0.5 * (a + b); b = a; }
+    g[n] = a; g[r] = b;
     f[n] = (float)a;
     f[r] = (float)b;
 }
 
-extern "C" int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N, int do_fold, tspws_stream_t st)
+extern "C" int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N, const double *d_gtile,
+                                   int ntile, int do_rm, int do_fold, tspws_stream_t st)
 {
     dim3 grid(((N + 1) / 2 + 255) / 256, G);
-    group_post_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(d_gsum, d_gsum32, N, do_fold);
+    group_post_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(d_gsum, d_gsum32, N, d_gtile, ntile, do_rm, do_fold);
     TSPWS_LAUNCHED_N("group_post_kernel", (cudaStream_t)st);
     return 0;
 }
@@ -748,12 +722,13 @@ fwd2_acc_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restri
 {
     extern __shared__ float fw_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = item_begin + blockIdx.x * FW_WARPS + w;
+    /* blockIdx.x = chunk (fastest): CTAs running together share the item's filter rows in L1/L2 */
+    const int idx = item_begin + blockIdx.y * FW_WARPS + w;
     if (idx >= item_end) return;
     const tspws_fwd2_item_t it = items[idx];
     const tspws_scale_t sc = scales[it.s];
-    const int k0 = blockIdx.y * chunk, k1 = min(ntr, k0 + chunk);
-    fwd2_body<LG, false>(sc, it, g_all, x, N, k0, k1, ncoef, blockIdx.y, part_ps, part_st, nullptr, 0,
+    const int k0 = blockIdx.x * chunk, k1 = min(ntr, k0 + chunk);
+    fwd2_body<LG, false>(sc, it, g_all, x, N, k0, k1, ncoef, blockIdx.x, part_ps, part_st, nullptr, 0,
                          fw_smem + (size_t)w * smem_per_warp, smem_per_warp / 2, lane);
 }
 
@@ -767,11 +742,13 @@ fwd2_pertrace_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__r
 {
     extern __shared__ float fw_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * FW_WARPS + w;
+    /* blockIdx.x = trace (fastest): the traces of one item run together -> one code variant and
+     * one set of filter rows live at a time */
+    const int idx = blockIdx.y * FW_WARPS + w;
     if (idx >= nitems) return;
     const tspws_fwd2_item_t it = items[idx];
     const tspws_scale_t sc = scales[it.s];
-    const int k = blockIdx.y;
+    const int k = blockIdx.x;
     float *xs = fw_smem + (size_t)w * smem_per_warp;
     switch (sc.lg) {
     case 0: fwd2_body<0, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
@@ -834,7 +811,7 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
 #define FW_ACC_LAUNCH(LGV)                                                                              \
     if (f->fw_lg_begin[LGV + 1] > f->fw_lg_begin[LGV]) {                                                \
         const int nb = f->fw_lg_begin[LGV + 1] - f->fw_lg_begin[LGV];                                   \
-        dim3 grid((nb + FW_WARPS - 1) / FW_WARPS, nchunk);                                              \
+        dim3 grid(nchunk, (nb + FW_WARPS - 1) / FW_WARPS);                                              \
         if (smem > 48 * 1024)                                                                           \
             cudaFuncSetAttribute(fwd2_acc_kernel<LGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         fwd2_acc_kernel<LGV><<<grid, FW_WARPS * 32, (LGV < 5 ? smem : 0), s>>>(f->d_scale, (const float2 *)f->d_g32, \
@@ -867,7 +844,7 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
         const size_t smem = (size_t)f->fw_smem_per_warp * FW_WARPS * sizeof(float);
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(fwd2_pertrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid((f->nitems2 + FW_WARPS - 1) / FW_WARPS, ntr);
+        dim3 grid(ntr, (f->nitems2 + FW_WARPS - 1) / FW_WARPS);
         fwd2_pertrace_kernel<<<grid, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, f->d_items2,
             f->nitems2, d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp);
         TSPWS_LAUNCHED_N("fwd2_pertrace_kernel", s);
@@ -893,13 +870,27 @@ phasor_combine_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__
     const int sg = blockIdx.z;
     float pr = 0.f, pi = 0.f;
     double sr = 0.0, si = 0.0;
-    for (int k = 0; k < seg; k++) {
-        const float2 *yp = ypart + (size_t)(sg * seg + k) * ypart_len + sc.ypart_off + m;
-        float re = 0.f, im = 0.f;
-        for (int sp = 0; sp < sc.nsplit; sp++) { const float2 y = yp[(size_t)sp * sc.Ns]; re += y.x; im += y.y; }
-        float a, b;
-        phasor_fast(re, im, a, b);
-        pr += a; pi += b; sr += (double)re; si += (double)im;
+    const float2 *yp0 = ypart + (size_t)sg * seg * ypart_len + sc.ypart_off + m;
+    for (int kb = 0; kb < seg; kb += 8) {             /* 8 traces per batch: all loads in flight first */
+        float2 y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[i] = make_float2(0.f, 0.f);
+        for (int sp = 0; sp < sc.nsplit; sp++) {
+            float2 t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                t[i] = (kb + i < seg) ? __ldcg(yp0 + (size_t)(kb + i) * ypart_len + (size_t)sp * sc.Ns) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { y[i].x += t[i].x; y[i].y += t[i].y; }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (kb + i < seg) {
+                float a, b;
+                phasor_fast(y[i].x, y[i].y, a, b);
+                pr += a; pi += b; sr += (double)y[i].x; si += (double)y[i].y;
+            }
+        }
     }
     const double f = weight_factor(rules[sg], (double)pr, (double)pi);
     const size_t o = (size_t)sg * ncoef + sc.coef_off + m;
@@ -1001,66 +992,74 @@ __global__ void __launch_bounds__(256)
 inv_kernel(const tspws_scale_t *__restrict__ scales, const typename cplx<T>::type *__restrict__ wall,
            const tspws_inv_group_t *__restrict__ groups, int ninv, int N, int ncoef,
            const typename cplx<T>::type *__restrict__ zout, const typename cplx<T>::type *__restrict__ st,
-           T *__restrict__ scratch, int nseg)
+           T *scratch, int nseg, unsigned int *tickets, const tspws_weight_t *__restrict__ rules,
+           float *__restrict__ out_ts, float *__restrict__ out_ls)
 {
     typedef typename cplx<T>::type T2;
+    __shared__ int is_last;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
     const tspws_inv_group_t grp = groups[blockIdx.y];
     const int sg = blockIdx.z;
     const T2 *__restrict__ Z = zout + (size_t)sg * ncoef;
     const T2 *__restrict__ S = WITH_ST ? st + (size_t)sg * ncoef : nullptr;
     T accz = 0, accs = 0;
-    for (int s = grp.s0; s < grp.s1; s++) {
-        const tspws_scale_t sc = scales[s];
-        const T2 *__restrict__ w  = wall + sc.tap_off;
-        const T2 *__restrict__ Zs = Z + sc.coef_off;
-        const T2 *__restrict__ Ss = WITH_ST ? S + sc.coef_off : nullptr;
-        T az = 0, as = 0;
+    if (n < N) {
+        for (int s = grp.s0; s < grp.s1; s++) {
+            const tspws_scale_t sc = scales[s];
+            const T2 *__restrict__ w  = wall + sc.tap_off;
+            const T2 *__restrict__ Zs = Z + sc.coef_off;
+            const T2 *__restrict__ Ss = WITH_ST ? S + sc.coef_off : nullptr;
+            T az = 0, as = 0;
+            const int top = (sc.Ns - 1) * sc.D;                     /* position of the last coefficient */
 #pragma unroll 1
-        for (int j = -1; j <= 1; j++) {
-            const long long base = (long long)n + sc.c + (long long)j * N;   /* l = base - m D */
-            if (base < 0) continue;
-            long long hi = base / sc.D;
-            if (hi > sc.Ns - 1) hi = sc.Ns - 1;
-            const long long lnum = base - (sc.L - 1);
-            long long lo = lnum <= 0 ? 0 : (lnum + sc.D - 1) / sc.D;
-            int l = (int)(base - lo * sc.D);
-            for (int m = (int)lo; m <= (int)hi; m++, l -= sc.D) {
-                const T2 wv = w[l];
-                const T2 z  = Zs[m];
-                az = fma(z.x, wv.x, az);
-                az = fma(-z.y, wv.y, az);
-                if (WITH_ST) {
-                    const T2 q = Ss[m];
-                    as = fma(q.x, wv.x, as);
-                    as = fma(-q.y, wv.y, as);
+            for (int j = -1; j <= 1; j++) {
+                const int base = n + sc.c + j * N;                  /* l = base - m D; |base| < 3N fits an int */
+                const int lnum = base - (sc.L - 1);
+                if (base < 0 || lnum > top) continue;               /* no coefficient reaches n in this image */
+                int hi = (int)((unsigned int)base / (unsigned int)sc.D);
+                if (hi > sc.Ns - 1) hi = sc.Ns - 1;
+                const int lo = lnum <= 0 ? 0 : (int)(((unsigned int)lnum + sc.D - 1) / (unsigned int)sc.D);
+                const T2 *wp = w + (base - lo * sc.D);              /* walks down by D taps per coefficient */
+                const T2 *zp = Zs + lo;
+                const ptrdiff_t sd = WITH_ST ? (Ss - Zs) : 0;
+#pragma unroll 4
+                for (int cnt = hi - lo + 1; cnt > 0; cnt--, wp -= sc.D, zp++) {
+                    const T2 wv = *wp;
+                    const T2 z  = *zp;
+                    az = fma(z.x, wv.x, az);
+                    az = fma(-z.y, wv.y, az);
+                    if (WITH_ST) {
+                        const T2 q = zp[sd];
+                        as = fma(q.x, wv.x, as);
+                        as = fma(-q.y, wv.y, as);
+                    }
                 }
             }
+            accz = fma((T)sc.gain, az, accz);
+            accs = fma((T)sc.gain, as, accs);
         }
-        accz = fma((T)sc.gain, az, accz);
-        accs = fma((T)sc.gain, as, accs);
+        const size_t o = ((size_t)blockIdx.y * nseg + sg) * N + n;
+        scratch[o] = accz;
+        if (WITH_ST) scratch[(size_t)ninv * nseg * N + o] = accs;
     }
-    const size_t o = ((size_t)blockIdx.y * nseg + sg) * N + n;
-    scratch[o] = accz;
-    if (WITH_ST) scratch[(size_t)ninv * nseg * N + o] = accs;
-}
-
-/* Sum the scale-group partials, cast like src/ts_pws1f_lib.c:233-241: tsPWS = (float)x,
- * ls = (float)x / mtr (float division). */
-template <typename T, bool WITH_ST>
-__global__ void __launch_bounds__(256)
-inv_finish_kernel(const T *__restrict__ scratch, int ninv, int nseg, int N,
-                  const tspws_weight_t *__restrict__ rules, float *__restrict__ out_ts, float *__restrict__ out_ls)
-{
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const int sg = blockIdx.y;
+    /* the last scale group to finish this tile of samples adds the partials in group order and
+     * casts like src/ts_pws1f_lib.c:233-241: tsPWS = (float)x, ls = (float)x / mtr (float division) */
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int *tk = &tickets[sg * gridDim.x + blockIdx.x];
+        const unsigned int c = atomicAdd(tk, 1u);
+        is_last = (c == gridDim.y - 1);
+        if (is_last) *tk = 0;
+    }
+    __syncthreads();
+    if (!is_last || n >= N) return;
+    __threadfence();
     double az = 0, as = 0;
     for (int g = 0; g < ninv; g++) {
         const size_t o = ((size_t)g * nseg + sg) * N + n;
-        az += (double)scratch[o];
-        if (WITH_ST) as += (double)scratch[(size_t)ninv * nseg * N + o];
+        az += (double)__ldcg(scratch + o);
+        if (WITH_ST) as += (double)__ldcg(scratch + (size_t)ninv * nseg * N + o);
     }
     out_ts[(size_t)sg * N + n] = (float)az;
     if (WITH_ST) out_ls[(size_t)sg * N + n] = __fdiv_rn((float)as, (float)(unsigned int)rules[sg].T);
@@ -1068,34 +1067,28 @@ inv_finish_kernel(const T *__restrict__ scratch, int ninv, int nseg, int N,
 
 template <typename T>
 static int inv_launch(const tspws_devframe_t *f, const void *d_zout, const void *d_st, int nseg,
-                      const tspws_weight_t *d_rules, void *d_scratch, float *d_ts, float *d_ls, cudaStream_t s)
+                      const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
+                      float *d_ts, float *d_ls, cudaStream_t s)
 {
     typedef typename cplx<T>::type T2;
     const T2 *w = (const T2 *)(sizeof(T) == 4 ? f->d_w32 : f->d_w64);
     dim3 grid((f->N + 255) / 256, f->ninv, nseg);
-    dim3 gridf((f->N + 255) / 256, nseg);
-    if (d_st) {
+    if (d_st)
         inv_kernel<T, true><<<grid, 256, 0, s>>>(f->d_scale, w, f->d_invgrp, f->ninv, f->N, f->ncoef,
-            (const T2 *)d_zout, (const T2 *)d_st, (T *)d_scratch, nseg);
-        TSPWS_LAUNCHED_N("inv_kernel", s);
-        inv_finish_kernel<T, true><<<gridf, 256, 0, s>>>((const T *)d_scratch, f->ninv, nseg, f->N, d_rules, d_ts, d_ls);
-        TSPWS_LAUNCHED_N("inv_finish_kernel", s);
-    } else {
+            (const T2 *)d_zout, (const T2 *)d_st, (T *)d_scratch, nseg, d_tickets, d_rules, d_ts, d_ls);
+    else
         inv_kernel<T, false><<<grid, 256, 0, s>>>(f->d_scale, w, f->d_invgrp, f->ninv, f->N, f->ncoef,
-            (const T2 *)d_zout, nullptr, (T *)d_scratch, nseg);
-        TSPWS_LAUNCHED_N("inv_kernel", s);
-        inv_finish_kernel<T, false><<<gridf, 256, 0, s>>>((const T *)d_scratch, f->ninv, nseg, f->N, d_rules, d_ts, d_ls);
-        TSPWS_LAUNCHED_N("inv_finish_kernel", s);
-    }
+            (const T2 *)d_zout, nullptr, (T *)d_scratch, nseg, d_tickets, d_rules, d_ts, d_ls);
+    TSPWS_LAUNCHED_N("inv_kernel", s);
     return 0;
 }
 
 extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, const void *d_st, int acc64,
-                                int nseg, const tspws_weight_t *d_rules, void *d_scratch,
+                                int nseg, const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
                                 float *d_out_ts, float *d_out_ls, tspws_stream_t st)
 {
     if (nseg <= 0) return 0;
     if (acc64 && !f->d_w64) return (int)cudaErrorInvalidValue;
-    return acc64 ? inv_launch<double>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_out_ts, d_out_ls, (cudaStream_t)st)
-                 : inv_launch<float>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_out_ts, d_out_ls, (cudaStream_t)st);
+    return acc64 ? inv_launch<double>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_tickets, d_out_ts, d_out_ls, (cudaStream_t)st)
+                 : inv_launch<float>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_tickets, d_out_ts, d_out_ls, (cudaStream_t)st);
 }

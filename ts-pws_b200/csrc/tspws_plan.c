@@ -6,8 +6,8 @@
  * allocation, no host round trip and no synchronisation:
  *
  *   two-stage (Kmax groups, reference src/ts_pws1f_lib.c:212-222):
- *     reduce : colsum -> [rowmean] -> finalize                  => exchange = fp64 group sums
- *     finish : group_post(fold, fp32) -> forward(Kmax traces) -> reduce+weight -> inverse
+ *     reduce : colsum (last-block combine)                      => exchange = fp64 group sums
+ *     finish : group_post(mean, fold, fp32) -> forward(Kmax traces) -> reduce+weight -> inverse
  *   single-stage (reference src/ts_pws1f_lib.c:209-211):
  *     reduce : prep(fold, rm, in place) -> forward(all traces) -> reduce+weight
  *                                                                => exchange = PS | ST sums
@@ -37,11 +37,12 @@ struct tspws_plan {
     tspws_devframe_t  dev;
     tspws_weight_t    rule, *d_rule;
     /* two-stage */
-    int    ncs, rowpart_ld, rowpart_n;
+    int    ncs, ntile;
     tspws_csum_item_t *d_cs;
     int    *d_slot_off, *d_grp_t0;
-    double *d_part, *d_gsum;
-    float  *d_rowpart, *d_gsum32, *d_mean;
+    double *d_part, *d_gsum, *d_gtile;      /* gsum [K][N] and gtile [K][ntile] are one block */
+    float  *d_gsum32;
+    unsigned int *d_tickets, *d_inv_tickets;
     /* forward / weights / inverse */
     int    chunk, nchunk, ntr_fwd;
     void  *d_pps, *d_pst, *d_exch, *d_zout, *d_invscratch, *d_ypart;
@@ -146,7 +147,9 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
             }
             if (sc[s].lg == 5 && per_trace) {
                 const int nblk = (D + 31) / 32;
-                sc[s].nsplit = (nblk + pbmax - 1) / pbmax;
+                int pb = pbmax;
+                if ((nblk + pb - 1) / pb > 8) pb = (nblk + 7) / 8;      /* at most 8 partial slots per scale */
+                sc[s].nsplit = (nblk + pb - 1) / pb;
             }
             sc[s].ypart_off = ypart;
             ypart += sc[s].nsplit * Ns;
@@ -211,7 +214,7 @@ static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
 
     /* inverse: split the scales into groups of about equal taps per output sample */
     {
-        int want = (int)env_long("TSPWS_INV_GROUPS", 8);
+        int want = (int)env_long("TSPWS_INV_GROUPS", 16);
         if (want > S) want = S;
         if (want < 1) want = 1;
         grp = (tspws_inv_group_t *)calloc(want, sizeof(*grp));
@@ -300,17 +303,18 @@ static int twostage_build(tspws_plan_t *pl)
         if (t != n) { fprintf(stderr, "tspws_b200: internal error, group runs do not cover the shard\n"); goto done; }
     }
     pl->ncs = ni;
-    pl->rowpart_n  = ntiles * 8;
-    pl->rowpart_ld = pl->rowpart_n;
+    pl->ntile = ntiles;
     const size_t N = (size_t)pl->N;
     if (cudaMalloc((void **)&pl->d_cs, (ni ? ni : 1) * sizeof(*it)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&pl->d_slot_off, (K + 1) * sizeof(int)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&pl->d_grp_t0, (K + 1) * sizeof(int)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&pl->d_part, (ni ? ni : 1) * N * sizeof(double)) != cudaSuccess) goto done;
-    if (cudaMalloc((void **)&pl->d_mean, (size_t)(n ? n : 1) * sizeof(float)) != cudaSuccess) goto done;
-    if (cudaMalloc((void **)&pl->d_gsum, K * N * sizeof(double)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_tickets, (size_t)K * ntiles * sizeof(unsigned int)) != cudaSuccess) goto done;
+    if (cudaMemset(pl->d_tickets, 0, (size_t)K * ntiles * sizeof(unsigned int)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_gsum, (K * N + (size_t)K * ntiles) * sizeof(double)) != cudaSuccess) goto done;
+    if (cudaMemset(pl->d_gsum, 0, (K * N + (size_t)K * ntiles) * sizeof(double)) != cudaSuccess) goto done;
+    pl->d_gtile = pl->d_gsum + K * N;
     if (cudaMalloc((void **)&pl->d_gsum32, K * N * sizeof(float)) != cudaSuccess) goto done;
-    if (pl->p.lrm && cudaMalloc((void **)&pl->d_rowpart, (size_t)(n ? n : 1) * pl->rowpart_ld * sizeof(float)) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_cs, it, ni * sizeof(*it), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_slot_off, slot_off, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_grp_t0, grp_t0, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
@@ -325,9 +329,9 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     if (!pl) return;
     devframe_free(&pl->dev);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
-    cudaFree(pl->d_part); cudaFree(pl->d_mean); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
-    cudaFree(pl->d_rowpart); cudaFree(pl->d_pps); cudaFree(pl->d_pst); cudaFree(pl->d_exch);
-    cudaFree(pl->d_zout); cudaFree(pl->d_invscratch); cudaFree(pl->d_ypart);
+    cudaFree(pl->d_part); cudaFree(pl->d_tickets); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
+    cudaFree(pl->d_pps); cudaFree(pl->d_pst); cudaFree(pl->d_exch);
+    cudaFree(pl->d_zout); cudaFree(pl->d_invscratch); cudaFree(pl->d_ypart); cudaFree(pl->d_inv_tickets);
     tspws_b200_frame_destroy(pl->fr);
     free(pl);
 }
@@ -379,6 +383,8 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     CK(cudaMalloc(&pl->d_zout, ncoef * pl->csz));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.ninv ? pl->dev.ninv : 1) * max * (pl->csz / 2)));
     CK(cudaMemset(pl->d_exch, 0, 2 * ncoef * pl->csz));
+    CK(cudaMalloc((void **)&pl->d_inv_tickets, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
+    CK(cudaMemset(pl->d_inv_tickets, 0, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
     return pl;
 fail:
     tspws_b200_plan_destroy(pl);
@@ -395,11 +401,10 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     pl->summed_across_ranks = 0;
     tspws_cu_profile_mark(stream);
     if (pl->two_stage) {
-        if ((e = tspws_cu_colsum(d_sigall, pl->N, pl->d_cs, pl->ncs, pl->d_part,
-                                 pl->p.lrm ? pl->d_rowpart : NULL, pl->rowpart_ld, stream))) return TSPWS_ERR_CUDA;
-        if ((e = tspws_cu_colsum_finalize(pl->d_part, pl->d_slot_off, (int)pl->K, pl->N,
-                                          pl->p.lrm ? pl->d_rowpart : NULL, pl->rowpart_ld, pl->rowpart_n,
-                                          pl->d_grp_t0, (int)pl->mtr_local, pl->d_mean, pl->d_gsum, stream))) return TSPWS_ERR_CUDA;
+        if (pl->mtr_local != pl->mtr_total)   /* groups without local traces must contribute zeros */
+            if (cudaMemsetAsync(pl->d_gsum, 0, tspws_b200_plan_exchange_bytes(pl), (cudaStream_t)stream) != cudaSuccess) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_colsum(d_sigall, pl->N, pl->d_cs, pl->ncs, pl->d_part, pl->d_slot_off, pl->d_tickets,
+                                 pl->d_gsum, pl->d_gtile, stream))) return TSPWS_ERR_CUDA;
         return 0;
     }
     if ((e = tspws_cu_prep(d_sigall, (int)pl->mtr_local, pl->N, pl->p.fold, pl->p.lrm, stream))) return TSPWS_ERR_CUDA;
@@ -418,7 +423,8 @@ void *tspws_b200_plan_exchange_ptr(tspws_plan_t *pl)
 size_t tspws_b200_plan_exchange_bytes(tspws_plan_t *pl)
 {
     if (!pl) return 0;
-    return pl->two_stage ? (size_t)pl->K * pl->N * sizeof(double) : 2 * pl->fr->ncoef * pl->csz;
+    return pl->two_stage ? ((size_t)pl->K * pl->N + (size_t)pl->K * pl->ntile) * sizeof(double)
+                         : 2 * pl->fr->ncoef * pl->csz;
 }
 int tspws_b200_plan_exchange_is_f64(tspws_plan_t *pl) { return pl && pl->two_stage; }
 
@@ -428,7 +434,8 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     int e;
     tspws_cu_profile_mark(stream);
     if (pl->two_stage) {
-        if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, (int)pl->K, pl->N, pl->p.fold, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, (int)pl->K, pl->N, pl->d_gtile, pl->ntile,
+                                     pl->p.lrm, pl->p.fold, stream))) return TSPWS_ERR_CUDA;
         if (pl->dev.per_trace) {
             if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
             if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule,
@@ -442,7 +449,7 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
         if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), 0, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     }
     if ((e = tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), pl->acc64, 1, pl->d_rule, pl->d_invscratch,
-                              d_tspws, d_ls, stream))) return TSPWS_ERR_CUDA;
+                              pl->d_inv_tickets, d_tspws, d_ls, stream))) return TSPWS_ERR_CUDA;
     return 0;
 }
 
