@@ -210,6 +210,10 @@ int tspws_b200_plan_reduce(tspws_plan_t *plan, float *d_sigall, void *stream);
 void  *tspws_b200_plan_exchange_ptr(tspws_plan_t *plan);
 size_t tspws_b200_plan_exchange_bytes(tspws_plan_t *plan);
 int    tspws_b200_plan_exchange_is_f64(tspws_plan_t *plan);
+/* Use a caller-owned device buffer (>= exchange_bytes) as the exchange block, so that e.g.
+ * torch.distributed / NCCL can all-reduce it in place; then tell the plan it has been summed. */
+int    tspws_b200_plan_bind_exchange(tspws_plan_t *plan, void *d_buf);
+int    tspws_b200_plan_mark_exchanged(tspws_plan_t *plan);
 /* Phase B (replicated): transforms of the group sums (two-stage), weighting, two inverse
  * frame transforms.  d_ls / d_tspws: device pointers [max] fp32. */
 int tspws_b200_plan_finish(tspws_plan_t *plan, float *d_ls, float *d_tspws, void *stream);

@@ -155,6 +155,10 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_plan_exchange_bytes.argtypes = [C.c_void_p]
     lib.tspws_b200_plan_exchange_is_f64.restype = C.c_int
     lib.tspws_b200_plan_exchange_is_f64.argtypes = [C.c_void_p]
+    lib.tspws_b200_plan_bind_exchange.restype = C.c_int
+    lib.tspws_b200_plan_bind_exchange.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tspws_b200_plan_mark_exchanged.restype = C.c_int
+    lib.tspws_b200_plan_mark_exchanged.argtypes = [C.c_void_p]
     lib.tspws_b200_plan_finish.restype = C.c_int
     lib.tspws_b200_plan_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tspws_b200_plan_stack.restype = C.c_int
@@ -179,7 +183,7 @@ EXPORTS = [
     "tspws_b200_get_option", "tspws_b200_device_count", "tspws_b200_shutdown", "tspws_b200_version",
     "tspws_b200_kernel_launches", "tspws_b200_profile", "tspws_b200_profile_reset", "tspws_b200_profile_read", "tspws_b200_plan_create", "tspws_b200_plan_destroy",
     "tspws_b200_plan_reduce", "tspws_b200_plan_exchange_ptr", "tspws_b200_plan_exchange_bytes",
-    "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
+    "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
     "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",
 ]
 

@@ -47,6 +47,8 @@ struct tspws_plan {
     int    chunk, nchunk, ntr_fwd;
     void  *d_pps, *d_pst, *d_exch, *d_zout, *d_invscratch, *d_ypart;
     int    summed_across_ranks;
+    int    exch_bound;              /* exchange block belongs to the caller */
+    void  *own_gsum, *own_exch;
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -327,6 +329,7 @@ done:
 void tspws_b200_plan_destroy(tspws_plan_t *pl)
 {
     if (!pl) return;
+    if (pl->exch_bound) { pl->d_gsum = (double *)pl->own_gsum; pl->d_exch = pl->own_exch; }
     devframe_free(&pl->dev);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
     cudaFree(pl->d_part); cudaFree(pl->d_tickets); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
@@ -417,8 +420,32 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
 void *tspws_b200_plan_exchange_ptr(tspws_plan_t *pl)
 {
     if (!pl) return NULL;
-    pl->summed_across_ranks = 1;          /* the caller is about to all-reduce it */
     return pl->two_stage ? (void *)pl->d_gsum : pl->d_exch;
+}
+
+/* Use a caller-owned device buffer (>= exchange_bytes, 16 B aligned) as the exchange block, e.g. a
+ * torch tensor that torch.distributed can all-reduce in place. */
+int tspws_b200_plan_bind_exchange(tspws_plan_t *pl, void *d_buf)
+{
+    if (!pl || !d_buf) return TSPWS_ERR_NULL;
+    if ((size_t)d_buf & 15) return TSPWS_ERR_ARG;
+    if (!pl->exch_bound) { pl->own_gsum = pl->d_gsum; pl->own_exch = pl->d_exch; }
+    if (pl->two_stage) {
+        pl->d_gsum  = (double *)d_buf;
+        pl->d_gtile = pl->d_gsum + (size_t)pl->K * pl->N;
+    } else {
+        pl->d_exch = d_buf;
+    }
+    pl->exch_bound = 1;
+    return 0;
+}
+
+/* The exchange block now holds the sum over all ranks (call between reduce and finish). */
+int tspws_b200_plan_mark_exchanged(tspws_plan_t *pl)
+{
+    if (!pl) return TSPWS_ERR_NULL;
+    pl->summed_across_ranks = 1;
+    return 0;
 }
 size_t tspws_b200_plan_exchange_bytes(tspws_plan_t *pl)
 {
