@@ -46,3 +46,31 @@ def make_input(case: dict) -> np.ndarray:
     if case.get("zero_trace") is not None:
         x[case["zero_trace"]] = 0.0
     return x
+
+
+# Resampling / convergence cases.  `plans`: how the reference's selection rows are reproduced:
+#   ("rand", seed)  srand(seed) before the reference call; the same rows are re-drawn with the
+#                   reference's SubsamplingPlan after re-seeding and stored in the fixture;
+#   ("jack",)       JackknifePlans from synthetic daily start times.
+RESAMPLE_CASES = {
+    "subsample_two_stage_24x600": dict(mtr=24, n=600, dt=1.0, seed=31, plans=("rand", 99),
+                                       params=dict(lrm=1, Kmax=4, unbiased=1, subsmpl_N=5, subsmpl_p=0.5)),
+    "subsample_two_stage_fold_mexhat_30x512": dict(mtr=30, n=512, dt=1.0, seed=32, plans=("rand", 7),
+                                       params=dict(type=-3, lrm=1, fold=1, Kmax=5, subsmpl_N=9, subsmpl_p=0.7)),
+    "subsample_single_stage_16x512": dict(mtr=16, n=512, dt=1.0, seed=33, plans=("rand", 7),
+                                       params=dict(lrm=1, subsmpl_N=4, subsmpl_p=0.5)),
+    "subsample_single_stage_unbiased_20x700": dict(mtr=20, n=700, dt=1.0, seed=34, plans=("rand", 5),
+                                       params=dict(lrm=1, unbiased=1, subsmpl_N=19, subsmpl_p=0.3)),
+    "jackknife_two_stage_60x400": dict(mtr=60, n=400, dt=1.0, seed=35, plans=("jack",),
+                                       params=dict(lrm=1, Kmax=4, unbiased=1, jackknife_n=6, jackknife_d=2)),
+}
+CONVERGENCE_CASES = {
+    "convergence_single_12x400": dict(mtr=12, n=400, dt=1.0, seed=41, params=dict(lrm=1, unbiased=1, convergence=1, AllSteps=1)),
+    "convergence_two_stage_14x400": dict(mtr=14, n=400, dt=1.0, seed=42, params=dict(lrm=1, Kmax=4, unbiased=1, convergence=1, AllSteps=1)),
+    "convergence_mexhat_biased_9x300": dict(mtr=9, n=300, dt=1.0, seed=43, params=dict(type=-3, fold=1, Kmax=3, convergence=1)),
+}
+
+
+def jackknife_times(mtr: int) -> np.ndarray:
+    """Synthetic daily start times from 2001-01-01, one trace every 5 days."""
+    return (978307200 + 86400 * 5 * np.arange(mtr)).astype(np.int64)

@@ -43,11 +43,58 @@ def run_reference(B, ref, case):
                 input_sha=np.frombuffer(hashlib.sha256(x.tobytes()).digest(), dtype=np.uint8))
 
 
+def run_reference_resample(B, ref, case):
+    """Reference resampling outputs + the selection rows it used (single-threaded: its two-stage
+    sampler calls rand() inside an OpenMP loop, src/ts_pws1f_lib.c:640)."""
+    import ctypes as C
+    import math
+    C.CDLL("libgomp.so.1").omp_set_num_threads(1)
+    libc = C.CDLL(None)
+    x = CS.make_input(case)
+    p = B.default_params(**case["params"])
+    mtr = case["mtr"]
+    times = None
+    if case["plans"][0] == "rand":
+        libc.srand(case["plans"][1])
+        r = B.call_tspws_main(ref, x, p, dt=case["dt"])
+        libc.srand(case["plans"][1])
+        sel = R.subsampling_plans(p.subsmpl_N, mtr, int(math.ceil(mtr * p.subsmpl_p)))
+    else:
+        times = CS.jackknife_times(mtr)
+        r = B.call_tspws_main(ref, x, p, dt=case["dt"], times=times)
+        rc, sel = R.jackknife_plans(times, p.jackknife_n, p.jackknife_d, math.comb(p.jackknife_n, p.jackknife_d))
+        assert rc == 0
+    assert r["rc"] == 0
+    return dict(ls=r["ls"], tsPWS=r["tsPWS"], ls_subsmpl=r["ls_subsmpl"], tsPWS_subsmpl=r["tsPWS_subsmpl"],
+                mtr_subsmpl=r["mtr_subsmpl"], sel=sel.astype(np.int8),
+                input_sha=np.frombuffer(hashlib.sha256(x.tobytes()).digest(), dtype=np.uint8))
+
+
+def run_reference_convergence(B, ref, case):
+    x = CS.make_input(case)
+    p = B.default_params(**case["params"])
+    r = B.call_tspws_main(ref, x, p, dt=case["dt"])
+    assert r["rc"] == 0
+    g = dict(ls=r["ls"], tsPWS=r["tsPWS"], input_sha=np.frombuffer(hashlib.sha256(x.tobytes()).digest(), dtype=np.uint8))
+    for k in ("ls_sim", "tsPWS_sim", "ls_misfit", "tsPWS_misfit", "ls_steps", "tsPWS_steps"):
+        if k in r:
+            g[k] = r[k]
+    return g
+
+
 def main():
     B = _pkg()
     ref = B.declare_reference(R.load())
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
+    for name, case in CS.RESAMPLE_CASES.items():
+        g = run_reference_resample(B, ref, case)
+        np.savez_compressed(os.path.join(out, name + ".npz"), **g)
+        print(f"{name}: M={g['sel'].shape[0]} K={g['sel'].sum(axis=1).tolist()} max|ts_sub|={np.abs(g['tsPWS_subsmpl']).max():.3e}")
+    for name, case in CS.CONVERGENCE_CASES.items():
+        g = run_reference_convergence(B, ref, case)
+        np.savez_compressed(os.path.join(out, name + ".npz"), **g)
+        print(f"{name}: sim[-1]={g['tsPWS_sim'][-1]:.6f} misfit[0]={g['tsPWS_misfit'][0]:.3e}")
     for name, case in CS.CASES.items():
         g = run_reference(B, ref, case)
         # ST/PS are stored as complex64-pairs of float64? keep float64 for the 1e-5 coherence check,

@@ -178,9 +178,10 @@ def jackknife_plans(times, n, d, Ccomb):
     t = np.ascontiguousarray(times, dtype=np.int64)
     mtr = len(t)
     block = C.create_string_buffer(Ccomb * mtr)
-    rows = (C.c_char_p * Ccomb)()
+    rows = (C.c_void_p * Ccomb)()
     base = C.addressof(block)
     for c in range(Ccomb):
-        rows[c] = C.cast(base + c * mtr, C.c_char_p)
-    rc = lib.JackknifePlans(rows, t.ctypes.data_as(C.POINTER(C.c_long)), mtr, d, n, Ccomb)
+        rows[c] = base + c * mtr
+    lib.JackknifePlans.argtypes = [C.c_void_p, C.POINTER(C.c_long), C.c_uint, C.c_uint, C.c_uint, C.c_uint]
+    rc = lib.JackknifePlans(C.cast(rows, C.c_void_p), t.ctypes.data_as(C.POINTER(C.c_long)), mtr, d, n, Ccomb)
     return rc, np.frombuffer(block.raw, dtype=np.int8).reshape(Ccomb, mtr).copy()

@@ -452,6 +452,45 @@ def misfit(x1: np.ndarray, x2: np.ndarray) -> float:
     return float(np.dot(d, d))
 
 
+def convergence(p: Params, sigall: np.ndarray, dt: float = 1.0, reference=None) -> dict:
+    """Convergence curves (src/ts_pws1f_lib.c:247-314) for already-derived p: after every added trace
+    the ts-PWS of the first Tr traces (plain stack while Tr <= Kmax or Kmax == 0, regrouped two-stage
+    stack otherwise) and the running time-domain mean, each compared (GNCC, squared misfit) with the
+    final stack or `reference`."""
+    main = tspws_main(p, sigall, dt=dt)
+    x, fr, mtr = main["sigall"], main["frame"], main["mtr"]
+    ref_ts = reference if reference is not None else main["tsPWS"]
+    ref_ls = reference if reference is not None else main["ls"]
+    ts_sim, ts_mis, ls_sim, ls_mis = (np.zeros(mtr) for _ in range(4))
+    ts_steps = np.zeros((mtr, x.shape[1]), np.float32)
+    ls_steps = np.zeros((mtr, x.shape[1]), np.float32)
+    st = np.zeros(fr.ncoef, complex)
+    ps = np.zeros(fr.ncoef, complex)
+    for itr in range(mtr):
+        Tr = itr + 1
+        if not p.Kmax or p.Kmax >= Tr:
+            K = Tr
+            Y = analysis(fr, x[itr])
+            st = st + Y
+            ps = ps + phasor(Y)
+        else:
+            K = p.Kmax
+            st, ps = stacks(fr, partial_linear_stacks(x[:Tr], K))
+        d = synthesis(fr, weight(st, ps, K, Tr, p.wu, bool(p.unbiased)))
+        ts_sim[itr], ts_mis[itr] = similarity(d, ref_ts), misfit(d, ref_ts)
+        ts_steps[itr] = d.astype(np.float32)
+    run = np.zeros(x.shape[1])
+    for itr in range(mtr):
+        run = run + x[itr].astype(np.float64)
+        fa1 = float(np.float32(1.0 / (itr + 1)))
+        run = run * fa1
+        ls_sim[itr], ls_mis[itr] = similarity(run, ref_ls), misfit(run, ref_ls)
+        ls_steps[itr] = run.astype(np.float32)
+        run = run * (itr + 1)
+    return dict(main=main, tsPWS_sim=ts_sim, tsPWS_misfit=ts_mis, ls_sim=ls_sim, ls_misfit=ls_mis,
+                tsPWS_steps=ts_steps, ls_steps=ls_steps)
+
+
 # --------------------------------------------------------------------------------------
 # Synthetic traces (SURVEY.md §8(d)) -- counter-based so any rank can make any trace
 # --------------------------------------------------------------------------------------

@@ -153,6 +153,26 @@ int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, const void *
                      int nseg, const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
                      float *d_out_ts, float *d_out_ls, tspws_stream_t st);
 
+/* device frame construction (tspws_plan.c) */
+int  tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64, int per_trace);
+void tspws_devframe_free(tspws_devframe_t *d);
+
+/* ---- resampling / convergence support ---- */
+int tspws_cu_regroup(const float *d_x, int N, int ntr, const signed char *d_gid /*[M][ntr]*/, int M, int G,
+                     float *d_out /*[M][G][N]*/, tspws_stream_t st);
+int tspws_cu_group_total(const float *d_gs, int M, int G, int N, const double *d_scale /*[M]*/, float *d_out /*[M][N]*/,
+                         tspws_stream_t st);
+int tspws_cu_coef_matrix(const tspws_devframe_t *f, const void *d_ypart, int ntr, void *d_Y, void *d_P, tspws_stream_t st);
+int tspws_cu_select_sum(const void *d_P, int T, int ncoef, const signed char *d_sel, int sel_ld, int t0, int M,
+                        void *d_acc /*double2 [M][ncoef]*/, tspws_stream_t st);
+int tspws_cu_weight_mixed(const void *d_ps64, const void *d_st32, int ncoef, int nseg, const tspws_weight_t *d_rules,
+                          void *d_zout, tspws_stream_t st);
+int tspws_cu_prefix_weight(const void *d_Y, const void *d_P, int ncoef, int B, void *d_st_state, void *d_ps_state,
+                           const tspws_weight_t *d_rules, void *d_zout, tspws_stream_t st);
+int tspws_cu_simil(const float *d_cand, int B, int N, const float *d_ref, double *d_sim, double *d_mis, tspws_stream_t st);
+int tspws_cu_lsconv(const float *d_x, int ntr, int N, const float *d_ref, float *d_steps, double *d_part,
+                    double *d_sim, double *d_mis, tspws_stream_t st);
+
 unsigned long tspws_cu_launch_count(void);
 void tspws_cu_profile_mark(tspws_stream_t st);
 int  tspws_cu_profile_enable(int on);

@@ -983,6 +983,309 @@ extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_
 }
 
 /* ===================================================================================== */
+/* resampling support                                                                    */
+/* ===================================================================================== */
+/* Regrouped column sums for MB resamples at once (src/ts_pws1f_lib.c:643-654, :759-772):
+ * gid[m][t] in {-1, 0..G-1} is the group trace t falls in for resample m (-1: not selected);
+ * groups are visited in increasing order as t grows, so a thread only ever holds the CURRENT
+ * group's sum per resample and stores it when the group changes -- no atomics, every trace is
+ * read once per MB resamples.  out: [M][G][N] fp32 (pre-zeroed by the caller). */
+#define RG_MB 8
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+regroup_kernel(const float *__restrict__ x, int N, int ntr, const signed char *__restrict__ gid,
+               int M, int G, float *__restrict__ out)
+{
+    const int m0 = blockIdx.y * RG_MB;
+    const int nm = min(RG_MB, M - m0);
+    const int col = VEC ? (blockIdx.x * 256 + threadIdx.x) * 4 : blockIdx.x * 256 + threadIdx.x;
+    if (col >= N) return;
+    double acc[RG_MB][VEC ? 4 : 1];
+    int cur[RG_MB];
+#pragma unroll
+    for (int i = 0; i < RG_MB; i++) {
+        cur[i] = -1;
+#pragma unroll
+        for (int c = 0; c < (VEC ? 4 : 1); c++) acc[i][c] = 0.0;
+    }
+    for (int t = 0; t < ntr; t++) {
+        float v[VEC ? 4 : 1];
+        if (VEC) { const float4 q = __ldg(reinterpret_cast<const float4 *>(x + (size_t)t * N + col)); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else v[0] = __ldg(x + (size_t)t * N + col);
+#pragma unroll
+        for (int i = 0; i < RG_MB; i++) {
+            if (i < nm) {
+                const int g = gid[(size_t)(m0 + i) * ntr + t];
+                if (g >= 0) {
+                    if (g != cur[i]) {
+                        if (cur[i] >= 0) {
+                            float *o = out + ((size_t)(m0 + i) * G + cur[i]) * N + col;
+#pragma unroll
+                            for (int c = 0; c < (VEC ? 4 : 1); c++) { o[c] = (float)acc[i][c]; acc[i][c] = 0.0; }
+                        }
+                        cur[i] = g;
+                    }
+#pragma unroll
+                    for (int c = 0; c < (VEC ? 4 : 1); c++) acc[i][c] += (double)v[c];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RG_MB; i++) {
+        if (i < nm && cur[i] >= 0) {
+            float *o = out + ((size_t)(m0 + i) * G + cur[i]) * N + col;
+#pragma unroll
+            for (int c = 0; c < (VEC ? 4 : 1); c++) o[c] = (float)acc[i][c];
+        }
+    }
+}
+
+extern "C" int tspws_cu_regroup(const float *d_x, int N, int ntr, const signed char *d_gid, int M, int G,
+                                float *d_out, tspws_stream_t st)
+{
+    if (M <= 0 || ntr <= 0) return 0;
+    cudaStream_t s = (cudaStream_t)st;
+    if (cudaMemsetAsync(d_out, 0, (size_t)M * G * N * sizeof(float), s) != cudaSuccess) return (int)cudaGetLastError();
+    const bool vec = (N % 4 == 0) && (((uintptr_t)d_x & 15) == 0) && (((uintptr_t)d_out & 15) == 0);
+    if (vec) {
+        dim3 grid((N / 4 + 255) / 256, (M + RG_MB - 1) / RG_MB);
+        regroup_kernel<true><<<grid, 256, 0, s>>>(d_x, N, ntr, d_gid, M, G, d_out);
+    } else {
+        dim3 grid((N + 255) / 256, (M + RG_MB - 1) / RG_MB);
+        regroup_kernel<false><<<grid, 256, 0, s>>>(d_x, N, ntr, d_gid, M, G, d_out);
+    }
+    TSPWS_LAUNCHED_N("regroup_kernel", s);
+    return 0;
+}
+
+/* out[m][n] = (float)( scale[m] * sum_g (double) gs[m][g][n] )  -- the time-domain linear stack of a
+ * resample (src/ts_pws1f_lib.c:680-691).  grid = (n tiles, M). */
+__global__ void __launch_bounds__(256)
+group_total_kernel(const float *__restrict__ gs, int G, int N, const double *__restrict__ scale, float *__restrict__ out)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float *p = gs + (size_t)blockIdx.y * G * N + n;
+    double a = 0.0;
+    for (int g = 0; g < G; g++) a += (double)p[(size_t)g * N];
+    out[(size_t)blockIdx.y * N + n] = (float)(a * scale[blockIdx.y]);
+}
+
+extern "C" int tspws_cu_group_total(const float *d_gs, int M, int G, int N, const double *d_scale, float *d_out,
+                                    tspws_stream_t st)
+{
+    if (M <= 0) return 0;
+    dim3 grid((N + 255) / 256, M);
+    group_total_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(d_gs, G, N, d_scale, d_out);
+    TSPWS_LAUNCHED_N("group_total_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* Per-trace coefficient matrices from the per-trace forward output: Y[t][i] = sum of phase splits,
+ * P[t][i] = unit phasor of Y (zero when skipped).  grid = (tiles over Ns, scales, traces). */
+__global__ void __launch_bounds__(256)
+coef_matrix_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ ypart, int ypart_len,
+                   int ncoef, float2 *__restrict__ Y, float2 *__restrict__ P)
+{
+    const tspws_scale_t sc = scales[blockIdx.y];
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= sc.Ns) return;
+    const float2 *yp = ypart + (size_t)blockIdx.z * ypart_len + sc.ypart_off + m;
+    float re = 0.f, im = 0.f;
+    for (int sp = 0; sp < sc.nsplit; sp++) { const float2 y = yp[(size_t)sp * sc.Ns]; re += y.x; im += y.y; }
+    const size_t o = (size_t)blockIdx.z * ncoef + sc.coef_off + m;
+    if (Y) Y[o] = make_float2(re, im);
+    if (P) { float a, b; phasor_fast(re, im, a, b); P[o] = make_float2(a, b); }
+}
+
+extern "C" int tspws_cu_coef_matrix(const tspws_devframe_t *f, const void *d_ypart, int ntr, void *d_Y, void *d_P,
+                                    tspws_stream_t st)
+{
+    if (ntr <= 0 || f->S <= 0) return 0;
+    dim3 grid((f->max_Ns + 255) / 256, f->S, ntr);
+    coef_matrix_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(f->d_scale, (const float2 *)d_ypart, f->ypart_len, f->ncoef,
+                                                           (float2 *)d_Y, (float2 *)d_P);
+    TSPWS_LAUNCHED_N("coef_matrix_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* Selection contraction (src/ts_pws1f_lib.c:555-563): acc[m][i] += sum_t sel[m][t0+t] * P[t][i]
+ * for SS_MB resamples per thread; P is read once per SS_MB resamples.  acc: [M][ncoef] double2. */
+#define SS_MB 16
+__global__ void __launch_bounds__(256)
+select_sum_kernel(const float2 *__restrict__ P, int T, int ncoef, const signed char *__restrict__ sel, int sel_ld,
+                  int t0, int M, double2 *__restrict__ acc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncoef) return;
+    const int m0 = blockIdx.y * SS_MB;
+    const int nm = min(SS_MB, M - m0);
+    double ar[SS_MB], ai[SS_MB];
+#pragma unroll
+    for (int j = 0; j < SS_MB; j++) { ar[j] = 0.0; ai[j] = 0.0; }
+    for (int t = 0; t < T; t++) {
+        const float2 p = __ldg(P + (size_t)t * ncoef + i);
+#pragma unroll
+        for (int j = 0; j < SS_MB; j++)
+            if (j < nm && sel[(size_t)(m0 + j) * sel_ld + t0 + t] == 1) { ar[j] += (double)p.x; ai[j] += (double)p.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < SS_MB; j++)
+        if (j < nm) {
+            double2 *o = acc + (size_t)(m0 + j) * ncoef + i;
+            double2 v = *o;
+            v.x += ar[j]; v.y += ai[j];
+            *o = v;
+        }
+}
+
+extern "C" int tspws_cu_select_sum(const void *d_P, int T, int ncoef, const signed char *d_sel, int sel_ld, int t0,
+                                   int M, void *d_acc, tspws_stream_t st)
+{
+    if (T <= 0 || M <= 0) return 0;
+    dim3 grid((ncoef + 255) / 256, (M + SS_MB - 1) / SS_MB);
+    select_sum_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const float2 *)d_P, T, ncoef, d_sel, sel_ld, t0, M, (double2 *)d_acc);
+    TSPWS_LAUNCHED_N("select_sum_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* Zout[m] = ST[m] * weight(PS[m]) with PS in double2 and ST in float2 (single-stage resampling). */
+__global__ void __launch_bounds__(256)
+weight_mixed_kernel(const double2 *__restrict__ ps, const float2 *__restrict__ st, int ncoef,
+                    const tspws_weight_t *__restrict__ rules, float2 *__restrict__ zout)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncoef) return;
+    const size_t o = (size_t)blockIdx.y * ncoef + i;
+    const double2 p = ps[o];
+    const float2 s = st[o];
+    const double f = weight_factor(rules[blockIdx.y], p.x, p.y);
+    zout[o] = make_float2((float)((double)s.x * f), (float)((double)s.y * f));
+}
+
+extern "C" int tspws_cu_weight_mixed(const void *d_ps64, const void *d_st32, int ncoef, int nseg,
+                                     const tspws_weight_t *d_rules, void *d_zout, tspws_stream_t st)
+{
+    if (nseg <= 0) return 0;
+    dim3 grid((ncoef + 255) / 256, nseg);
+    weight_mixed_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const double2 *)d_ps64, (const float2 *)d_st32, ncoef, d_rules,
+                                                            (float2 *)d_zout);
+    TSPWS_LAUNCHED_N("weight_mixed_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* Convergence (src/ts_pws1f_lib.c:259-286, single-stage branch): running sums over traces
+ * t0..t0+B-1 of Y and P on top of the state (st, ps), one weighted coefficient set per prefix. */
+__global__ void __launch_bounds__(256)
+prefix_weight_kernel(const float2 *__restrict__ Y, const float2 *__restrict__ P, int ncoef, int B,
+                     double2 *__restrict__ st_state, double2 *__restrict__ ps_state,
+                     const tspws_weight_t *__restrict__ rules, float2 *__restrict__ zout)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncoef) return;
+    double2 s = st_state[i], p = ps_state[i];
+    for (int b = 0; b < B; b++) {
+        const float2 y = Y[(size_t)b * ncoef + i], q = P[(size_t)b * ncoef + i];
+        s.x += (double)y.x; s.y += (double)y.y;
+        p.x += (double)q.x; p.y += (double)q.y;
+        const double f = weight_factor(rules[b], p.x, p.y);
+        zout[(size_t)b * ncoef + i] = make_float2((float)(s.x * f), (float)(s.y * f));
+    }
+    st_state[i] = s; ps_state[i] = p;
+}
+
+extern "C" int tspws_cu_prefix_weight(const void *d_Y, const void *d_P, int ncoef, int B, void *d_st_state,
+                                      void *d_ps_state, const tspws_weight_t *d_rules, void *d_zout, tspws_stream_t st)
+{
+    if (B <= 0) return 0;
+    prefix_weight_kernel<<<(ncoef + 255) / 256, 256, 0, (cudaStream_t)st>>>((const float2 *)d_Y, (const float2 *)d_P, ncoef, B,
+        (double2 *)d_st_state, (double2 *)d_ps_state, d_rules, (float2 *)d_zout);
+    TSPWS_LAUNCHED_N("prefix_weight_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* similarity (GNCC) and misfit of B candidate traces against a reference trace
+ * (src/ts_pws1f_lib.c:433-462): one CTA per candidate; sums in double. */
+__global__ void __launch_bounds__(256)
+simil_kernel(const float *__restrict__ cand, int N, const float *__restrict__ ref, double *__restrict__ sim,
+             double *__restrict__ mis)
+{
+    __shared__ double sh[33];
+    const float *c = cand + (size_t)blockIdx.x * N;
+    double xy = 0, xx = 0, yy = 0, dd = 0;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        const double a = (double)c[n], b = (double)ref[n];
+        xy += a * b; xx += a * a; yy += b * b; dd += (a - b) * (a - b);
+    }
+    xy = block_sum(xy, sh); xx = block_sum(xx, sh); yy = block_sum(yy, sh); dd = block_sum(dd, sh);
+    if (threadIdx.x == 0) { sim[blockIdx.x] = xy / sqrt(xx) / sqrt(yy); mis[blockIdx.x] = dd; }
+}
+
+extern "C" int tspws_cu_simil(const float *d_cand, int B, int N, const float *d_ref, double *d_sim, double *d_mis,
+                              tspws_stream_t st)
+{
+    if (B <= 0) return 0;
+    simil_kernel<<<B, 256, 0, (cudaStream_t)st>>>(d_cand, N, d_ref, d_sim, d_mis);
+    TSPWS_LAUNCHED_N("simil_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* Linear-stack convergence (src/ts_pws1f_lib.c:288-308): running time-domain mean after every trace,
+ * float-cast, its similarity / misfit against `ref`, and optionally the traces themselves.
+ * Each thread owns samples and walks the traces; per-trace dot products are reduced per CTA and
+ * finished by simil_finish_kernel.  part: [ntr][gridDim.x][4] doubles. */
+__global__ void __launch_bounds__(256)
+lsconv_kernel(const float *__restrict__ x, int ntr, int N, const float *__restrict__ ref,
+              float *__restrict__ steps, double *__restrict__ part)
+{
+    __shared__ double sh[33];
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = n < N;
+    double run = 0.0;
+    const double r = ok ? (double)ref[n] : 0.0;
+    for (int t = 0; t < ntr; t++) {
+        if (ok) run += (double)x[(size_t)t * N + n];
+        const float fa1 = (float)(1.0 / (double)(t + 1));            /* fa1 = 1.0/(itr+1) is a float in the reference */
+        const double cur = ok ? run * (double)fa1 : 0.0;             /* dsig[n] *= fa1 (double) */
+        if (steps && ok) steps[(size_t)t * N + n] = (float)cur;
+        /* the reference keeps dsig scaled by fa1*(itr+1) afterwards (:296,:307): reproduce that drift */
+        if (ok) run = cur * (double)(t + 1);
+        const double xy = block_sum(cur * r, sh), xx = block_sum(cur * cur, sh);
+        const double yy = block_sum(r * r, sh), dd = block_sum((cur - r) * (cur - r), sh);
+        if (threadIdx.x == 0) {
+            double *o = part + ((size_t)t * gridDim.x + blockIdx.x) * 4;
+            o[0] = xy; o[1] = xx; o[2] = yy; o[3] = dd;
+        }
+    }
+}
+__global__ void simil_finish_kernel(const double *__restrict__ part, int nblk, int ntr, double *__restrict__ sim,
+                                    double *__restrict__ mis)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntr) return;
+    double xy = 0, xx = 0, yy = 0, dd = 0;
+    for (int b = 0; b < nblk; b++) {
+        const double *o = part + ((size_t)t * nblk + b) * 4;
+        xy += o[0]; xx += o[1]; yy += o[2]; dd += o[3];
+    }
+    sim[t] = xy / sqrt(xx) / sqrt(yy);
+    mis[t] = dd;
+}
+
+extern "C" int tspws_cu_lsconv(const float *d_x, int ntr, int N, const float *d_ref, float *d_steps, double *d_part,
+                               double *d_sim, double *d_mis, tspws_stream_t st)
+{
+    if (ntr <= 0) return 0;
+    const int nblk = (N + 255) / 256;
+    lsconv_kernel<<<nblk, 256, 0, (cudaStream_t)st>>>(d_x, ntr, N, d_ref, d_steps, d_part);
+    TSPWS_LAUNCHED_N("lsconv_kernel", (cudaStream_t)st);
+    simil_finish_kernel<<<(ntr + 255) / 256, 256, 0, (cudaStream_t)st>>>(d_part, nblk, ntr, d_sim, d_mis);
+    TSPWS_LAUNCHED_N("simil_finish_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* ===================================================================================== */
 /* inverse frame transform (two coefficient sets at once: Zout -> tsPWS, ST -> ls)       */
 /*   x^[n] = sum_s gain_s sum_m Re( Z_s[m] w_s[l] ),  (m D_s - c_s + l) mod N == n       */
 /*   grid = (n tiles, scale groups, segments); partials per scale group go to scratch    */

@@ -64,7 +64,7 @@ static long env_long(const char *name, long dflt)
 static int pow2_floor(int v) { int r = 1; while (2 * r <= v) r *= 2; return r; }
 
 /* ---- device frame: scale records, filters (fp32 [+fp64]), forward items, inverse groups ---- */
-static int devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64, int per_trace)
+int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64, int per_trace)
 {
     memset(d, 0, sizeof(*d));
     const int S = (int)f->S;
@@ -260,7 +260,7 @@ done:
     return ok ? 0 : -1;
 }
 
-static void devframe_free(tspws_devframe_t *d)
+void tspws_devframe_free(tspws_devframe_t *d)
 {
     cudaFree(d->d_scale); cudaFree(d->d_w32); cudaFree(d->d_w64);
     cudaFree(d->d_items); cudaFree(d->d_invgrp);
@@ -330,7 +330,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
 {
     if (!pl) return;
     if (pl->exch_bound) { pl->d_gsum = (double *)pl->own_gsum; pl->d_exch = pl->own_exch; }
-    devframe_free(&pl->dev);
+    tspws_devframe_free(&pl->dev);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
     cudaFree(pl->d_part); cudaFree(pl->d_tickets); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
     cudaFree(pl->d_pps); cudaFree(pl->d_pst); cudaFree(pl->d_exch);
@@ -357,7 +357,7 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     if (!pl->fr) { fprintf(stderr, "tspws_b200: cannot build the wavelet frame\n"); free(pl); return NULL; }
     for (unsigned int s = 0; s < pl->fr->S; s++)
         if (pl->fr->L[s] > (unsigned int)max) goto fail;          /* cannot happen: L is capped at N */
-    if (devframe_build(&pl->dev, pl->fr, pl->acc64, pl->two_stage && !pl->acc64)) goto fail;
+    if (tspws_devframe_build(&pl->dev, pl->fr, pl->acc64, pl->two_stage && !pl->acc64)) goto fail;
 
     CK(cudaMalloc((void **)&pl->d_rule, sizeof(tspws_weight_t)));
     CK(cudaMemcpy(pl->d_rule, &pl->rule, sizeof(tspws_weight_t), cudaMemcpyHostToDevice));

@@ -1,24 +1,385 @@
 /*
- * tspws_resample.c -- resampling (sub-sampling / jackknife) and convergence drivers.
- * (filled in below the main stack)
+ * tspws_resample.c -- resampling (random sub-sampling, day-of-year jackknife) and convergence
+ * curves on the GPU.  Host C drivers over the kernels of tspws_kernels.cu.
+ *
+ *   single-stage sub-sampling  reference tspws_subsmpl_float     src/ts_pws1f_lib.c:501-610
+ *   two-stage sub-sampling     reference TwoStage_subsmpl_float  src/ts_pws1f_lib.c:612-709
+ *   two-stage jackknife        reference TwoStage_jackknife_float src/ts_pws1f_lib.c:719-831
+ *   (single-stage jackknife is an empty stub in the reference, :711-716 -- outputs stay untouched)
+ *   convergence                src/ts_pws1f_lib.c:247-314
+ *
+ * Formulation: a resample is a 0/1 selection row over the traces.
+ *   two-stage : the selected traces, by rank, are regrouped into Kmax sums (regroup_kernel, every
+ *               trace read once per 8 resamples), then Kmax transforms per resample in the
+ *               chunk-accumulating forward kernel, weights with (Kmax, K_m), one inverse each.
+ *   single    : PS_m = Sel . Phasor (select_sum_kernel over the per-trace phasor matrix, computed
+ *               once), ST_m = analysis(Sel . X) by linearity, ls_m = Sel . X / K in the time domain.
  */
+#include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <cuda_runtime_api.h>
+
 #include "tspws_internal.h"
 
+#define RS_BATCH 64          /* resamples (or prefixes) processed per batch */
+#define TR_BATCH 128         /* traces per batch of per-trace coefficient matrices */
+
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "tspws_b200: CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    rc = TSPWS_ERR_CUDA; goto done; } } while (0)
+#define CKK(call) do { if ((call)) { fprintf(stderr, "tspws_b200: kernel launch failed at %s:%d\n", __FILE__, __LINE__); \
+    rc = TSPWS_ERR_CUDA; goto done; } } while (0)
+
+typedef struct {
+    tspws_frame_t   *fr;
+    tspws_devframe_t acc;     /* chunk-accumulate item lists */
+    tspws_devframe_t pt;      /* per-trace item lists        */
+    int have_pt;
+} rs_frames_t;
+
+static int frames_open(rs_frames_t *F, const t_tsPWS *p, int max, int need_pt)
+{
+    memset(F, 0, sizeof(*F));
+    F->fr = tspws_b200_frame_create(p->type, p->J, p->V, (unsigned int)max, p->s0, p->b0, p->w0, (int)p->uni);
+    if (!F->fr) return TSPWS_ERR_ALLOC;
+    if (tspws_devframe_build(&F->acc, F->fr, 0, 0)) return TSPWS_ERR_CUDA;
+    if (need_pt) { if (tspws_devframe_build(&F->pt, F->fr, 0, 1)) return TSPWS_ERR_CUDA; F->have_pt = 1; }
+    return 0;
+}
+static void frames_close(rs_frames_t *F)
+{
+    tspws_devframe_free(&F->acc);
+    if (F->have_pt) tspws_devframe_free(&F->pt);
+    tspws_b200_frame_destroy(F->fr);
+    memset(F, 0, sizeof(*F));
+}
+
+/* group of the r-th selected trace out of K: src/ts_pws1f_lib.c:648 (unsigned product, double division) */
+static int rank_group(unsigned int r, unsigned int Kmax, unsigned int K)
+{
+    return (int)(unsigned int)floor((double)(r * Kmax) / (double)K);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* two-stage machinery: nres selection rows -> ls / tsPWS rows (host pointers)            */
+/* ------------------------------------------------------------------------------------ */
+static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, unsigned int mtr, int max,
+                          const char *sel /*[nres][mtr]*/, unsigned int nres, unsigned int Kmax,
+                          float **ls_rows, float **ts_rows, unsigned int *K_out,
+                          const float *d_ref, double *sim_out, double *mis_out, cudaStream_t st)
+{
+    int rc = 0;
+    const size_t N = (size_t)max, ncoef = F->fr->ncoef ? F->fr->ncoef : 1;
+    const int B = RS_BATCH;
+    signed char *h_gid = NULL, *d_gid = NULL;
+    float *d_gs = NULL, *d_ls = NULL, *d_ts = NULL, *h_buf = NULL;
+    void *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
+    double *d_scale = NULL, *h_scale = NULL, *d_sim = NULL, *h_sim = NULL;
+    tspws_weight_t *d_rules = NULL, *h_rules = NULL;
+    unsigned int *d_tk = NULL, *Ks = NULL;
+    const int ntk = (max + 255) / 256;
+
+    if (Kmax > 127) { fprintf(stderr, "tspws_b200: two-stage resampling supports Kmax <= 127\n"); return TSPWS_ERR_ARG; }
+    h_gid   = (signed char *)malloc((size_t)B * mtr);
+    h_scale = (double *)malloc(B * sizeof(double));
+    h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
+    h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
+    h_sim   = (double *)malloc(2 * B * sizeof(double));
+    Ks      = (unsigned int *)malloc(B * sizeof(unsigned int));
+    if (!h_gid || !h_scale || !h_rules || !h_buf || !h_sim || !Ks) { rc = TSPWS_ERR_ALLOC; goto done; }
+    CKR(cudaMalloc((void **)&d_gid, (size_t)B * mtr));
+    CKR(cudaMalloc((void **)&d_gs, (size_t)B * Kmax * N * sizeof(float)));
+    CKR(cudaMalloc((void **)&d_ls, (size_t)B * N * sizeof(float)));
+    CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
+    CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.ninv ? F->acc.ninv : 1) * B * N * sizeof(float)));
+    CKR(cudaMalloc((void **)&d_scale, B * sizeof(double)));
+    CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
+    CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
+    CKR(cudaMalloc((void **)&d_sim, 2 * B * sizeof(double)));
+    CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
+
+    for (unsigned int m0 = 0; m0 < nres; m0 += B) {
+        const int nb = (int)((nres - m0 < (unsigned int)B) ? nres - m0 : (unsigned int)B);
+        for (int b = 0; b < nb; b++) {
+            const char *row = sel + (size_t)(m0 + b) * mtr;
+            unsigned int K = 0;
+            for (unsigned int t = 0; t < mtr; t++) K += (row[t] == 1);
+            unsigned int r = 0;
+            for (unsigned int t = 0; t < mtr; t++)
+                h_gid[(size_t)b * mtr + t] = (row[t] == 1) ? (signed char)rank_group(r++, Kmax, K) : (signed char)-1;
+            Ks[b] = K;
+            h_scale[b] = K ? 1.0 / (double)K : 0.0;                                   /* W/K with W = 1 (:672,:686) */
+            h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, Kmax, K ? K : 1);
+            if (K_out) K_out[m0 + b] = K;
+        }
+        CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)nb * mtr, cudaMemcpyHostToDevice, st));
+        CKR(cudaMemcpyAsync(d_scale, h_scale, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+        CKR(cudaMemcpyAsync(d_rules, h_rules, nb * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, nb, (int)Kmax, d_gs, st));
+        if (ls_rows) {
+            CKK(tspws_cu_group_total(d_gs, nb, (int)Kmax, max, d_scale, d_ls, st));
+            CKR(cudaMemcpyAsync(h_buf, d_ls, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CKR(cudaStreamSynchronize(st));
+            for (int b = 0; b < nb; b++) memcpy(ls_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
+        }
+        CKK(tspws_cu_forward_fast(&F->acc, d_gs, nb * (int)Kmax, (int)Kmax, d_pps, d_pst, st));
+        CKK(tspws_cu_weight(d_pps, d_pst, 0, (int)F->fr->ncoef, nb, d_rules, d_zout, st));
+        CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st));
+        if (d_ref && sim_out) {
+            CKK(tspws_cu_simil(d_ts, nb, max, d_ref, d_sim, d_sim + B, st));
+            CKR(cudaMemcpyAsync(h_sim, d_sim, 2 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+        if (ts_rows) CKR(cudaMemcpyAsync(h_buf, d_ts, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        for (int b = 0; b < nb; b++) {
+            if (ts_rows && ts_rows[m0 + b]) memcpy(ts_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
+            if (d_ref && sim_out) { sim_out[m0 + b] = h_sim[b]; mis_out[m0 + b] = h_sim[B + b]; }
+        }
+    }
+done:
+    free(h_gid); free(h_scale); free(h_rules); free(h_buf); free(h_sim); free(Ks);
+    cudaFree(d_gid); cudaFree(d_gs); cudaFree(d_ls); cudaFree(d_ts); cudaFree(d_pps); cudaFree(d_pst);
+    cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale); cudaFree(d_rules); cudaFree(d_tk); cudaFree(d_sim);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* single-stage sub-sampling                                                             */
+/* ------------------------------------------------------------------------------------ */
+static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float *d_x, unsigned int mtr, int max,
+                                  const char *sel, unsigned int M, unsigned int K,
+                                  float **ls_rows, float **ts_rows, cudaStream_t st)
+{
+    int rc = 0;
+    const size_t N = (size_t)max, ncoef = F->fr->ncoef ? F->fr->ncoef : 1;
+    const int B = RS_BATCH, ntk = (max + 255) / 256;
+    signed char *h_gid = NULL, *d_gid = NULL, *d_sel = NULL;
+    float *d_S = NULL, *d_ls = NULL, *d_ts = NULL, *h_buf = NULL;
+    void *d_ypart = NULL, *d_P = NULL, *d_ps64 = NULL, *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
+    double *d_scale = NULL, *h_scale = NULL;
+    tspws_weight_t *d_rules = NULL, *h_rules = NULL;
+    unsigned int *d_tk = NULL;
+
+    h_gid   = (signed char *)malloc((size_t)M * mtr);
+    h_scale = (double *)malloc(B * sizeof(double));
+    h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
+    h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
+    if (!h_gid || !h_scale || !h_rules || !h_buf) { rc = TSPWS_ERR_ALLOC; goto done; }
+    for (size_t i = 0; i < (size_t)M * mtr; i++) h_gid[i] = (sel[i] == 1) ? 0 : -1;
+    for (int b = 0; b < B; b++) { h_scale[b] = 1.0 / (double)K; h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, K, K); }
+
+    CKR(cudaMalloc((void **)&d_gid, (size_t)M * mtr));
+    CKR(cudaMalloc((void **)&d_sel, (size_t)M * mtr));
+    CKR(cudaMalloc((void **)&d_S, (size_t)B * N * sizeof(float)));
+    CKR(cudaMalloc((void **)&d_ls, (size_t)B * N * sizeof(float)));
+    CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
+    CKR(cudaMalloc(&d_ypart, (size_t)TR_BATCH * (F->pt.ypart_len ? F->pt.ypart_len : 1) * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_P, (size_t)TR_BATCH * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_ps64, (size_t)M * ncoef * 2 * sizeof(double)));
+    CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.ninv ? F->acc.ninv : 1) * B * N * sizeof(float)));
+    CKR(cudaMalloc((void **)&d_scale, B * sizeof(double)));
+    CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
+    CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
+    CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
+    CKR(cudaMemsetAsync(d_ps64, 0, (size_t)M * ncoef * 2 * sizeof(double), st));
+    CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)M * mtr, cudaMemcpyHostToDevice, st));
+    CKR(cudaMemcpyAsync(d_sel, sel, (size_t)M * mtr, cudaMemcpyHostToDevice, st));
+    CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
+    CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+
+    /* phase stacks: PS_m = sum_t sel[m][t] phasor(Y_t); every trace is transformed once */
+    for (unsigned int t0 = 0; t0 < mtr; t0 += TR_BATCH) {
+        const int nt = (int)((mtr - t0 < TR_BATCH) ? mtr - t0 : TR_BATCH);
+        CKK(tspws_cu_forward_pertrace(&F->pt, d_x + (size_t)t0 * N, nt, d_ypart, st));
+        CKK(tspws_cu_coef_matrix(&F->pt, d_ypart, nt, NULL, d_P, st));
+        CKK(tspws_cu_select_sum(d_P, nt, (int)F->fr->ncoef, d_sel, (int)mtr, (int)t0, (int)M, d_ps64, st));
+    }
+    /* per batch of resamples: time-domain sums -> ls, ST by linearity, weights, inverse */
+    for (unsigned int m0 = 0; m0 < M; m0 += B) {
+        const int nb = (int)((M - m0 < (unsigned int)B) ? M - m0 : (unsigned int)B);
+        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, nb, 1, d_S, st));
+        CKK(tspws_cu_group_total(d_S, nb, 1, max, d_scale, d_ls, st));
+        CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, st));
+        CKK(tspws_cu_weight_mixed((char *)d_ps64 + (size_t)m0 * ncoef * 2 * sizeof(double), d_pst, (int)F->fr->ncoef, nb,
+                                  d_rules, d_zout, st));
+        CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st));
+        CKR(cudaMemcpyAsync(h_buf, d_ls, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        for (int b = 0; b < nb; b++) memcpy(ls_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
+        CKR(cudaMemcpyAsync(h_buf, d_ts, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        for (int b = 0; b < nb; b++) memcpy(ts_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
+    }
+done:
+    free(h_gid); free(h_scale); free(h_rules); free(h_buf);
+    cudaFree(d_gid); cudaFree(d_sel); cudaFree(d_S); cudaFree(d_ls); cudaFree(d_ts); cudaFree(d_ypart); cudaFree(d_P);
+    cudaFree(d_ps64); cudaFree(d_pps); cudaFree(d_pst); cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale);
+    cudaFree(d_rules); cudaFree(d_tk);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
 int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
                        unsigned int mtr, int max, const char *sel_override, unsigned int selM,
                        cudaStream_t stream)
 {
-    (void)p; (void)out; (void)in; (void)d_x; (void)mtr; (void)max; (void)sel_override; (void)selM; (void)stream;
-    fprintf(stderr, "tspws_b200: resampling is not implemented yet\n");
-    return TSPWS_ERR_ARG;
+    int rc = 0;
+    const int two_stage = p->Kmax && p->Kmax <= mtr;
+    rs_frames_t F;
+    char *sel = NULL;
+    if (!out->ls_subsmpl || !out->tsPWS_subsmpl) { printf("tspws_main: NULL resampling outputs\n"); return -1; }
+    if ((rc = frames_open(&F, p, max, !two_stage))) { frames_close(&F); return rc; }
+
+    /* ---- random sub-sampling (src/ts_pws1f_lib.c:324-333) ---- */
+    if (p->subsmpl_N > 0 && p->subsmpl_p > 0) {
+        const unsigned int K = (unsigned int)ceil((double)mtr * p->subsmpl_p);
+        const unsigned int M = p->subsmpl_N;
+        sel = (char *)malloc((size_t)M * mtr);
+        if (!sel) { rc = TSPWS_ERR_ALLOC; goto done; }
+        if (sel_override && selM == M) memcpy(sel, sel_override, (size_t)M * mtr);
+        else for (unsigned int m = 0; m < M; m++) tspws_b200_subsampling_plan(sel + (size_t)m * mtr, mtr, K);
+        if (K == 0 || K > mtr) { fprintf(stderr, "tspws_b200: subsmpl_p out of range\n"); rc = TSPWS_ERR_ARG; goto done; }
+        if (two_stage) rc = two_stage_rows(p, &F, d_x, mtr, max, sel, M, p->Kmax, out->ls_subsmpl, out->tsPWS_subsmpl,
+                                           NULL, NULL, NULL, NULL, stream);
+        else           rc = single_stage_subsample(p, &F, d_x, mtr, max, sel, M, K, out->ls_subsmpl, out->tsPWS_subsmpl, stream);
+        free(sel); sel = NULL;
+        if (rc) goto done;
+    }
+    /* ---- delete-d jackknife over day-of-year bins (src/ts_pws1f_lib.c:335-345) ---- */
+    if (p->jackknife_n > 0 && p->jackknife_d > 0) {
+        const unsigned int Cn = out->M;
+        if (!two_stage) goto done;                    /* reference: empty stub, outputs untouched (:711-716) */
+        if (!Cn) goto done;
+        sel = (char *)malloc((size_t)Cn * mtr);
+        if (!sel) { rc = TSPWS_ERR_ALLOC; goto done; }
+        if (sel_override && selM == Cn) memcpy(sel, sel_override, (size_t)Cn * mtr);
+        else {
+            const int e = tspws_b200_jackknife_plans(sel, in->time, mtr, p->jackknife_d, p->jackknife_n, Cn);
+            if (e) {   /* the reference goes on with an uninitialised matrix here */
+                printf("Warning: jackknife needs the start time of every trace (binary input); skipped.\n");
+                goto done;
+            }
+        }
+        rc = two_stage_rows(p, &F, d_x, mtr, max, sel, Cn, p->Kmax, out->ls_subsmpl, out->tsPWS_subsmpl,
+                            out->mtr_subsmpl, NULL, NULL, NULL, stream);
+    }
+done:
+    free(sel);
+    frames_close(&F);
+    return rc;
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* convergence curves (src/ts_pws1f_lib.c:247-314)                                        */
+/* ------------------------------------------------------------------------------------ */
 int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
-                          unsigned int mtr, int max, cudaStream_t stream)
+                          unsigned int mtr, int max, cudaStream_t st)
 {
-    (void)p; (void)out; (void)in; (void)d_x; (void)mtr; (void)max; (void)stream;
-    fprintf(stderr, "tspws_b200: convergence curves are not implemented yet\n");
-    return TSPWS_ERR_ARG;
+    int rc = 0;
+    const size_t N = (size_t)max;
+    const int B = RS_BATCH, ntk = (max + 255) / 256;
+    rs_frames_t F;
+    float *d_ref = NULL, *d_ts = NULL, *d_steps = NULL, *h_buf = NULL;
+    void *d_ypart = NULL, *d_Y = NULL, *d_P = NULL, *d_zout = NULL, *d_scr = NULL, *d_sst = NULL, *d_sps = NULL;
+    double *d_sim = NULL, *h_sim = NULL, *d_part = NULL;
+    tspws_weight_t *d_rules = NULL, *h_rules = NULL;
+    unsigned int *d_tk = NULL;
+    char *sel = NULL;
+    float **rows = NULL;
+    if (!out->tsPWS_sim || !out->tsPWS_misfit || !out->ls_sim || !out->ls_misfit) {
+        printf("tspws_main: NULL convergence outputs\n");
+        return -1;
+    }
+    if ((rc = frames_open(&F, p, max, 1))) { frames_close(&F); return rc; }
+    const size_t ncoef = F.fr->ncoef ? F.fr->ncoef : 1;
+    /* prefixes 1..n_single are plain (single-stage) stacks; longer ones are regrouped two-stage stacks (:262-269) */
+    const unsigned int n_single = p->Kmax ? (p->Kmax < mtr ? p->Kmax : mtr) : mtr;
+
+    h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
+    h_sim   = (double *)malloc(2 * B * sizeof(double));
+    h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
+    if (!h_rules || !h_sim || !h_buf) { rc = TSPWS_ERR_ALLOC; goto done; }
+    CKR(cudaMalloc((void **)&d_ref, 2 * N * sizeof(float)));
+    CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
+    CKR(cudaMalloc(&d_ypart, (size_t)B * (F.pt.ypart_len ? F.pt.ypart_len : 1) * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_Y, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_P, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(cudaMalloc(&d_scr, (size_t)2 * (F.acc.ninv ? F.acc.ninv : 1) * B * N * sizeof(float)));
+    CKR(cudaMalloc(&d_sst, ncoef * 2 * sizeof(double)));
+    CKR(cudaMalloc(&d_sps, ncoef * 2 * sizeof(double)));
+    CKR(cudaMalloc((void **)&d_sim, 2 * B * sizeof(double)));
+    CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
+    CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
+    CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
+    CKR(cudaMemsetAsync(d_sst, 0, ncoef * 2 * sizeof(double), st));
+    CKR(cudaMemsetAsync(d_sps, 0, ncoef * 2 * sizeof(double), st));
+    /* reference traces of the two curves: the final stacks, or the caller's alternative (:277,:298) */
+    CKR(cudaMemcpyAsync(d_ref, in->reference ? in->reference : out->tsPWS, N * sizeof(float), cudaMemcpyHostToDevice, st));
+    CKR(cudaMemcpyAsync(d_ref + N, in->reference ? in->reference : out->ls, N * sizeof(float), cudaMemcpyHostToDevice, st));
+
+    /* ---- ts-PWS convergence, plain prefixes: running sums of Y and phasors ---- */
+    for (unsigned int t0 = 0; t0 < n_single; t0 += B) {
+        const int nb = (int)((n_single - t0 < (unsigned int)B) ? n_single - t0 : (unsigned int)B);
+        for (int b = 0; b < nb; b++) h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, t0 + b + 1, t0 + b + 1);
+        CKR(cudaMemcpyAsync(d_rules, h_rules, nb * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+        CKK(tspws_cu_forward_pertrace(&F.pt, d_x + (size_t)t0 * N, nb, d_ypart, st));
+        CKK(tspws_cu_coef_matrix(&F.pt, d_ypart, nb, d_Y, d_P, st));
+        CKK(tspws_cu_prefix_weight(d_Y, d_P, (int)F.fr->ncoef, nb, d_sst, d_sps, d_rules, d_zout, st));
+        CKK(tspws_cu_inverse(&F.acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st));
+        CKK(tspws_cu_simil(d_ts, nb, max, d_ref, d_sim, d_sim + B, st));
+        CKR(cudaMemcpyAsync(h_sim, d_sim, 2 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (out->tsPWS_steps) CKR(cudaMemcpyAsync(out->tsPWS_steps + (size_t)t0 * N, d_ts, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CKR(cudaStreamSynchronize(st));
+        for (int b = 0; b < nb; b++) { out->tsPWS_sim[t0 + b] = h_sim[b]; out->tsPWS_misfit[t0 + b] = h_sim[B + b]; }
+    }
+    /* ---- longer prefixes: two-stage stacks of the first Tr traces, regrouped for every Tr ---- */
+    if (n_single < mtr) {
+        const unsigned int nres = mtr - n_single;
+        sel  = (char *)malloc((size_t)B * mtr);
+        rows = (float **)malloc(nres * sizeof(float *));
+        if (!sel || !rows) { rc = TSPWS_ERR_ALLOC; goto done; }
+        for (unsigned int i = 0; i < nres; i++) rows[i] = out->tsPWS_steps ? out->tsPWS_steps + (size_t)(n_single + i) * N : NULL;
+        for (unsigned int r0 = 0; r0 < nres; r0 += B) {
+            const unsigned int nb = (nres - r0 < (unsigned int)B) ? nres - r0 : (unsigned int)B;
+            for (unsigned int b = 0; b < nb; b++) {
+                const unsigned int Tr = n_single + r0 + b + 1;
+                memset(sel + (size_t)b * mtr, 1, Tr);
+                memset(sel + (size_t)b * mtr + Tr, 0, mtr - Tr);
+            }
+            rc = two_stage_rows(p, &F, d_x, mtr, max, sel, nb, p->Kmax, NULL, rows + r0, NULL, d_ref,
+                                out->tsPWS_sim + n_single + r0, out->tsPWS_misfit + n_single + r0, st);
+            if (rc) goto done;
+        }
+    }
+    /* ---- linear-stack convergence in the time domain (:288-308) ---- */
+    {
+        const int nblk = (max + 255) / 256;
+        double *d_ls_sim = NULL;
+        CKR(cudaMalloc((void **)&d_part, (size_t)mtr * nblk * 4 * sizeof(double)));
+        CKR(cudaMalloc((void **)&d_ls_sim, 2 * (size_t)mtr * sizeof(double)));
+        if (out->ls_steps) CKR(cudaMalloc((void **)&d_steps, (size_t)mtr * N * sizeof(float)));
+        if (tspws_cu_lsconv(d_x, (int)mtr, max, d_ref + N, d_steps, d_part, d_ls_sim, d_ls_sim + mtr, st)) { cudaFree(d_ls_sim); rc = TSPWS_ERR_CUDA; goto done; }
+        cudaMemcpyAsync(out->ls_sim, d_ls_sim, mtr * sizeof(double), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(out->ls_misfit, d_ls_sim + mtr, mtr * sizeof(double), cudaMemcpyDeviceToHost, st);
+        if (out->ls_steps) cudaMemcpyAsync(out->ls_steps, d_steps, (size_t)mtr * N * sizeof(float), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(d_ls_sim);
+        if (e != cudaSuccess) { rc = TSPWS_ERR_CUDA; goto done; }
+    }
+done:
+    free(h_rules); free(h_sim); free(h_buf); free(sel); free(rows);
+    cudaFree(d_ref); cudaFree(d_ts); cudaFree(d_steps); cudaFree(d_ypart); cudaFree(d_Y); cudaFree(d_P); cudaFree(d_zout);
+    cudaFree(d_scr); cudaFree(d_sst); cudaFree(d_sps); cudaFree(d_sim); cudaFree(d_rules); cudaFree(d_tk); cudaFree(d_part);
+    frames_close(&F);
+    return rc;
 }
