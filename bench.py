@@ -220,7 +220,9 @@ def run_ours(args, wl, name):
     plan = lib.tspws_b200_plan_create(C.byref(p), n, mtr, mtr * world, rank * mtr)
     if not plan:
         raise SystemExit("tspws_b200_plan_create failed")
-    stream = torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream()                      # a real stream: the legacy default stream cannot be graph-captured
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
     exch = None
     if world > 1:
         nbytes = lib.tspws_b200_plan_exchange_bytes(plan)

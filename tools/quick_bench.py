@@ -15,7 +15,8 @@ def run(name, mtr, n, reps=5, **kw):
     ls = torch.empty(n, device="cuda"); ts = torch.empty(n, device="cuda")
     plan = lib.tspws_b200_plan_create(C.byref(p), n, mtr, mtr, 0)
     assert plan
-    stream = torch.cuda.current_stream().cuda_stream
+    side = torch.cuda.Stream(); torch.cuda.set_stream(side)
+    stream = side.cuda_stream
     def step():
         rc = lib.tspws_b200_plan_stack(plan, x.data_ptr(), ls.data_ptr(), ts.data_ptr(), stream)
         assert rc == 0, rc

@@ -29,7 +29,18 @@ typedef struct {
     int   g_off;     /* offset of the padded conjugated filter g      */
     int   nsplit;    /* partial-Y slots (phase splits) in per-trace mode */
     int   ypart_off; /* offset of this scale in the partial-Y scratch (per unit of K traces) */
-    int   pad;
+    /* 4-samples-per-thread inverse (D % 4 == 0, N % 4 == 0): filter shifted so that its origin is a
+     * multiple of 4 and zero-padded to a multiple of 4 taps */
+    int   inv4;      /* 1: eligible                                   */
+    int   ci;        /* shifted origin c' = c + (4 - c % 4) % 4        */
+    int   Li4;       /* padded length                                  */
+    int   wi_off;    /* offset (multiple of 4) in the inverse filter array */
+    /* polyphase (register-tiled) inverse, D >= 32 and N % D == 0:
+     *   x^[(a D + rho - c') mod N] = gain * sum_t Re( Z[(a - Qi + 1 + t) mod Ns] * gi[t][rho] ),
+     *   gi[t][rho] = w'[rho + (Qi - 1 - t) D]  (time-reversed phase rows) */
+    int   inv2;      /* 1: eligible                                   */
+    int   Qi;        /* taps per phase = ceil(Li4 / D)                 */
+    int   gi_off;    /* offset of gi in the reversed filter array      */
     double gain;     /* synthesis gain ln2/(2 Cpsi V scale) * D       */
 } tspws_scale_t;
 
@@ -67,6 +78,7 @@ typedef struct {
     void              *d_w32;     /* float2[ntaps]  */
     void              *d_w64;     /* double2[ntaps] (NULL unless the fp64 tail is enabled) */
     void              *d_g32;     /* float2[ng]: conjugated, phase-padded filters of the polyphase kernel */
+    void              *d_wi32;    /* float2[]: origin-aligned, zero-padded filters of the 4-sample inverse */
     tspws_fwd_item_t  *d_items;   /* [nitems]  generic kernel: all scales   */
     int                nitems;
     tspws_fwd_item_t  *d_items_gen; /* [nitems_gen] generic kernel: only scales with lg < 0 */
@@ -78,8 +90,16 @@ typedef struct {
     int                per_trace; /* item list built for per-trace (partial-Y) mode */
     int                ypart_len; /* partial-Y scratch length per trace (complex)   */
     int                max_Ns;
-    tspws_inv_group_t *d_invgrp;  /* [ninv]         */
+    int               *d_tile16;  /* [ntile16][2]: (scale, first coefficient) of every 16-coefficient tile */
+    int                ntile16;
+    tspws_inv_group_t *d_invgrp;  /* [ninv]  scale groups of the fp64 inverse                       */
     int                ninv;
+    tspws_inv_group_t *d_invgrp4; /* [ninv4] one group per scale the polyphase inverse does not cover */
+    int                ninv4;
+    void              *d_gi32;    /* float2[]: reversed, phase-padded filters of the polyphase inverse */
+    int               *d_items_inv2; /* [nitems_inv2][4]: (scale, first a, phase block, -)         */
+    int                nitems_inv2;
+    int                inv_slots; /* scratch slots of the inverse: max(S, ninv)                         */
 } tspws_devframe_t;
 
 /* ---- weighting rule (src/ts_pws1f_lib.c:226-228, :909-984) ---- */
@@ -142,6 +162,8 @@ int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_ypart, int 
 int tspws_cu_reduce_weight(const void *d_part_ps, const void *d_part_st, int acc64, int ncoef,
                            int nseg, int seg, const tspws_weight_t *d_rules /*[nseg] device*/,
                            void *d_ps, void *d_st, void *d_zout, tspws_stream_t st);
+/* d_zout layout: fp32 -> float4 per coefficient (Zout.re, Zout.im, ST.re, ST.im) ("zs", what the
+ * fp32 inverse reads with one 16-byte load); fp64 -> double2 Zout only. */
 /* Weighting only (PS, ST already reduced, e.g. after an all-reduce). */
 int tspws_cu_weight(const void *d_ps, const void *d_st, int acc64, int ncoef, int nseg,
                     const tspws_weight_t *d_rules, void *d_zout, tspws_stream_t st);
@@ -175,6 +197,8 @@ int tspws_cu_lsconv(const float *d_x, int ntr, int N, const float *d_ref, float 
 
 unsigned long tspws_cu_launch_count(void);
 void tspws_cu_profile_mark(tspws_stream_t st);
+int  tspws_cu_profile_enabled(void);
+void tspws_cu_launch_count_add(unsigned long n);
 int  tspws_cu_profile_enable(int on);
 int  tspws_cu_profile_reset(void);
 int  tspws_cu_profile_read(char *buf, int cap);

@@ -26,6 +26,7 @@
 
 static unsigned long g_launches = 0;
 extern "C" unsigned long tspws_cu_launch_count(void) { return g_launches; }
+extern "C" void tspws_cu_launch_count_add(unsigned long n) { g_launches += n; }
 
 /* ---- optional per-kernel timing with CUDA events on the launching stream: an event is recorded
  * after every launch (and at tspws_cu_profile_mark), and a kernel is charged the time since the
@@ -75,6 +76,7 @@ static void prof_record(const char *name, cudaStream_t s)
     g_prof.nev = i + 1;
 }
 
+extern "C" int tspws_cu_profile_enabled(void) { return g_prof.on; }
 extern "C" void tspws_cu_profile_mark(tspws_stream_t st) { if (g_prof.on) prof_record(nullptr, (cudaStream_t)st); }
 extern "C" int tspws_cu_profile_enable(int on)
 {
@@ -858,45 +860,51 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
     return 0;
 }
 
-/* per-trace coefficients -> PS, ST, Zout.  grid = (tiles over Ns, scales, segments). */
+/* per-trace coefficients -> PS, ST, Zout.
+ * A CTA covers 16 consecutive coefficients of one scale; its 256 threads are 16 coefficients x 16
+ * trace slots, so that the loads of the `seg` traces (and of the phase splits of coarse scales) are
+ * all in flight at once instead of forming one long latency chain per coefficient; the 16 slots
+ * are then added in slot order through shared memory (deterministic).
+ * grid = (16-coefficient tiles of all scales, segments). */
 __global__ void __launch_bounds__(256)
-phasor_combine_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ ypart, int ypart_len,
+phasor_combine_kernel(const int4 *__restrict__ tiles,
+                      const float2 *__restrict__ ypart, int ypart_len,
                       int ncoef, int seg, const tspws_weight_t *__restrict__ rules,
                       float2 *__restrict__ ps, float2 *__restrict__ st, float2 *__restrict__ zout)
 {
-    const tspws_scale_t sc = scales[blockIdx.y];
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= sc.Ns) return;
-    const int sg = blockIdx.z;
+    __shared__ float  s_p[16][16][2];
+    __shared__ double s_s[16][16][2];
+    /* tile = (offset in a trace's partial-Y block, offset in the coefficient arrays, valid
+     * coefficients | nsplit << 8, Ns = stride between phase splits) */
+    const int4 tile = tiles[blockIdx.x];
+    const int ci = threadIdx.x & 15, slot = threadIdx.x >> 4;
+    const int nvalid = tile.z & 255, nsplit = tile.z >> 8, Ns = tile.w;
+    const int sg = blockIdx.y;
     float pr = 0.f, pi = 0.f;
     double sr = 0.0, si = 0.0;
-    const float2 *yp0 = ypart + (size_t)sg * seg * ypart_len + sc.ypart_off + m;
-    for (int kb = 0; kb < seg; kb += 8) {             /* 8 traces per batch: all loads in flight first */
-        float2 y[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) y[i] = make_float2(0.f, 0.f);
-        for (int sp = 0; sp < sc.nsplit; sp++) {
-            float2 t[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                t[i] = (kb + i < seg) ? __ldcg(yp0 + (size_t)(kb + i) * ypart_len + (size_t)sp * sc.Ns) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 8; i++) { y[i].x += t[i].x; y[i].y += t[i].y; }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            if (kb + i < seg) {
-                float a, b;
-                phasor_fast(y[i].x, y[i].y, a, b);
-                pr += a; pi += b; sr += (double)y[i].x; si += (double)y[i].y;
-            }
+    if (ci < nvalid) {
+        for (int k = slot; k < seg; k += 16) {
+            const float2 *yp = ypart + (size_t)(sg * seg + k) * ypart_len + tile.x + ci;
+            float re = 0.f, im = 0.f;
+#pragma unroll 8
+            for (int sp = 0; sp < nsplit; sp++) { const float2 y = __ldcg(yp + (size_t)sp * Ns); re += y.x; im += y.y; }
+            float a, b;
+            phasor_fast(re, im, a, b);
+            pr += a; pi += b; sr += (double)re; si += (double)im;
         }
     }
+    s_p[slot][ci][0] = pr; s_p[slot][ci][1] = pi;
+    s_s[slot][ci][0] = sr; s_s[slot][ci][1] = si;
+    __syncthreads();
+    if (slot != 0 || ci >= nvalid) return;
+    pr = pi = 0.f; sr = si = 0.0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) { pr += s_p[j][ci][0]; pi += s_p[j][ci][1]; sr += s_s[j][ci][0]; si += s_s[j][ci][1]; }
     const double f = weight_factor(rules[sg], (double)pr, (double)pi);
-    const size_t o = (size_t)sg * ncoef + sc.coef_off + m;
+    const size_t o = (size_t)sg * ncoef + tile.y + ci;
     ps[o]   = make_float2(pr, pi);
     st[o]   = make_float2((float)sr, (float)si);
-    zout[o] = make_float2((float)(sr * f), (float)(si * f));
+    reinterpret_cast<float4 *>(zout)[o] = make_float4((float)(sr * f), (float)(si * f), (float)sr, (float)si);
 }
 
 /* ===================================================================================== */
@@ -940,7 +948,11 @@ reduce_weight_kernel(const typename cplx<T>::type *part_ps, const typename cplx<
     T2 v;
     v.x = (T)pr; v.y = (T)pi; ps[o] = v;
     v.x = (T)sr; v.y = (T)si; st[o] = v;
-    v.x = (T)(sr * f); v.y = (T)(si * f); zout[o] = v;
+    if (sizeof(T) == 4) {
+        reinterpret_cast<float4 *>(zout)[o] = make_float4((float)(sr * f), (float)(si * f), (float)sr, (float)si);
+    } else {
+        v.x = (T)(sr * f); v.y = (T)(si * f); zout[o] = v;
+    }
 }
 
 extern "C" int tspws_cu_reduce_weight(const void *d_part_ps, const void *d_part_st, int acc64, int ncoef,
@@ -973,10 +985,9 @@ extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_
                                        tspws_stream_t st)
 {
     if (nseg <= 0 || f->S <= 0) return 0;
-    int maxNs = (f->N + 0);               /* Ns <= N */
-    dim3 grid((maxNs + 255) / 256, f->S, nseg);
-    if (f->max_Ns > 0) grid.x = (f->max_Ns + 255) / 256;
-    phasor_combine_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(f->d_scale, (const float2 *)d_ypart, f->ypart_len,
+    if (f->ntile16 <= 0) return 0;
+    dim3 grid(f->ntile16, nseg);
+    phasor_combine_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const int4 *)f->d_tile16, (const float2 *)d_ypart, f->ypart_len,
         f->ncoef, seg, d_rules, (float2 *)d_ps, (float2 *)d_st, (float2 *)d_zout);
     TSPWS_LAUNCHED_N("phasor_combine_kernel", (cudaStream_t)st);
     return 0;
@@ -1161,7 +1172,7 @@ weight_mixed_kernel(const double2 *__restrict__ ps, const float2 *__restrict__ s
     const double2 p = ps[o];
     const float2 s = st[o];
     const double f = weight_factor(rules[blockIdx.y], p.x, p.y);
-    zout[o] = make_float2((float)((double)s.x * f), (float)((double)s.y * f));
+    reinterpret_cast<float4 *>(zout)[o] = make_float4((float)((double)s.x * f), (float)((double)s.y * f), s.x, s.y);
 }
 
 extern "C" int tspws_cu_weight_mixed(const void *d_ps64, const void *d_st32, int ncoef, int nseg,
@@ -1190,7 +1201,7 @@ prefix_weight_kernel(const float2 *__restrict__ Y, const float2 *__restrict__ P,
         s.x += (double)y.x; s.y += (double)y.y;
         p.x += (double)q.x; p.y += (double)q.y;
         const double f = weight_factor(rules[b], p.x, p.y);
-        zout[(size_t)b * ncoef + i] = make_float2((float)(s.x * f), (float)(s.y * f));
+        reinterpret_cast<float4 *>(zout)[(size_t)b * ncoef + i] = make_float4((float)(s.x * f), (float)(s.y * f), (float)s.x, (float)s.y);
     }
     st_state[i] = s; ps_state[i] = p;
 }
@@ -1368,6 +1379,271 @@ inv_kernel(const tspws_scale_t *__restrict__ scales, const typename cplx<T>::typ
     if (WITH_ST) out_ls[(size_t)sg * N + n] = __fdiv_rn((float)as, (float)(unsigned int)rules[sg].T);
 }
 
+/* fp32 inverse, 4 consecutive samples per thread.  For scales with D % 4 == 0 the four samples
+ * n0..n0+3 (n0 % 4 == 0) see the same coefficients m and four consecutive taps of the origin-aligned
+ * filter: per coefficient one 16-byte load of (Zout, ST) and two of the taps feed 16 FMAs.  Other
+ * scales (D = 1, 2, odd) take the one-sample path.  grid = (tiles of 1024 samples, scale groups,
+ * segments); the last scale group to finish a tile adds the partials in group order and casts. */
+#define INV4_THREADS 64
+template <bool WITH_ST, bool FINISH>
+__global__ void __launch_bounds__(INV4_THREADS)
+inv4_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ wall, const float2 *__restrict__ wi,
+            const tspws_inv_group_t *__restrict__ groups, int ninv, int N, int ncoef,
+            const float4 *__restrict__ zs, float *scratch, int nseg, unsigned int *tickets,
+            const tspws_weight_t *__restrict__ rules, float *__restrict__ out_ts, float *__restrict__ out_ls)
+{
+    __shared__ int is_last;
+    const int n0 = (blockIdx.x * INV4_THREADS + threadIdx.x) * 4;
+    const tspws_inv_group_t grp = groups[blockIdx.y];
+    const int sg = blockIdx.z;
+    const float4 *__restrict__ ZS = zs + (size_t)sg * ncoef;
+    float az[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n0 < N) {
+        for (int s = grp.s0; s < grp.s1; s++) {
+            const tspws_scale_t sc = scales[s];
+            const float4 *__restrict__ Zs = ZS + sc.coef_off;
+            const int top = (sc.Ns - 1) * sc.D;
+            float bz[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
+            if (sc.inv4) {
+                const float2 *__restrict__ w = wi + sc.wi_off;
+#pragma unroll 1
+                for (int j = -1; j <= 1; j++) {
+                    const int base = n0 + sc.ci + j * N;               /* tap of sample n0 = base - m D, a multiple of 4 */
+                    const int lnum = base - (sc.Li4 - 4);
+                    if (base < 0 || lnum > top) continue;
+                    int hi = (int)((unsigned int)base / (unsigned int)sc.D);
+                    if (hi > sc.Ns - 1) hi = sc.Ns - 1;
+                    const int lo = lnum <= 0 ? 0 : (int)(((unsigned int)lnum + sc.D - 1) / (unsigned int)sc.D);
+                    const float2 *wp = w + (base - lo * sc.D);
+                    const float4 *zp = Zs + lo;
+#pragma unroll 2
+                    for (int cnt = hi - lo + 1; cnt > 0; cnt--, wp -= sc.D, zp++) {
+                        const float4 w01 = __ldg(reinterpret_cast<const float4 *>(wp));
+                        const float4 w23 = __ldg(reinterpret_cast<const float4 *>(wp + 2));
+                        const float4 z   = __ldg(zp);
+                        bz[0] = fmaf(z.x, w01.x, bz[0]); bz[0] = fmaf(-z.y, w01.y, bz[0]);
+                        bz[1] = fmaf(z.x, w01.z, bz[1]); bz[1] = fmaf(-z.y, w01.w, bz[1]);
+                        bz[2] = fmaf(z.x, w23.x, bz[2]); bz[2] = fmaf(-z.y, w23.y, bz[2]);
+                        bz[3] = fmaf(z.x, w23.z, bz[3]); bz[3] = fmaf(-z.y, w23.w, bz[3]);
+                        if (WITH_ST) {
+                            bs[0] = fmaf(z.z, w01.x, bs[0]); bs[0] = fmaf(-z.w, w01.y, bs[0]);
+                            bs[1] = fmaf(z.z, w01.z, bs[1]); bs[1] = fmaf(-z.w, w01.w, bs[1]);
+                            bs[2] = fmaf(z.z, w23.x, bs[2]); bs[2] = fmaf(-z.w, w23.y, bs[2]);
+                            bs[3] = fmaf(z.z, w23.z, bs[3]); bs[3] = fmaf(-z.w, w23.w, bs[3]);
+                        }
+                    }
+                }
+            } else {
+                const float2 *__restrict__ w = wall + sc.tap_off;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (n0 + i >= N) break;
+#pragma unroll 1
+                    for (int j = -1; j <= 1; j++) {
+                        const int base = n0 + i + sc.c + j * N;
+                        const int lnum = base - (sc.L - 1);
+                        if (base < 0 || lnum > top) continue;
+                        int hi = (int)((unsigned int)base / (unsigned int)sc.D);
+                        if (hi > sc.Ns - 1) hi = sc.Ns - 1;
+                        const int lo = lnum <= 0 ? 0 : (int)(((unsigned int)lnum + sc.D - 1) / (unsigned int)sc.D);
+                        const float2 *wp = w + (base - lo * sc.D);
+                        const float4 *zp = Zs + lo;
+#pragma unroll 4
+                        for (int cnt = hi - lo + 1; cnt > 0; cnt--, wp -= sc.D, zp++) {
+                            const float2 wv = __ldg(wp);
+                            const float4 z  = __ldg(zp);
+                            bz[i] = fmaf(z.x, wv.x, bz[i]); bz[i] = fmaf(-z.y, wv.y, bz[i]);
+                            if (WITH_ST) { bs[i] = fmaf(z.z, wv.x, bs[i]); bs[i] = fmaf(-z.w, wv.y, bs[i]); }
+                        }
+                    }
+                }
+            }
+            const float gn = (float)sc.gain;
+#pragma unroll
+            for (int i = 0; i < 4; i++) { az[i] = fmaf(gn, bz[i], az[i]); as[i] = fmaf(gn, bs[i], as[i]); }
+        }
+        /* slot = scale group (FINISH: summed below by the last group) or the scale itself */
+        const size_t o = ((size_t)(FINISH ? blockIdx.y : grp.s0) * nseg + sg) * N + n0;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (n0 + i < N) {
+                scratch[o + i] = az[i];
+                if (WITH_ST) scratch[(size_t)ninv * nseg * N + o + i] = as[i];
+            }
+    }
+    if (!FINISH) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int *tk = &tickets[sg * gridDim.x + blockIdx.x];
+        const unsigned int c = atomicAdd(tk, 1u);
+        is_last = (c == gridDim.y - 1);
+        if (is_last) *tk = 0;
+    }
+    __syncthreads();
+    if (!is_last || n0 >= N) return;
+    __threadfence();
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    if ((N & 3) == 0) {
+        /* independent 16-byte loads, 8 groups in flight at a time (the adds stay in group order) */
+#pragma unroll 8
+        for (int g = 0; g < ninv; g++) {
+            const size_t o = ((size_t)g * nseg + sg) * N + n0;
+            const float4 p = __ldcg(reinterpret_cast<const float4 *>(scratch + o));
+            a[0] += (double)p.x; a[1] += (double)p.y; a[2] += (double)p.z; a[3] += (double)p.w;
+            if (WITH_ST) {
+                const float4 q = __ldcg(reinterpret_cast<const float4 *>(scratch + (size_t)ninv * nseg * N + o));
+                b[0] += (double)q.x; b[1] += (double)q.y; b[2] += (double)q.z; b[3] += (double)q.w;
+            }
+        }
+    } else {
+        for (int g = 0; g < ninv; g++) {
+            const size_t o = ((size_t)g * nseg + sg) * N + n0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (n0 + i < N) {
+                    a[i] += (double)__ldcg(scratch + o + i);
+                    if (WITH_ST) b[i] += (double)__ldcg(scratch + (size_t)ninv * nseg * N + o + i);
+                }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int n = n0 + i;
+        if (n >= N) break;
+        out_ts[(size_t)sg * N + n] = (float)a[i];
+        if (WITH_ST) out_ls[(size_t)sg * N + n] = __fdiv_rn((float)b[i], (float)(unsigned int)rules[sg].T);
+    }
+}
+
+/* Polyphase register-tiled inverse for D >= 32 (N % D == 0): the transpose of the forward tile.
+ * A lane owns one phase rho and 8 consecutive coefficient positions a; it slides a 16-slot register
+ * ring of (Zout, ST) coefficients -- warp-uniform 16-byte loads -- past the Qi taps of its phase
+ * (coalesced 8-byte loads, each used for 8 samples x 2 outputs from registers), so the filter is
+ * read from L2 once per 8 samples instead of once per sample.  Output sample n = (a D + rho - c') mod N
+ * of scale s goes to scratch slot s; inv_finish_kernel adds the slots.
+ * One warp per item (scale, a-tile, block of 32 phases). */
+#define IV_R 8
+#define IV_WS 16
+template <bool WITH_ST>
+__global__ void __launch_bounds__(128)
+inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ gi_all, const int4 *__restrict__ items,
+            int nitems, int N, int ncoef, int nslots, const float4 *__restrict__ zs, float *__restrict__ scratch, int nseg)
+{
+    const int widx = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (widx >= nitems) return;
+    const int lane = threadIdx.x & 31;
+    const int4 it = items[widx];
+    const tspws_scale_t sc = scales[it.x];
+    const int sg = blockIdx.y;
+    const int D = sc.D, Qi = sc.Qi, Ns = sc.Ns, a0 = it.y;
+    const int rho = it.z * 32 + lane;
+    const bool act = rho < D;
+    const float4 *__restrict__ Z = zs + (size_t)sg * ncoef + sc.coef_off;
+    const float2 *__restrict__ g = gi_all + sc.gi_off + (act ? rho : 0);
+    float2 accr[IV_R];                                    /* (tsPWS, ls) partial of sample r */
+#pragma unroll
+    for (int r = 0; r < IV_R; r++) accr[r] = make_float2(0.f, 0.f);
+    int zi = (a0 - Qi + 1) % Ns;                          /* window slot 0 */
+    if (zi < 0) zi += Ns;
+    float2 wre[IV_WS], wim[IV_WS];                        /* (Zr, Sr) and (Zi, Si) of every ring slot */
+    float2 gq[8];
+#pragma unroll
+    for (int j = 0; j < IV_WS; j++) {
+        const float4 z = __ldg(Z + zi);
+        wre[j] = make_float2(z.x, z.z); wim[j] = make_float2(z.y, z.w);
+        if (++zi >= Ns) zi = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) gq[q] = __ldg(g + (size_t)q * D);
+    for (int t0 = 0; t0 < Qi; t0 += IV_WS) {
+#pragma unroll
+        for (int tt = 0; tt < IV_WS; tt++) {
+            if (t0 + tt < Qi) {
+                const float2 gv = gq[tt & 7];
+                const float2 gx = make_float2(gv.x, gv.x), gy = make_float2(-gv.y, -gv.y);
+#pragma unroll
+                for (int r = 0; r < IV_R; r++) {
+                    accr[r] = __ffma2_rn(wre[(tt + r) % IV_WS], gx, accr[r]);
+                    accr[r] = __ffma2_rn(wim[(tt + r) % IV_WS], gy, accr[r]);
+                }
+                if (t0 + tt + IV_WS - IV_R + 1 < Qi) {
+                    const float4 z = __ldg(Z + zi);
+                    wre[tt] = make_float2(z.x, z.z); wim[tt] = make_float2(z.y, z.w);
+                    if (++zi >= Ns) zi = 0;
+                }
+                gq[tt & 7] = __ldg(g + (size_t)(t0 + tt + 8) * D);
+            }
+        }
+    }
+    if (!act) return;
+    const float gn = (float)sc.gain;
+    long long nn = ((long long)a0 * D + rho - sc.ci) % N;
+    if (nn < 0) nn += N;
+    int n = (int)nn;
+    float *o = scratch + ((size_t)it.x * nseg + sg) * N;
+#pragma unroll
+    for (int r = 0; r < IV_R; r++) {
+        if (a0 + r < Ns) {
+            o[n] = gn * accr[r].x;
+            if (WITH_ST) o[(size_t)nslots * nseg * N + n] = gn * accr[r].y;
+        }
+        n += D;
+        if (n >= N) n -= N;
+    }
+}
+
+/* out[n] = sum over scratch slots; casts like src/ts_pws1f_lib.c:233-241.
+ * A CTA covers 64 groups of 4 samples; its 256 threads are 64 sample groups x 4 slot quarters, each
+ * quarter adds its slots (g = quarter, quarter + 4, ...) with independent 16-byte loads, then the four
+ * quarter sums are added in quarter order through shared memory (deterministic).
+ * grid = (tiles of 256 samples, segments). */
+template <bool WITH_ST>
+__global__ void __launch_bounds__(256)
+inv_finish_kernel(const float *__restrict__ scratch, int nslots, int nseg, int N, const tspws_weight_t *__restrict__ rules,
+                  float *__restrict__ out_ts, float *__restrict__ out_ls)
+{
+    __shared__ double sh[4][64][8];
+    const int col = threadIdx.x & 63, quarter = threadIdx.x >> 6;
+    const int n0 = (blockIdx.x * 64 + col) * 4;
+    const int sg = blockIdx.y;
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    if (n0 < N) {
+        if ((N & 3) == 0) {
+#pragma unroll 4
+            for (int g = quarter; g < nslots; g += 4) {
+                const size_t o = ((size_t)g * nseg + sg) * N + n0;
+                const float4 p = __ldg(reinterpret_cast<const float4 *>(scratch + o));
+                a[0] += (double)p.x; a[1] += (double)p.y; a[2] += (double)p.z; a[3] += (double)p.w;
+                if (WITH_ST) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(scratch + (size_t)nslots * nseg * N + o));
+                    b[0] += (double)q.x; b[1] += (double)q.y; b[2] += (double)q.z; b[3] += (double)q.w;
+                }
+            }
+        } else {
+            for (int g = quarter; g < nslots; g += 4) {
+                const size_t o = ((size_t)g * nseg + sg) * N + n0;
+                for (int i = 0; i < 4 && n0 + i < N; i++) {
+                    a[i] += (double)scratch[o + i];
+                    if (WITH_ST) b[i] += (double)scratch[(size_t)nslots * nseg * N + o + i];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { sh[quarter][col][i] = a[i]; sh[quarter][col][4 + i] = b[i]; }
+    __syncthreads();
+    if (quarter != 0 || n0 >= N) return;
+    for (int i = 0; i < 4 && n0 + i < N; i++) {
+        const double ta = ((sh[0][col][i] + sh[1][col][i]) + sh[2][col][i]) + sh[3][col][i];
+        out_ts[(size_t)sg * N + n0 + i] = (float)ta;
+        if (WITH_ST) {
+            const double tb = ((sh[0][col][4 + i] + sh[1][col][4 + i]) + sh[2][col][4 + i]) + sh[3][col][4 + i];
+            out_ls[(size_t)sg * N + n0 + i] = __fdiv_rn((float)tb, (float)(unsigned int)rules[sg].T);
+        }
+    }
+}
+
 template <typename T>
 static int inv_launch(const tspws_devframe_t *f, const void *d_zout, const void *d_st, int nseg,
                       const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
@@ -1392,6 +1668,35 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
 {
     if (nseg <= 0) return 0;
     if (acc64 && !f->d_w64) return (int)cudaErrorInvalidValue;
-    return acc64 ? inv_launch<double>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_tickets, d_out_ts, d_out_ls, (cudaStream_t)st)
-                 : inv_launch<float>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_tickets, d_out_ts, d_out_ls, (cudaStream_t)st);
+    if (acc64) return inv_launch<double>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_tickets, d_out_ts, d_out_ls, (cudaStream_t)st);
+    /* fp32: d_zout is the interleaved (Zout, ST) float4 array; d_st only says whether ls is wanted.
+     * Every scale writes its contribution to its own scratch slot (polyphase kernel for D >= 32,
+     * 4-sample kernel for the rest); the finish kernel adds the slots in scale order. */
+    cudaStream_t s = (cudaStream_t)st;
+    const int S = f->S;
+    if (f->nitems_inv2 > 0) {
+        dim3 grid((f->nitems_inv2 + 3) / 4, nseg);
+        if (d_st) inv2_kernel<true><<<grid, 128, 0, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
+                      f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg);
+        else      inv2_kernel<false><<<grid, 128, 0, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
+                      f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg);
+        TSPWS_LAUNCHED_N("inv2_kernel", s);
+    }
+    if (f->ninv4 > 0) {
+        dim3 grid((f->N + 4 * INV4_THREADS - 1) / (4 * INV4_THREADS), f->ninv4, nseg);
+        if (d_st)
+            inv4_kernel<true, false><<<grid, INV4_THREADS, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, (const float2 *)f->d_wi32, f->d_invgrp4, S,
+                f->N, f->ncoef, (const float4 *)d_zout, (float *)d_scratch, nseg, d_tickets, d_rules, d_out_ts, d_out_ls);
+        else
+            inv4_kernel<false, false><<<grid, INV4_THREADS, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, (const float2 *)f->d_wi32, f->d_invgrp4, S,
+                f->N, f->ncoef, (const float4 *)d_zout, (float *)d_scratch, nseg, d_tickets, d_rules, d_out_ts, d_out_ls);
+        TSPWS_LAUNCHED_N("inv4_kernel", s);
+    }
+    {
+        dim3 grid((f->N + 255) / 256, nseg);
+        if (d_st) inv_finish_kernel<true><<<grid, 256, 0, s>>>((const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
+        else      inv_finish_kernel<false><<<grid, 256, 0, s>>>((const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
+        TSPWS_LAUNCHED_N("inv_finish_kernel", s);
+    }
+    return 0;
 }

@@ -48,6 +48,11 @@ struct tspws_plan {
     void  *d_pps, *d_pst, *d_exch, *d_zout, *d_invscratch, *d_ypart;
     int    summed_across_ranks;
     int    exch_bound;              /* exchange block belongs to the caller */
+    /* the whole stack as one CUDA graph (captured on first use for a given set of pointers) */
+    cudaGraphExec_t gexec;
+    const void *g_x, *g_ls, *g_ts;
+    unsigned long g_kernels;
+    int    graph_broken;
     void  *own_gsum, *own_exch;
 };
 
@@ -238,10 +243,97 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
     if (cudaMalloc(&d->d_w32, (f->ntaps ? f->ntaps : 1) * 2 * sizeof(float)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&d->d_items, (nitems ? nitems : 1) * sizeof(*items)) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&d->d_invgrp, (d->ninv ? d->ninv : 1) * sizeof(*grp)) != cudaSuccess) goto done;
-    if (cudaMemcpy(d->d_scale, sc, S * sizeof(*sc), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_w32, w32, f->ntaps * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_items, items, nitems * sizeof(*items), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_invgrp, grp, d->ninv * sizeof(*grp), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    {   /* origin-aligned, zero-padded filters of the 4-sample fp32 inverse */
+        size_t nwi = 0;
+        for (int s = 0; s < S; s++) {
+            const int dl = (4 - sc[s].c % 4) % 4;
+            sc[s].ci = sc[s].c + dl;
+            sc[s].Li4 = (sc[s].L + dl + 3) & ~3;
+            sc[s].inv4 = (f->N % 4 == 0) && (sc[s].D % 4 == 0) && !env_long("TSPWS_NO_INV4", 0);
+            sc[s].wi_off = (int)nwi;
+            if (sc[s].inv4) nwi += (size_t)sc[s].Li4;
+        }
+        float *wi = (float *)calloc((nwi ? nwi : 4) * 2, sizeof(float));
+        if (!wi) goto done;
+        for (int s = 0; s < S; s++) {
+            if (!sc[s].inv4) continue;
+            const int dl = sc[s].ci - sc[s].c;
+            for (int l = 0; l < sc[s].L; l++) {
+                wi[2 * ((size_t)sc[s].wi_off + dl + l)]     = w32[2 * (f->tap_off[s] + l)];
+                wi[2 * ((size_t)sc[s].wi_off + dl + l) + 1] = w32[2 * (f->tap_off[s] + l) + 1];
+            }
+        }
+        int bad = cudaMalloc(&d->d_wi32, (nwi ? nwi : 4) * 2 * sizeof(float)) != cudaSuccess ||
+                  cudaMemcpy(d->d_wi32, wi, (nwi ? nwi : 4) * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess;
+        free(wi);
+        if (bad) goto done;
+    }
+    {   /* polyphase inverse (D >= 32, N % D == 0): reversed phase rows + items; the other scales go to
+         * the 4-sample kernel, one group each */
+        size_t ngi = 0;
+        int ni2 = 0, n4 = 0;
+        const int noinv2 = (int)env_long("TSPWS_NO_INV2", 0);
+        for (int s = 0; s < S; s++) {
+            const int D = sc[s].D;
+            sc[s].Qi = (sc[s].Li4 + D - 1) / D;
+            sc[s].inv2 = !noinv2 && D >= 32 && (f->N % D == 0);
+            sc[s].gi_off = (int)ngi;
+            if (sc[s].inv2) {
+                ngi += (size_t)(sc[s].Qi + 8) * D;
+                ni2 += ((sc[s].Ns + 7) / 8) * ((D + 31) / 32);
+            } else n4++;
+        }
+        float *gi = (float *)calloc((ngi ? ngi : 1) * 2, sizeof(float));
+        int *it2 = (int *)calloc((size_t)(ni2 ? ni2 : 1) * 4, sizeof(int));
+        tspws_inv_group_t *g4 = (tspws_inv_group_t *)calloc(n4 ? n4 : 1, sizeof(*g4));
+        if (!gi || !it2 || !g4) { free(gi); free(it2); free(g4); goto done; }
+        int k = 0, k4 = 0;
+        for (int s = 0; s < S; s++) {
+            if (!sc[s].inv2) { g4[k4].s0 = s; g4[k4].s1 = s + 1; k4++; continue; }
+            const int D = sc[s].D, Qi = sc[s].Qi, dl = sc[s].ci - sc[s].c;
+            for (int t = 0; t < Qi; t++)
+                for (int rho = 0; rho < D; rho++) {
+                    const int l = rho + (Qi - 1 - t) * D - dl;          /* tap of the original filter */
+                    if (l < 0 || l >= sc[s].L) continue;
+                    gi[2 * ((size_t)sc[s].gi_off + (size_t)t * D + rho)]     = w32[2 * (f->tap_off[s] + l)];
+                    gi[2 * ((size_t)sc[s].gi_off + (size_t)t * D + rho) + 1] = w32[2 * (f->tap_off[s] + l) + 1];
+                }
+            for (int a0 = 0; a0 < sc[s].Ns; a0 += 8)
+                for (int pb = 0; pb < (D + 31) / 32; pb++) { it2[4 * k] = s; it2[4 * k + 1] = a0; it2[4 * k + 2] = pb; k++; }
+        }
+        int bad = cudaMalloc(&d->d_gi32, (ngi ? ngi : 1) * 2 * sizeof(float)) != cudaSuccess ||
+                  cudaMemcpy(d->d_gi32, gi, (ngi ? ngi : 1) * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+                  cudaMalloc((void **)&d->d_items_inv2, (size_t)(ni2 ? ni2 : 1) * 4 * sizeof(int)) != cudaSuccess ||
+                  cudaMemcpy(d->d_items_inv2, it2, (size_t)ni2 * 4 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                  cudaMalloc((void **)&d->d_invgrp4, (size_t)(n4 ? n4 : 1) * sizeof(*g4)) != cudaSuccess ||
+                  cudaMemcpy(d->d_invgrp4, g4, (size_t)n4 * sizeof(*g4), cudaMemcpyHostToDevice) != cudaSuccess;
+        free(gi); free(it2); free(g4);
+        if (bad) goto done;
+        d->nitems_inv2 = ni2; d->ninv4 = n4;
+        d->inv_slots = S > d->ninv ? S : d->ninv;
+    }
+    {   /* 16-coefficient tiles of all scales (work list of the combine kernel) */
+        int nt = 0;
+        for (int s = 0; s < S; s++) nt += (sc[s].Ns + 15) / 16;
+        int *tl = (int *)malloc((size_t)(nt ? nt : 1) * 4 * sizeof(int));
+        if (!tl) goto done;
+        int k = 0;
+        for (int s = 0; s < S; s++)
+            for (int m0 = 0; m0 < sc[s].Ns; m0 += 16) {
+                const int nv = sc[s].Ns - m0 < 16 ? sc[s].Ns - m0 : 16;
+                tl[4 * k] = sc[s].ypart_off + m0; tl[4 * k + 1] = sc[s].coef_off + m0;
+                tl[4 * k + 2] = nv | (sc[s].nsplit << 8); tl[4 * k + 3] = sc[s].Ns;
+                k++;
+            }
+        int bad = cudaMalloc((void **)&d->d_tile16, (size_t)(nt ? nt : 1) * 4 * sizeof(int)) != cudaSuccess ||
+                  cudaMemcpy(d->d_tile16, tl, (size_t)nt * 4 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess;
+        free(tl);
+        if (bad) goto done;
+        d->ntile16 = nt;
+    }
     if (cudaMalloc(&d->d_g32, (ng ? ng : 1) * 2 * sizeof(float)) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_g32, g32, (ng ? ng : 1) * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMalloc((void **)&d->d_items2, (nitems2 ? nitems2 : 1) * sizeof(*items2)) != cudaSuccess) goto done;
@@ -253,6 +345,8 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
         if (cudaMalloc(&d->d_w64, (f->ntaps ? f->ntaps : 1) * 2 * sizeof(double)) != cudaSuccess) goto done;
         if (cudaMemcpy(d->d_w64, f->w, f->ntaps * 2 * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     }
+    /* the scale records go up last: every block above fills some of their fields */
+    if (cudaMemcpy(d->d_scale, sc, S * sizeof(*sc), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     d->nitems = nitems;
     ok = 1;
 done:
@@ -264,7 +358,7 @@ void tspws_devframe_free(tspws_devframe_t *d)
 {
     cudaFree(d->d_scale); cudaFree(d->d_w32); cudaFree(d->d_w64);
     cudaFree(d->d_items); cudaFree(d->d_invgrp);
-    cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen);
+    cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen); cudaFree(d->d_tile16); cudaFree(d->d_wi32); cudaFree(d->d_gi32); cudaFree(d->d_items_inv2); cudaFree(d->d_invgrp4);
     memset(d, 0, sizeof(*d));
 }
 
@@ -330,6 +424,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
 {
     if (!pl) return;
     if (pl->exch_bound) { pl->d_gsum = (double *)pl->own_gsum; pl->d_exch = pl->own_exch; }
+    if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
     tspws_devframe_free(&pl->dev);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
     cudaFree(pl->d_part); cudaFree(pl->d_tickets); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
@@ -383,8 +478,8 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
         CK(cudaMalloc(&pl->d_pst, (size_t)pl->nchunk * ncoef * pl->csz));
     }
     CK(cudaMalloc(&pl->d_exch, 2 * ncoef * pl->csz));
-    CK(cudaMalloc(&pl->d_zout, ncoef * pl->csz));
-    CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.ninv ? pl->dev.ninv : 1) * max * (pl->csz / 2)));
+    CK(cudaMalloc(&pl->d_zout, ncoef * (pl->acc64 ? 2 * sizeof(double) : 4 * sizeof(float))));
+    CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.inv_slots ? pl->dev.inv_slots : 1) * max * (pl->csz / 2)));
     CK(cudaMemset(pl->d_exch, 0, 2 * ncoef * pl->csz));
     CK(cudaMalloc((void **)&pl->d_inv_tickets, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
     CK(cudaMemset(pl->d_inv_tickets, 0, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
@@ -480,11 +575,51 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     return 0;
 }
 
-int tspws_b200_plan_stack(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
+static int plan_stack_direct(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
 {
     int e = tspws_b200_plan_reduce(pl, d_sigall, stream);
     if (e) return e;
     return tspws_b200_plan_finish(pl, d_ls, d_tspws, stream);
+}
+
+/* One stack = a fixed sequence of launches with fixed arguments, so it is replayed as a CUDA graph
+ * (cuts the launch gaps between the short tail kernels).  Capture needs a non-legacy stream; when it
+ * is not possible (legacy default stream, profiling on, TSPWS_NO_GRAPH=1) the launches go directly. */
+int tspws_b200_plan_stack(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
+{
+    if (!pl) return TSPWS_ERR_NULL;
+    if (pl->graph_broken || !stream || tspws_cu_profile_enabled() || env_long("TSPWS_NO_GRAPH", 0))
+        return plan_stack_direct(pl, d_sigall, d_ls, d_tspws, stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (pl->gexec && (pl->g_x != d_sigall || pl->g_ls != d_ls || pl->g_ts != d_tspws)) {
+        cudaGraphExecDestroy(pl->gexec);
+        pl->gexec = NULL;
+    }
+    if (!pl->gexec) {
+        cudaGraph_t g = NULL;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            pl->graph_broken = 1;
+            return plan_stack_direct(pl, d_sigall, d_ls, d_tspws, stream);
+        }
+        const unsigned long n0 = tspws_cu_launch_count();
+        const int e = plan_stack_direct(pl, d_sigall, d_ls, d_tspws, stream);
+        const cudaError_t ce = cudaStreamEndCapture(s, &g);
+        pl->g_kernels = tspws_cu_launch_count() - n0;
+        tspws_cu_launch_count_add(0ul - pl->g_kernels);            /* nothing has run yet */
+        if (e || ce != cudaSuccess || !g || cudaGraphInstantiate(&pl->gexec, g, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            pl->gexec = NULL;
+            pl->graph_broken = 1;
+            return plan_stack_direct(pl, d_sigall, d_ls, d_tspws, stream);
+        }
+        cudaGraphDestroy(g);
+        pl->g_x = d_sigall; pl->g_ls = d_ls; pl->g_ts = d_tspws;
+    }
+    if (cudaGraphLaunch(pl->gexec, s) != cudaSuccess) { cudaGetLastError(); return TSPWS_ERR_CUDA; }
+    tspws_cu_launch_count_add(pl->g_kernels);
+    return 0;
 }
 
 int tspws_b200_plan_stacks_ptr(tspws_plan_t *pl, const void **d_st, const void **d_ps, unsigned int *K, int *is_f64)

@@ -96,8 +96,8 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
     CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.ninv ? F->acc.ninv : 1) * B * N * sizeof(float)));
+    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
+    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.inv_slots ? F->acc.inv_slots : 1) * B * N * sizeof(float)));
     CKR(cudaMalloc((void **)&d_scale, B * sizeof(double)));
     CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
     CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
@@ -184,8 +184,8 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     CKR(cudaMalloc(&d_ps64, (size_t)M * ncoef * 2 * sizeof(double)));
     CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.ninv ? F->acc.ninv : 1) * B * N * sizeof(float)));
+    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
+    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.inv_slots ? F->acc.inv_slots : 1) * B * N * sizeof(float)));
     CKR(cudaMalloc((void **)&d_scale, B * sizeof(double)));
     CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
     CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
@@ -313,8 +313,8 @@ int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, 
     CKR(cudaMalloc(&d_ypart, (size_t)B * (F.pt.ypart_len ? F.pt.ypart_len : 1) * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_Y, (size_t)B * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_P, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_scr, (size_t)2 * (F.acc.ninv ? F.acc.ninv : 1) * B * N * sizeof(float)));
+    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
+    CKR(cudaMalloc(&d_scr, (size_t)2 * (F.acc.inv_slots ? F.acc.inv_slots : 1) * B * N * sizeof(float)));
     CKR(cudaMalloc(&d_sst, ncoef * 2 * sizeof(double)));
     CKR(cudaMalloc(&d_sps, ncoef * 2 * sizeof(double)));
     CKR(cudaMalloc((void **)&d_sim, 2 * B * sizeof(double)));
