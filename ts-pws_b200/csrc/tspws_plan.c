@@ -53,6 +53,10 @@ struct tspws_plan {
     const void *g_x, *g_ls, *g_ts;
     unsigned long g_kernels;
     int    graph_broken;
+    /* two-stage overlap: the transforms of finished groups run on a side stream under the colsum of later groups */
+    cudaStream_t side;
+    cudaEvent_t  ev_seg[16], ev_join;
+    int         *h_slot_off;        /* [K+1] first work item of every group */
     void  *own_gsum, *own_exch;
 };
 
@@ -414,6 +418,7 @@ static int twostage_build(tspws_plan_t *pl)
     if (cudaMemcpy(pl->d_cs, it, ni * sizeof(*it), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_slot_off, slot_off, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_grp_t0, grp_t0, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    pl->h_slot_off = slot_off; slot_off = NULL;
     rc = 0;
 done:
     free(grp_t0); free(slot_off); free(it);
@@ -425,6 +430,8 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     if (!pl) return;
     if (pl->exch_bound) { pl->d_gsum = (double *)pl->own_gsum; pl->d_exch = pl->own_exch; }
     if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
+    if (pl->side) { cudaStreamDestroy(pl->side); cudaEventDestroy(pl->ev_join); for (int i = 0; i < 16; i++) cudaEventDestroy(pl->ev_seg[i]); }
+    free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
     cudaFree(pl->d_part); cudaFree(pl->d_tickets); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
@@ -481,6 +488,13 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     CK(cudaMalloc(&pl->d_zout, ncoef * (pl->acc64 ? 2 * sizeof(double) : 4 * sizeof(float))));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.inv_slots ? pl->dev.inv_slots : 1) * max * (pl->csz / 2)));
     CK(cudaMemset(pl->d_exch, 0, 2 * ncoef * pl->csz));
+    if (pl->two_stage && pl->dev.per_trace && mtr_local == mtr_total && env_long("TSPWS_OVERLAP", 1)) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        CK(cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
+        for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&pl->ev_seg[i], cudaEventDisableTiming));
+    }
     CK(cudaMalloc((void **)&pl->d_inv_tickets, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
     CK(cudaMemset(pl->d_inv_tickets, 0, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
     return pl;
@@ -575,8 +589,49 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     return 0;
 }
 
+/* EXPERIMENT (off by default, TSPWS_OVERLAP=1): two-stage stack with the tail hidden under the stream:
+ * the groups are cut into a few segments; as soon as the colsum of a segment has finished, its
+ * group_post + forward transforms run on a high-priority side stream while the main stream keeps
+ * streaming the next segment.  Measured on B200 (8192 x 16384, Kmax = 10): 1 segment 162 us, 2: 195 us,
+ * 4: 199 us, 10: 244 us -- cutting the HBM stream into several launches costs more than the overlap
+ * hides (each segment under-fills the SMs and the co-running transforms steal issue slots). */
+static int plan_stack_overlap(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
+{
+    cudaStream_t A = (cudaStream_t)stream, B = pl->side;
+    const int K = (int)pl->K;
+    int nseg = (int)env_long("TSPWS_OVERLAP_SEGS", 4);
+    if (nseg > K) nseg = K;
+    if (nseg > 16) nseg = 16;
+    if (nseg < 1) nseg = 1;
+    const size_t N = (size_t)pl->N;
+    pl->summed_across_ranks = 0;
+    for (int sgm = 0; sgm < nseg; sgm++) {
+        /* later segments are shorter: what they leave exposed after the stream ends is smaller */
+        const int g0 = (int)((long)K * sgm * (2 * nseg - sgm + 1) / ((long)nseg * (nseg + 1)));
+        const int g1 = (int)((long)K * (sgm + 1) * (2 * nseg - sgm) / ((long)nseg * (nseg + 1)));
+        if (g1 <= g0) continue;
+        const int i0 = pl->h_slot_off[g0], i1 = pl->h_slot_off[g1];
+        if (tspws_cu_colsum(d_sigall, pl->N, pl->d_cs + i0, i1 - i0, pl->d_part, pl->d_slot_off, pl->d_tickets,
+                            pl->d_gsum, pl->d_gtile, A)) return TSPWS_ERR_CUDA;
+        if (cudaEventRecord(pl->ev_seg[sgm], A) != cudaSuccess) return TSPWS_ERR_CUDA;
+        if (cudaStreamWaitEvent(B, pl->ev_seg[sgm], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
+        if (tspws_cu_group_post(pl->d_gsum + g0 * N, pl->d_gsum32 + g0 * N, g1 - g0, pl->N, pl->d_gtile + (size_t)g0 * pl->ntile,
+                                pl->ntile, pl->p.lrm, pl->p.fold, B)) return TSPWS_ERR_CUDA;
+        if (tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32 + g0 * N, g1 - g0,
+                                      (float *)pl->d_ypart + 2 * (size_t)g0 * pl->dev.ypart_len, B)) return TSPWS_ERR_CUDA;
+    }
+    if (cudaEventRecord(pl->ev_join, B) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (cudaStreamWaitEvent(A, pl->ev_join, 0) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, plan_ps(pl), plan_st(pl), pl->d_zout, A)) return TSPWS_ERR_CUDA;
+    if (tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), 0, 1, pl->d_rule, pl->d_invscratch, pl->d_inv_tickets,
+                         d_tspws, d_ls, A)) return TSPWS_ERR_CUDA;
+    return 0;
+}
+
 static int plan_stack_direct(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
 {
+    if (pl->side && !tspws_cu_profile_enabled() && !pl->exch_bound)
+        return plan_stack_overlap(pl, d_sigall, d_ls, d_tspws, stream);
     int e = tspws_b200_plan_reduce(pl, d_sigall, stream);
     if (e) return e;
     return tspws_b200_plan_finish(pl, d_ls, d_tspws, stream);
