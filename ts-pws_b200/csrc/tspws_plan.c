@@ -488,7 +488,7 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     CK(cudaMalloc(&pl->d_zout, ncoef * (pl->acc64 ? 2 * sizeof(double) : 4 * sizeof(float))));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.inv_slots ? pl->dev.inv_slots : 1) * max * (pl->csz / 2)));
     CK(cudaMemset(pl->d_exch, 0, 2 * ncoef * pl->csz));
-    if (pl->two_stage && pl->dev.per_trace && mtr_local == mtr_total && env_long("TSPWS_OVERLAP", 1)) {
+    if (pl->two_stage && pl->dev.per_trace && mtr_local == mtr_total && env_long("TSPWS_OVERLAP", 0)) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         CK(cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi));
