@@ -195,6 +195,7 @@ int tspws_cu_simil(const float *d_cand, int B, int N, const float *d_ref, double
 int tspws_cu_lsconv(const float *d_x, int ntr, int N, const float *d_ref, float *d_steps, double *d_part,
                     double *d_sim, double *d_mis, tspws_stream_t st);
 
+void tspws_cu_inverse_side_stream(tspws_stream_t side);
 unsigned long tspws_cu_launch_count(void);
 void tspws_cu_profile_mark(tspws_stream_t st);
 int  tspws_cu_profile_enabled(void);

@@ -861,45 +861,58 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
 }
 
 /* per-trace coefficients -> PS, ST, Zout.
- * A CTA covers 16 consecutive coefficients of one scale; its 256 threads are 16 coefficients x 16
- * trace slots, so that the loads of the `seg` traces (and of the phase splits of coarse scales) are
- * all in flight at once instead of forming one long latency chain per coefficient; the 16 slots
- * are then added in slot order through shared memory (deterministic).
- * grid = (16-coefficient tiles of all scales, segments). */
+ * A CTA covers 64 consecutive coefficients of one scale; its 256 threads are 64 coefficients x 4
+ * trace slots (slot j takes traces j, j+4, ...), so that the loads of the `seg` traces (and of the
+ * phase splits of coarse scales) are in flight together instead of forming one latency chain per
+ * coefficient; the 4 slots are then added in slot order through shared memory (deterministic).
+ * grid = (64-coefficient tiles of all scales, segments): one wave at the headline size. */
+#define PC_TILE 64
 __global__ void __launch_bounds__(256)
 phasor_combine_kernel(const int4 *__restrict__ tiles,
                       const float2 *__restrict__ ypart, int ypart_len,
                       int ncoef, int seg, const tspws_weight_t *__restrict__ rules,
                       float2 *__restrict__ ps, float2 *__restrict__ st, float2 *__restrict__ zout)
 {
-    __shared__ float  s_p[16][16][2];
-    __shared__ double s_s[16][16][2];
+    __shared__ float  s_p[4][PC_TILE][2];
+    __shared__ double s_s[4][PC_TILE][2];
     /* tile = (offset in a trace's partial-Y block, offset in the coefficient arrays, valid
      * coefficients | nsplit << 8, Ns = stride between phase splits) */
     const int4 tile = tiles[blockIdx.x];
-    const int ci = threadIdx.x & 15, slot = threadIdx.x >> 4;
+    const int ci = threadIdx.x & (PC_TILE - 1), slot = threadIdx.x / PC_TILE;
     const int nvalid = tile.z & 255, nsplit = tile.z >> 8, Ns = tile.w;
     const int sg = blockIdx.y;
     float pr = 0.f, pi = 0.f;
     double sr = 0.0, si = 0.0;
     if (ci < nvalid) {
-        for (int k = slot; k < seg; k += 16) {
-            const float2 *yp = ypart + (size_t)(sg * seg + k) * ypart_len + tile.x + ci;
-            float re = 0.f, im = 0.f;
+        const float2 *yp0 = ypart + (size_t)sg * seg * ypart_len + tile.x + ci;
+        if (nsplit == 1) {
+#pragma unroll 4
+            for (int k = slot; k < seg; k += 4) {
+                const float2 y = __ldcg(yp0 + (size_t)k * ypart_len);
+                float a, b;
+                phasor_fast(y.x, y.y, a, b);
+                pr += a; pi += b; sr += (double)y.x; si += (double)y.y;
+            }
+        } else {
+            for (int k = slot; k < seg; k += 4) {
+                const float2 *yp = yp0 + (size_t)k * ypart_len;
+                float re = 0.f, im = 0.f;
 #pragma unroll 8
-            for (int sp = 0; sp < nsplit; sp++) { const float2 y = __ldcg(yp + (size_t)sp * Ns); re += y.x; im += y.y; }
-            float a, b;
-            phasor_fast(re, im, a, b);
-            pr += a; pi += b; sr += (double)re; si += (double)im;
+                for (int sp = 0; sp < nsplit; sp++) { const float2 y = __ldcg(yp + (size_t)sp * Ns); re += y.x; im += y.y; }
+                float a, b;
+                phasor_fast(re, im, a, b);
+                pr += a; pi += b; sr += (double)re; si += (double)im;
+            }
         }
     }
     s_p[slot][ci][0] = pr; s_p[slot][ci][1] = pi;
     s_s[slot][ci][0] = sr; s_s[slot][ci][1] = si;
     __syncthreads();
     if (slot != 0 || ci >= nvalid) return;
-    pr = pi = 0.f; sr = si = 0.0;
-#pragma unroll
-    for (int j = 0; j < 16; j++) { pr += s_p[j][ci][0]; pi += s_p[j][ci][1]; sr += s_s[j][ci][0]; si += s_s[j][ci][1]; }
+    pr = ((s_p[0][ci][0] + s_p[1][ci][0]) + s_p[2][ci][0]) + s_p[3][ci][0];
+    pi = ((s_p[0][ci][1] + s_p[1][ci][1]) + s_p[2][ci][1]) + s_p[3][ci][1];
+    sr = ((s_s[0][ci][0] + s_s[1][ci][0]) + s_s[2][ci][0]) + s_s[3][ci][0];
+    si = ((s_s[0][ci][1] + s_s[1][ci][1]) + s_s[2][ci][1]) + s_s[3][ci][1];
     const double f = weight_factor(rules[sg], (double)pr, (double)pi);
     const size_t o = (size_t)sg * ncoef + tile.y + ci;
     ps[o]   = make_float2(pr, pi);
@@ -1662,6 +1675,19 @@ static int inv_launch(const tspws_devframe_t *f, const void *d_zout, const void 
     return 0;
 }
 
+/* optional side stream + two events: when set, the two independent halves of the fp32 inverse
+ * (polyphase kernel, 4-sample kernel) run concurrently (fork / join, also inside a graph capture) */
+static cudaStream_t g_inv_side = nullptr;
+static cudaEvent_t  g_inv_fork = nullptr, g_inv_join = nullptr;
+extern "C" void tspws_cu_inverse_side_stream(tspws_stream_t side)
+{
+    g_inv_side = (cudaStream_t)side;
+    if (side && !g_inv_fork) {
+        cudaEventCreateWithFlags(&g_inv_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g_inv_join, cudaEventDisableTiming);
+    }
+}
+
 extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, const void *d_st, int acc64,
                                 int nseg, const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
                                 float *d_out_ts, float *d_out_ls, tspws_stream_t st)
@@ -1674,6 +1700,11 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
      * 4-sample kernel for the rest); the finish kernel adds the slots in scale order. */
     cudaStream_t s = (cudaStream_t)st;
     const int S = f->S;
+    const bool fork = g_inv_side && !g_prof.on && f->nitems_inv2 > 0 && f->ninv4 > 0 && g_inv_side != s;
+    cudaStream_t s4 = fork ? g_inv_side : s;
+    if (fork) {
+        if (cudaEventRecord(g_inv_fork, s) != cudaSuccess || cudaStreamWaitEvent(s4, g_inv_fork, 0) != cudaSuccess) return (int)cudaGetLastError();
+    }
     if (f->nitems_inv2 > 0) {
         dim3 grid((f->nitems_inv2 + 3) / 4, nseg);
         if (d_st) inv2_kernel<true><<<grid, 128, 0, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
@@ -1685,12 +1716,15 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
     if (f->ninv4 > 0) {
         dim3 grid((f->N + 4 * INV4_THREADS - 1) / (4 * INV4_THREADS), f->ninv4, nseg);
         if (d_st)
-            inv4_kernel<true, false><<<grid, INV4_THREADS, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, (const float2 *)f->d_wi32, f->d_invgrp4, S,
+            inv4_kernel<true, false><<<grid, INV4_THREADS, 0, s4>>>(f->d_scale, (const float2 *)f->d_w32, (const float2 *)f->d_wi32, f->d_invgrp4, S,
                 f->N, f->ncoef, (const float4 *)d_zout, (float *)d_scratch, nseg, d_tickets, d_rules, d_out_ts, d_out_ls);
         else
-            inv4_kernel<false, false><<<grid, INV4_THREADS, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, (const float2 *)f->d_wi32, f->d_invgrp4, S,
+            inv4_kernel<false, false><<<grid, INV4_THREADS, 0, s4>>>(f->d_scale, (const float2 *)f->d_w32, (const float2 *)f->d_wi32, f->d_invgrp4, S,
                 f->N, f->ncoef, (const float4 *)d_zout, (float *)d_scratch, nseg, d_tickets, d_rules, d_out_ts, d_out_ls);
-        TSPWS_LAUNCHED_N("inv4_kernel", s);
+        TSPWS_LAUNCHED_N("inv4_kernel", s4);
+    }
+    if (fork) {
+        if (cudaEventRecord(g_inv_join, s4) != cudaSuccess || cudaStreamWaitEvent(s, g_inv_join, 0) != cudaSuccess) return (int)cudaGetLastError();
     }
     {
         dim3 grid((f->N + 255) / 256, nseg);

@@ -53,6 +53,7 @@ struct tspws_plan {
     const void *g_x, *g_ls, *g_ts;
     unsigned long g_kernels;
     int    graph_broken;
+    int    overlap;
     /* two-stage overlap: the transforms of finished groups run on a side stream under the colsum of later groups */
     cudaStream_t side;
     cudaEvent_t  ev_seg[16], ev_join;
@@ -321,13 +322,13 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
     }
     {   /* 16-coefficient tiles of all scales (work list of the combine kernel) */
         int nt = 0;
-        for (int s = 0; s < S; s++) nt += (sc[s].Ns + 15) / 16;
+        for (int s = 0; s < S; s++) nt += (sc[s].Ns + 63) / 64;
         int *tl = (int *)malloc((size_t)(nt ? nt : 1) * 4 * sizeof(int));
         if (!tl) goto done;
         int k = 0;
         for (int s = 0; s < S; s++)
-            for (int m0 = 0; m0 < sc[s].Ns; m0 += 16) {
-                const int nv = sc[s].Ns - m0 < 16 ? sc[s].Ns - m0 : 16;
+            for (int m0 = 0; m0 < sc[s].Ns; m0 += 64) {
+                const int nv = sc[s].Ns - m0 < 64 ? sc[s].Ns - m0 : 64;
                 tl[4 * k] = sc[s].ypart_off + m0; tl[4 * k + 1] = sc[s].coef_off + m0;
                 tl[4 * k + 2] = nv | (sc[s].nsplit << 8); tl[4 * k + 3] = sc[s].Ns;
                 k++;
@@ -488,7 +489,8 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     CK(cudaMalloc(&pl->d_zout, ncoef * (pl->acc64 ? 2 * sizeof(double) : 4 * sizeof(float))));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.inv_slots ? pl->dev.inv_slots : 1) * max * (pl->csz / 2)));
     CK(cudaMemset(pl->d_exch, 0, 2 * ncoef * pl->csz));
-    if (pl->two_stage && pl->dev.per_trace && mtr_local == mtr_total && env_long("TSPWS_OVERLAP", 0)) {
+    pl->overlap = pl->two_stage && pl->dev.per_trace && mtr_local == mtr_total && env_long("TSPWS_OVERLAP", 0);
+    if (!pl->acc64 && env_long("TSPWS_SIDE_STREAM", 1)) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         CK(cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi));
@@ -584,9 +586,11 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     } else if (pl->summed_across_ranks) {
         if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), 0, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     }
-    if ((e = tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), pl->acc64, 1, pl->d_rule, pl->d_invscratch,
-                              pl->d_inv_tickets, d_tspws, d_ls, stream))) return TSPWS_ERR_CUDA;
-    return 0;
+    tspws_cu_inverse_side_stream(pl->side);
+    e = tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), pl->acc64, 1, pl->d_rule, pl->d_invscratch,
+                         pl->d_inv_tickets, d_tspws, d_ls, stream);
+    tspws_cu_inverse_side_stream(NULL);
+    return e ? TSPWS_ERR_CUDA : 0;
 }
 
 /* EXPERIMENT (off by default, TSPWS_OVERLAP=1): two-stage stack with the tail hidden under the stream:
@@ -630,7 +634,7 @@ static int plan_stack_overlap(tspws_plan_t *pl, float *d_sigall, float *d_ls, fl
 
 static int plan_stack_direct(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
 {
-    if (pl->side && !tspws_cu_profile_enabled() && !pl->exch_bound)
+    if (pl->overlap && pl->side && !tspws_cu_profile_enabled() && !pl->exch_bound)
         return plan_stack_overlap(pl, d_sigall, d_ls, d_tspws, stream);
     int e = tspws_b200_plan_reduce(pl, d_sigall, stream);
     if (e) return e;
