@@ -523,37 +523,43 @@ template <int NPEND>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(NPEND) : "memory"); }
 
 /* One pass: 16 coefficients x Qs taps of one phase.
- *   loadx(): next window sample (called once per sample, in order), loadg(q): filter tap q
- *   (the filter array is zero-padded by 8 taps, the window source by 24 samples: no guards).
- * The window lives in a 24-slot register ring (slot = j mod 24) so that every index is static after
- * unrolling 24 taps; a slot is refilled right after its last use, i.e. 8 taps before it is needed
- * again, and filter taps are refilled 8 taps ahead -- loads never stall the FMAs.
+ *   loadx(j): window sample j of the current 32-tap block (j is a compile-time constant after
+ *   unrolling, so addresses are immediates), loadg(q): filter tap q of the block, advance(): step
+ *   both to the next 32-tap block.  Qs is a multiple of 4 (the host pads the filters with zero
+ *   taps), the window source holds Qs + 32 samples and the filter array Qs + 8 taps, so only one
+ *   uniform guard per 4 taps remains.
+ * The window lives in a 32-slot register ring (slot = j mod 32): every index is static after
+ * unrolling 32 taps; a slot is refilled right after its last use, 16 taps before it is needed again,
+ * filter taps 4 taps ahead -- loads never stall the FMAs.
  * Arithmetic is Blackwell's packed FFMA2 (fma.rn.f32x2): one instruction updates (Re, Im) of a
- * coefficient, acc2[r] += (x, x) * (g.re, g.im); the window keeps every sample duplicated. */
-#define FW_WS 24
-template <typename LoadX, typename LoadG>
-__device__ __forceinline__ void fw_taps(float2 (&acc)[FW_R], const int Qs, LoadX loadx, LoadG loadg)
+ * coefficient, acc[r] += x * (g.re, g.im). */
+#define FW_WS 32
+template <typename LoadX, typename LoadG, typename Advance>
+__device__ __forceinline__ void fw_taps(float2 (&acc)[FW_R], const int Qs, LoadX loadx, LoadG loadg, Advance advance)
 {
     float2 win[FW_WS];
-    float2 gq[8];
+    float2 gq[4];
 #pragma unroll
-    for (int j = 0; j < FW_WS; j++) { const float t = loadx(); win[j] = make_float2(t, t); }
+    for (int j = 0; j < FW_WS; j++) { const float t = loadx(j); win[j] = make_float2(t, t); }
 #pragma unroll
-    for (int q = 0; q < 8; q++) gq[q] = loadg(q);
+    for (int q = 0; q < 4; q++) gq[q] = loadg(q);
     for (int t0 = 0; t0 < Qs; t0 += FW_WS) {
 #pragma unroll
-        for (int tt = 0; tt < FW_WS; tt++) {
-            if (t0 + tt < Qs) {
-                const float2 gv = gq[tt & 7];
+        for (int tq = 0; tq < FW_WS; tq += 4) {
+            if (t0 + tq < Qs) {
 #pragma unroll
-                for (int r = 0; r < FW_R; r++) acc[r] = __ffma2_rn(win[(tt + r) % FW_WS], gv, acc[r]);
-                if (t0 + tt + FW_WS - FW_R + 1 < Qs) {      /* sample t+24 is used by taps >= t+9 only */
-                    const float t = loadx();
-                    win[tt] = make_float2(t, t);
+                for (int u = 0; u < 4; u++) {
+                    const int tt = tq + u;
+                    const float2 gv = gq[tt & 3];
+#pragma unroll
+                    for (int r = 0; r < FW_R; r++) acc[r] = __ffma2_rn(win[(tt + r) % FW_WS], gv, acc[r]);
+                    const float t = loadx(tt + FW_WS);
+                    win[tt]    = make_float2(t, t);
+                    gq[tt & 3] = loadg(tt + 4);
                 }
-                if (t0 + tt + 8 < Qs) gq[tt & 7] = loadg(t0 + tt + 8);
             }
         }
+        advance();
     }
 }
 
@@ -603,7 +609,7 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
     const int base = (int)b0;                      /* sample of (tile 0, tap 0, phase 0)     */
 
     /* LG < 5: D = 2^LG phases x (32 >> LG) tiles; window staged by cp.async, double buffered.
-     * 24 samples more than needed are staged so that the register ring refills need no guard. */
+     * 32 samples more than needed are staged so that the register ring refills need no guard. */
     const int  W      = (TILES * FW_R + Qs + FW_WS) * LP;
     const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     if (LG < 5) {
@@ -611,6 +617,42 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
         fw_stage<LGS>(xs, x + (size_t)k_begin * N, base, W, N, lane, vec_ok);
         cp_async_commit();
     }
+
+    /* LG == 5: per (trace, block of 32 phases) the Qs+15 window rows of 32 consecutive samples are
+     * staged by cp.async into a warp-private double buffer one pass ahead (16-byte copies when the
+     * geometry allows), so the FMA loop only ever waits on shared memory. */
+    const int npb = it.pb1 - it.pb0;
+    const int nrows = Qs + FW_WS;                 /* the register ring reads 32 rows ahead, unguarded */
+    const bool vec5 = vec_ok && (D % 4 == 0);
+    auto stage5 = [&](float *buf, const int k, const int pb) {
+        const float *__restrict__ xk = x + (size_t)k * N;
+        if (vec5) {
+            int row = lane >> 3;
+            const int q4 = (lane & 7) * 4;
+            long long p0 = ((long long)base + pb * 32 + q4 + (long long)row * D) % N;
+            int pos = (int)p0;
+            const int step = (int)((4LL * D) % N);
+            for (; row < nrows; row += 4) {
+                cp_async<16>(buf + row * 32 + q4, xk + pos);
+                pos += step;
+                if (pos >= N) pos -= N;
+            }
+        } else {
+            int pos = (int)(((long long)base + pb * 32 + lane) % N);
+            const int step = D % N;
+            for (int row = 0; row < nrows; row++) {
+                cp_async<4>(buf + row * 32 + lane, xk + pos);
+                pos += step;
+                if (pos >= N) pos -= N;
+            }
+        }
+    };
+    if (LG == 5) {
+        __syncwarp();
+        stage5(xs, k_begin, it.pb0);
+        cp_async_commit();
+    }
+    int pass = 0;
 
     for (int k = k_begin; k < k_end; k++) {
         const float *__restrict__ xk = x + (size_t)k * N;
@@ -629,26 +671,38 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
             }
             __syncwarp();
             const int a = lane >> LGS, rho = lane & (LP - 1);
-            const float  *xw = cur + a * ((FW_R + 1) * LP) + rho;
-            const float2 *gr = g + rho;
-            int j = 0;
+            const float  *xb = cur + a * ((FW_R + 1) * LP) + rho;      /* sample j of the block at (j + (j >> 4)) LP */
+            const float2 *gb = g + rho;
             fw_taps(acc, Qs,
-                    [&]() { const float r = xw[(j + (j >> 4)) << LGS]; j++; return r; },
-                    [&](const int q) { return __ldg(gr + q * LP); });
+                    [&](const int j) { return xb[(j + (j >> 4)) * LP]; },
+                    [&](const int q) { return __ldg(gb + q * LP); },
+                    [&]() { xb += 34 * LP; gb += 32 * LP; });
             __syncwarp();
         } else {
-            /* D >= 32: 32 consecutive phases per block, samples straight from global / L1; the
-             * filter rows are zero-padded to a multiple of 32 phases, so idle lanes add zeros */
+            /* D >= 32: 32 consecutive phases per block; the filter rows are zero-padded to a multiple
+             * of 32 phases, so idle lanes add zeros */
             const int GS = (D + 31) & ~31;
-            for (int pb = it.pb0; pb < it.pb1; pb++) {
-                int pos = base + pb * 32 + lane;
-                if (pos >= N) pos -= N;
-                if (pos >= N) pos -= N;
-                const float2 *gr = g + pb * 32 + lane;
+            for (int pb = it.pb0; pb < it.pb1; pb++, pass++) {
+                const float *cur = xs + (pass & 1) * xs_half;
+                int kn = k, pbn = pb + 1;
+                if (pbn == it.pb1) { pbn = it.pb0; kn = k + 1; }
+                if (kn < k_end) {
+                    stage5(xs + ((pass & 1) ^ 1) * xs_half, kn, pbn);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncwarp();
+                const float  *xb = cur + lane;
+                const float2 *gp = g + pb * 32 + lane;                  /* taps are consumed strictly in order */
                 fw_taps(acc, Qs,
-                        [&]() { const float r = xk[pos]; pos += D; if (pos >= N) pos -= N; return r; },
-                        [&](const int q) { return __ldg(gr + (size_t)q * GS); });
+                        [&](const int j) { return xb[j * 32]; },
+                        [&](const int) { const float2 v = __ldg(gp); gp += GS; return v; },
+                        [&]() { xb += 32 * 32; });
+                __syncwarp();
             }
+            (void)npb;
         }
         float(&v)[2 * FW_R] = reinterpret_cast<float(&)[2 * FW_R]>(acc);
 
@@ -835,7 +889,7 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
         dim3 grid((unsigned)(((nchunk + cb - 1) / cb) * nig * cb));                                      \
         if (smem > 48 * 1024)                                                                           \
             cudaFuncSetAttribute(fwd2_acc_kernel<LGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        fwd2_acc_kernel<LGV><<<grid, FW_WARPS * 32, (LGV < 5 ? smem : 0), s>>>(f->d_scale, (const float2 *)f->d_g32, \
+        fwd2_acc_kernel<LGV><<<grid, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, \
             f->d_items2, f->fw_lg_begin[LGV], f->fw_lg_begin[LGV + 1], d_x, f->N, ntr, chunk, f->ncoef,  \
             (float2 *)d_part_ps, (float2 *)d_part_st, f->fw_smem_per_warp, cb);                          \
         TSPWS_LAUNCHED_N("fwd2_acc_kernel<" #LGV ">", s);                                                                               \

@@ -134,16 +134,20 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
             const int L = sc[s].L, c = sc[s].c, D = sc[s].D, Ns = sc[s].Ns;
             const int e = (D - c % D) % D;
             sc[s].A  = (c + e) / D;
-            sc[s].Qs = (e + L + D - 1) / D;
+            sc[s].Qs = (((e + L + D - 1) / D) + 3) & ~3;            /* padded to a multiple of 4 with zero taps */
             sc[s].lg = -1;
             sc[s].nsplit = 1;
             if (Ns > d->max_Ns) d->max_Ns = Ns;
             if (!nofast && D <= N) {
-                if (D >= 32) sc[s].lg = 5;
+                if (D >= 32) {
+                    sc[s].lg = 5;
+                    const int need5 = 2 * (sc[s].Qs + 32) * 32;      /* double-buffered window rows */
+                    if (need5 > d->fw_smem_per_warp) d->fw_smem_per_warp = need5;
+                }
                 else if ((D & (D - 1)) == 0) {
                     int lg = 0; while ((1 << lg) < D) lg++;
                     const int tiles = 32 >> lg;
-                    const long W = ((long)tiles * 16 + sc[s].Qs + 24) * D;   /* + ring over-read */
+                    const long W = ((long)tiles * 16 + sc[s].Qs + 32) * D;   /* + ring over-read */
                     long need = W + (W / (16 * D) + 1) * D + 8;          /* skewed window + copy overrun */
                     need = 2 * ((need + 3) & ~3L);                       /* double buffered, 16 B aligned */
                     if (W <= N && need * 4 * 4 * 3 <= 200 * 1024) {
