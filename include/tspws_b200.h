@@ -187,6 +187,20 @@ int tspws_b200_profile(int enable);
 int tspws_b200_profile_reset(void);
 int tspws_b200_profile_read(char *buf, int cap);
 
+/* ---- data formats on either side of the path, no sacio.a needed ----
+ * tspws_b200_load_sac_list : reference ReadData, SAC-list branch (src/ts_pws1f.c:609-722)
+ * tspws_b200_load_bin      : reference ReadData, `bin` branch (src/ts_pws1f.c:586-608,664-675)
+ * tspws_b200_save_bin      : the container the reference's sac2bin writes (src/sac2bin.c:192-195)
+ * tspws_b200_write_sac     : reference wrsac (src/ts_pws1f.c:725-763)
+ * Traces are placed in page-locked memory when `pinned` and CUDA are available. */
+int  tspws_b200_load_sac_list(const char *listfile, t_data *in, int pinned);
+int  tspws_b200_load_bin(const char *binfile, t_data *in, int pinned);
+int  tspws_b200_save_bin(const char *binfile, const t_data *in, const char *method);
+int  tspws_b200_write_sac(const char *path, const float *y, const t_hdr *hdr, int npts, float beg,
+                          const char *kinst, float user0);
+long tspws_b200_read_sac(const char *path, float *data, long maxpts, float *dt, float *beg, void *header632);
+void tspws_b200_free_data(t_data *in);
+
 /* ---- device-resident API (inputs already in HBM; used by bench.py and multi-GPU) ---- */
 typedef struct tspws_plan tspws_plan_t;
 

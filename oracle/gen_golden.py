@@ -82,6 +82,43 @@ def run_reference_convergence(B, ref, case):
     return g
 
 
+REAL_DIR = "/root/reference/examples/ECH.00Z.CAN.00Z_500days"
+# the three runs of the reference's examples/example.sh:16,27,39 on the first 60 daily correlations
+REAL_CASES = {
+    "ex1_default": dict(),
+    "ex2_fmin_J3": dict(wu=2.0, lrm=1, fold=1, fmin=0.004, J=3),
+    "ex3_two_stage_unbiased": dict(wu=2.0, lrm=1, fold=1, fmin=0.004, J=3, Kmax=10, unbiased=1),
+}
+
+
+def read_sac_py(path):
+    """Independent little-endian SAC reader (struct-level) used to cross-check the C loader."""
+    raw = open(path, "rb").read()
+    f = np.frombuffer(raw[:280], dtype="<f4")
+    i = np.frombuffer(raw[280:440], dtype="<i4")
+    npts = int(i[9])
+    return dict(delta=float(f[0]), b=float(f[5]), npts=npts, data=np.frombuffer(raw[632:632 + 4 * npts], dtype="<f4").copy())
+
+
+def run_reference_real(B, ref):
+    files = sorted(os.listdir(REAL_DIR))[:60]
+    traces = [read_sac_py(os.path.join(REAL_DIR, f)) for f in files]
+    x = np.stack([t["data"] for t in traces]).astype(np.float32)
+    dt, beg = np.float32(traces[0]["delta"]), np.float32(traces[0]["b"])
+    g = dict(x=x, dt=dt, beg=beg)
+    for name, kw in REAL_CASES.items():
+        r = B.call_tspws_main(ref, x, B.default_params(**kw), dt=float(dt), beg=float(beg))
+        assert r["rc"] == 0
+        pp = r["params"]
+        rf = R.RefFrame(pp.type, pp.J, pp.V, x.shape[1], pp.s0, pp.b0, pp.w0, pp.uni)
+        st, ps, K = rf.stacks(r["sigall"], pp.Kmax)
+        rf.close()
+        g[name + "_ls"], g[name + "_tsPWS"] = r["ls"], r["tsPWS"]
+        g[name + "_ps"], g[name + "_st"], g[name + "_K"] = ps.astype(np.complex64), st.astype(np.complex64), np.int64(K)
+        g[name + "_derived"] = np.array([pp.J, pp.V, pp.s0, pp.b0, pp.w0, pp.fmin, pp.fold], dtype=np.float64)
+    return g
+
+
 def main():
     B = _pkg()
     ref = B.declare_reference(R.load())
@@ -91,6 +128,10 @@ def main():
         g = run_reference_resample(B, ref, case)
         np.savez_compressed(os.path.join(out, name + ".npz"), **g)
         print(f"{name}: M={g['sel'].shape[0]} K={g['sel'].sum(axis=1).tolist()} max|ts_sub|={np.abs(g['tsPWS_subsmpl']).max():.3e}")
+    if os.path.isdir(REAL_DIR):
+        g = run_reference_real(B, ref)
+        np.savez_compressed(os.path.join(out, "real_ech_can_60.npz"), **g)
+        print("real_ech_can_60:", g["x"].shape, "dt", g["dt"], "beg", g["beg"], [k for k in g if k.endswith("_K")])
     for name, case in CS.CONVERGENCE_CASES.items():
         g = run_reference_convergence(B, ref, case)
         np.savez_compressed(os.path.join(out, name + ".npz"), **g)

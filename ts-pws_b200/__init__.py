@@ -143,6 +143,14 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_kernel_launches.restype = C.c_ulong
     lib.tspws_b200_profile.argtypes = [C.c_int]
     lib.tspws_b200_profile_read.argtypes = [C.c_char_p, C.c_int]
+    lib.tspws_b200_load_sac_list.argtypes = [C.c_char_p, C.POINTER(Data), C.c_int]
+    lib.tspws_b200_load_bin.argtypes = [C.c_char_p, C.POINTER(Data), C.c_int]
+    lib.tspws_b200_save_bin.argtypes = [C.c_char_p, C.POINTER(Data), C.c_char_p]
+    lib.tspws_b200_write_sac.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.POINTER(Hdr), C.c_int, C.c_float, C.c_char_p, C.c_float]
+    lib.tspws_b200_read_sac.restype = C.c_long
+    lib.tspws_b200_read_sac.argtypes = [C.c_char_p, C.POINTER(C.c_float), C.c_long, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]
+    lib.tspws_b200_free_data.restype = None
+    lib.tspws_b200_free_data.argtypes = [C.POINTER(Data)]
     lib.tspws_b200_plan_create.restype = C.c_void_p
     lib.tspws_b200_plan_create.argtypes = [C.POINTER(TsPWS), C.c_int, C.c_uint, C.c_uint, C.c_uint]
     lib.tspws_b200_plan_destroy.restype = None
@@ -183,6 +191,8 @@ EXPORTS = [
     "tspws_b200_get_option", "tspws_b200_device_count", "tspws_b200_shutdown", "tspws_b200_version",
     "tspws_b200_kernel_launches", "tspws_b200_profile", "tspws_b200_profile_reset", "tspws_b200_profile_read", "tspws_b200_plan_create", "tspws_b200_plan_destroy",
     "tspws_b200_plan_reduce", "tspws_b200_plan_exchange_ptr", "tspws_b200_plan_exchange_bytes",
+    "tspws_b200_load_sac_list", "tspws_b200_load_bin", "tspws_b200_save_bin", "tspws_b200_write_sac",
+    "tspws_b200_read_sac", "tspws_b200_free_data",
     "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
     "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",
 ]
