@@ -212,3 +212,56 @@ def test_cli_end_to_end_on_bin_file(pkg, gpu_lib, tmp_path):
         s = read_sac_py(str(tmp_path / fname))
         assert s["npts"] == (n + 1) // 2 and s["delta"] == 4.0 and abs(s["b"] - (float(g["beg"]) + 4.0 * (n // 2))) < 1e-3
         assert O.nerr(s["data"], g["ex3_two_stage_unbiased_" + key][n // 2:]) <= TOL_STACK
+
+
+def _bench_traces(mtr, n):
+    """The bench's synthetic traces (SURVEY §8d recipe), generated like bench.py does."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.make_traces(mtr, n)
+
+
+def test_full_size_two_stage_headline_vs_oracle(pkg, gpu_lib):
+    """BASELINE headline shape, 8192 x 16384, Morlet, Kmax = 10, unbiased, rm: the oracle only needs the
+    10 group sums (numpy, float64) and 10 transforms, so the FULL size is checked against it directly."""
+    mtr, n = 8192, 16384
+    x = _bench_traces(mtr, n)
+    kw = dict(Kmax=10, unbiased=1, lrm=1)
+    ls, ts, coh = _plan_stack(pkg, gpu_lib, x, **kw)                 # device-resident path (fused mean removal)
+    p = O.derive_params(O.Params(**kw), n, 1.0)
+    fr = O.frame_from_params(p, n)
+    m = (x.astype(np.float64).sum(axis=1) / n).astype(np.float32)    # reference: float-cast mean, float subtraction
+    G = np.zeros((10, n))
+    g = O.group_index(mtr, 10)
+    for k in range(10):
+        sel = g == k
+        G[k] = (x[sel] - m[sel, None]).astype(np.float64).sum(axis=0)
+    st, ps = O.stacks(fr, G)
+    o_ts = O.synthesis(fr, O.weight(st, ps, 10, mtr, 2.0, True)).astype(np.float32)
+    o_ls = O.synthesis(fr, st).astype(np.float32) / np.float32(mtr)
+    assert O.nerr(coh, np.abs(ps) / 10) <= TOL_COH
+    assert O.nerr(ls, o_ls) <= TOL_STACK
+    assert O.nerr(ts, o_ts) <= TOL_STACK
+    # and the host path (tspws_main, exact in-place mean removal) on the same traces
+    r = gpu_run(pkg, gpu_lib, x, **kw)
+    assert O.nerr(r["coherence"], np.abs(ps) / 10) <= TOL_COH
+    assert O.nerr(r["tsPWS"], o_ts) <= TOL_STACK and O.nerr(r["ls"], o_ls) <= TOL_STACK
+
+
+def test_large_single_stage_two_independent_kernel_paths_agree(pkg, gpu_lib):
+    """2048 x 16384, Morlet w0 = 6 (the C2 frame): the single-stage stack (chunk-accumulating kernels) must
+    equal the two-stage stack with one trace per group (per-trace kernels + combine) -- a size-independent
+    identity of the algorithm (Kmax == mtr) that cross-checks two different CUDA paths at scale; plus the
+    numpy oracle on the first 48 traces."""
+    mtr, n = 2048, 16384
+    x = _bench_traces(mtr, n)
+    a_ls, a_ts, a_coh = _plan_stack(pkg, gpu_lib, x, w0=6.0, w0set=4)
+    b_ls, b_ts, b_coh = _plan_stack(pkg, gpu_lib, x, w0=6.0, w0set=4, Kmax=mtr)
+    assert O.nerr(a_coh, b_coh) <= TOL_COH
+    assert O.nerr(a_ts, b_ts) <= TOL_STACK and O.nerr(a_ls, b_ls) <= TOL_STACK
+    s_ls, s_ts, s_coh = _plan_stack(pkg, gpu_lib, x[:48], w0=6.0, w0set=4)
+    o = O.tspws_main(O.Params(w0=6.0, w0set=4), x[:48])
+    assert O.nerr(s_coh, o["coherence"]) <= TOL_COH
+    assert O.nerr(s_ts, o["tsPWS"]) <= TOL_STACK and O.nerr(s_ls, o["ls"]) <= TOL_STACK

@@ -83,6 +83,10 @@ typedef struct {
     int                nitems;
     tspws_fwd_item_t  *d_items_gen; /* [nitems_gen] generic kernel: only scales with lg < 0 */
     int                nitems_gen;
+    tspws_fwd_item_t  *d_items_short; /* fp64 mean transform: warp items of the scales with L < 1024 */
+    int                nitems_short;
+    int               *d_long;    /* [nlong][2] (scale, coefficient) of the scales with L >= 1024   */
+    int                nlong;
     tspws_fwd2_item_t *d_items2;  /* [nitems2] polyphase kernel              */
     int                nitems2;
     int                fw_lg_begin[7]; /* items2 are sorted by lg: items of lg are [begin[lg], begin[lg+1]) */
@@ -135,8 +139,10 @@ int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t *d_items, i
                     double *d_part, const int *d_slot_off, unsigned int *d_tickets,
                     double *d_gsum, double *d_gtile, tspws_stream_t st);
 /* Mean removal + fold of the group sums (both linear) and the fp32 copy for the transform. */
-int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N, const double *d_gtile,
-                        int ntile, int do_rm, int do_fold, tspws_stream_t st);
+int tspws_cu_group_post(double *d_gsum, float *d_out32, double *d_gmean /*[N] or NULL*/, int G, int N,
+                        const double *d_gtile, int ntile, int do_rm, int do_fold, int split, tspws_stream_t st);
+/* fp64 transform (generic kernel) of ntr double traces -> [ntr][ncoef] double2 */
+int tspws_cu_forward_f64(const tspws_devframe_t *f, const double *d_x, int ntr, void *d_y, tspws_stream_t st);
 
 /* Forward frame transform + phasor / linear accumulation over chunks of traces (generic kernel,
  * any geometry, float or double).
@@ -155,8 +161,8 @@ int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int n
 /* ... and are combined here: for segment g (ntr = nseg*seg traces), PS = sum phasor(Y), ST = sum Y,
  * Zout = ST * weight(PS).  Outputs [nseg][ncoef] complex fp32. */
 int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_ypart, int nseg, int seg,
-                            const tspws_weight_t *d_rules, void *d_ps, void *d_st, void *d_zout,
-                            tspws_stream_t st);
+                            const tspws_weight_t *d_rules, const void *d_ymean /*double2 [nseg][ncoef] or NULL*/,
+                            void *d_ps, void *d_st, void *d_zout, tspws_stream_t st);
 /* Sum the chunk partials in segments of `seg` chunks -> PS, ST per segment, and the weighted
  * coefficients Zout = ST * weight(PS).  nseg segments; outputs [nseg][ncoef] complex. */
 int tspws_cu_reduce_weight(const void *d_part_ps, const void *d_part_st, int acc64, int ncoef,

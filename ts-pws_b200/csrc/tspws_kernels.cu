@@ -295,34 +295,62 @@ extern "C" int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t 
  *                  (src/ts_pws1f_lib.c:160-168); summed over a group that is the constant
  *                  sum_t mean_t = (1/N) sum_n G[n], taken here from the tile totals;
  *   fold         : 0.5 (G[n] + G[N-1-n]) (src/ts_pws1f_lib.c:76-86), linear as well;
- * and the fp32 copy the fp32 transform reads.  grid = (tiles over ceil(N/2), G). */
-__global__ void __launch_bounds__(256)
-group_post_kernel(double *__restrict__ gsum, float *__restrict__ gsum32, int N,
-                  const double *__restrict__ gtile, int ntile, int do_rm, int do_fold)
+ *   mean split   : the K group sums share a large coherent part (the stacked signal, K-fold
+ *                  amplified against the noise).  Their mean M[n] is split off in fp64 and only the
+ *                  residuals G_k - M go through the fp32 transform: Y_k = T64(M) + T32(G_k - M).
+ *                  The phase of a coefficient that is small in one group is then no longer limited
+ *                  by the fp32 rounding of the large common part (headline config: coherence error
+ *                  2e-5 -> 1e-6 against the reference's double).
+ * Emits the fp32 traces the fp32 transform reads.  grid = tiles over ceil(N/2). */
+__global__ void __launch_bounds__(64)
+group_post_kernel(double *__restrict__ gsum, float *__restrict__ out32, double *__restrict__ gmean, int N, int K,
+                  const double *__restrict__ gtile, int ntile, int do_rm, int do_fold, int split, int corr_in_smem)
 {
+    extern __shared__ double s_corr[];
+    if (do_rm && corr_in_smem) {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            double c = 0.0;
+            for (int i = 0; i < ntile; i++) c += gtile[k * ntile + i];     /* same order in every CTA */
+            s_corr[k] = c / (double)(unsigned int)N;
+        }
+        __syncthreads();
+    }
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = (N + 1) / 2;
-    double corr = 0.0;
-    if (do_rm) {
-        for (int i = 0; i < ntile; i++) corr += gtile[blockIdx.y * ntile + i];   /* same order in every thread */
-        corr /= (double)(unsigned int)N;
-    }
     if (n >= half) return;
-    double *g = gsum + (size_t)blockIdx.y * N;
-    float  *f = gsum32 + (size_t)blockIdx.y * N;
     const int r = N - 1 - n;
-    double a = g[n] - corr, b = g[r] - corr;
-    if (do_fold && r != n) { a = 0.5 * (a + b); b = a; }
-    g[n] = a; g[r] = b;
-    f[n] = (float)a;
-    f[r] = (float)b;
+    double sa = 0.0, sb = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        double corr = 0.0;
+        if (do_rm) {
+            if (corr_in_smem) corr = s_corr[k];
+            else { for (int i = 0; i < ntile; i++) corr += gtile[k * ntile + i]; corr /= (double)(unsigned int)N; }
+        }
+        double *g = gsum + (size_t)k * N;
+        double a = g[n] - corr, b = g[r] - corr;
+        if (do_fold && r != n) { a = 0.5 * (a + b); b = a; }
+        g[n] = a; g[r] = b;
+        sa += a; sb += b;
+    }
+    const double ma = split ? sa / (double)K : 0.0, mb = split ? sb / (double)K : 0.0;
+    if (gmean) { gmean[n] = ma; gmean[r] = mb; }
+#pragma unroll 4
+    for (int k = 0; k < K; k++) {
+        const double *g = gsum + (size_t)k * N;
+        float *f = out32 + (size_t)k * N;
+        f[n] = (float)(g[n] - ma);
+        f[r] = (float)(g[r] - mb);
+    }
 }
 
-extern "C" int tspws_cu_group_post(double *d_gsum, float *d_gsum32, int G, int N, const double *d_gtile,
-                                   int ntile, int do_rm, int do_fold, tspws_stream_t st)
+extern "C" int tspws_cu_group_post(double *d_gsum, float *d_out32, double *d_gmean, int G, int N, const double *d_gtile,
+                                   int ntile, int do_rm, int do_fold, int split, tspws_stream_t st)
 {
-    dim3 grid(((N + 1) / 2 + 255) / 256, G);
-    group_post_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(d_gsum, d_gsum32, N, d_gtile, ntile, do_rm, do_fold);
+    const int in_smem = (size_t)G * sizeof(double) <= 40 * 1024;
+    const size_t smem = (do_rm && in_smem) ? (size_t)G * sizeof(double) : 0;
+    group_post_kernel<<<((N + 1) / 2 + 63) / 64, 64, smem, (cudaStream_t)st>>>(d_gsum, d_out32, d_gmean, N, G, d_gtile, ntile,
+                                                                                  do_rm, do_fold, split, in_smem);
     TSPWS_LAUNCHED_N("group_post_kernel", (cudaStream_t)st);
     return 0;
 }
@@ -826,33 +854,37 @@ fwd2_pertrace_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__r
     }
 }
 
-/* generic kernel in per-trace mode, for the scales the polyphase kernel does not cover */
+/* generic kernel in per-trace mode: for the scales the polyphase kernel does not cover (fp32), and
+ * -- in double -- for the fp64 transform of the group mean.  out: [ntr][out_ld] complex at
+ * out_off(scale) + m, where out_off is ypart_off (fp32 partial-Y layout) or coef_off (plain). */
+template <typename T, bool PLAIN>
 __global__ void __launch_bounds__(FWD_WARPS * 32)
-fwd_pertrace_generic_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ wall,
+fwd_pertrace_generic_kernel(const tspws_scale_t *__restrict__ scales, const typename cplx<T>::type *__restrict__ wall,
                             const tspws_fwd_item_t *__restrict__ items, int nitems,
-                            const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len)
+                            const T *__restrict__ x, int N, typename cplx<T>::type *__restrict__ out, int out_ld)
 {
+    typedef typename cplx<T>::type T2;
     const int witem = blockIdx.x * FWD_WARPS + (threadIdx.x >> 5);
     if (witem >= nitems) return;
     const tspws_fwd_item_t it = items[witem];
     const tspws_scale_t sc = scales[it.s];
     const int lane = threadIdx.x & 31;
     const int G = sc.G, g = lane & (G - 1), og = lane / G, opp = 32 / G;
-    const float2 *__restrict__ w = wall + sc.tap_off;
-    const float *__restrict__ xk = x + (size_t)blockIdx.y * N;
+    const T2 *__restrict__ w = wall + sc.tap_off;
+    const T *__restrict__ xk = x + (size_t)blockIdx.y * N;
     for (int mb = 0; mb < it.nout; mb += opp) {
         const bool valid = (mb + og) < it.nout;
         const int  m     = it.m0 + (valid ? mb + og : it.nout - 1);
         long long pll = ((long long)m * sc.D - sc.c + g) % N;
         if (pll < 0) pll += N;
         int p = (int)pll;
-        float ar = 0.f, ai = 0.f;
+        T ar = 0, ai = 0;
 #pragma unroll 4
         for (int l = g; l < sc.L; l += G) {
-            const float2 wv = w[l];
-            const float  xv = xk[p];
-            ar = fmaf(xv, wv.x, ar);
-            ai = fmaf(-xv, wv.y, ai);
+            const T2 wv = w[l];
+            const T  xv = xk[p];
+            ar = fma(xv, wv.x, ar);
+            ai = fma(-xv, wv.y, ai);
             p += G;
             if (p >= N) p -= N;
         }
@@ -860,9 +892,90 @@ fwd_pertrace_generic_kernel(const tspws_scale_t *__restrict__ scales, const floa
             ar += __shfl_xor_sync(0xffffffffu, ar, o);
             ai += __shfl_xor_sync(0xffffffffu, ai, o);
         }
-        if (g == 0 && valid)
-            ypart[(size_t)blockIdx.y * ypart_len + sc.ypart_off + m] = make_float2(ar, ai);
+        if (g == 0 && valid) {
+            T2 v; v.x = ar; v.y = ai;
+            out[(size_t)blockIdx.y * out_ld + (PLAIN ? sc.coef_off : sc.ypart_off) + m] = v;
+        }
     }
+}
+
+/* fp64 transform of ntr double traces -> [ntr][ncoef] double2 in ONE launch of 256-thread CTAs:
+ *   CTAs [0, nshort_cta)  : 8 warp items each (short filters, lanes split the taps of a coefficient);
+ *   CTAs [nshort_cta, ..) : one coefficient each (long filters: 256 lanes split the taps -- a single
+ *                           warp would walk a 16384-tap filter in 128 dependent rounds of L2 latency). */
+__global__ void __launch_bounds__(256)
+fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restrict__ wall,
+               const tspws_fwd_item_t *__restrict__ items, int nitems, int nshort_cta,
+               const int2 *__restrict__ coefs, const double *__restrict__ x, int N,
+               double2 *__restrict__ out, int out_ld)
+{
+    __shared__ double sh[33];
+    const double *__restrict__ xk = x + (size_t)blockIdx.y * N;
+    if ((int)blockIdx.x < nshort_cta) {
+        const int witem = blockIdx.x * 8 + (threadIdx.x >> 5);
+        if (witem >= nitems) return;
+        const tspws_fwd_item_t it = items[witem];
+        const tspws_scale_t sc = scales[it.s];
+        const int lane = threadIdx.x & 31;
+        const int G = sc.G, g = lane & (G - 1), og = lane / G, opp = 32 / G;
+        const double2 *__restrict__ w = wall + sc.tap_off;
+        for (int mb = 0; mb < it.nout; mb += opp) {
+            const bool valid = (mb + og) < it.nout;
+            const int  m     = it.m0 + (valid ? mb + og : it.nout - 1);
+            long long pll = ((long long)m * sc.D - sc.c + g) % N;
+            if (pll < 0) pll += N;
+            int p = (int)pll;
+            double ar = 0.0, ai = 0.0;
+#pragma unroll 8
+            for (int l = g; l < sc.L; l += G) {
+                const double2 wv = __ldg(w + l);
+                const double  xv = __ldg(xk + p);
+                ar = fma(xv, wv.x, ar);
+                ai = fma(-xv, wv.y, ai);
+                p += G;
+                if (p >= N) p -= N;
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) {
+                ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+            }
+            if (g == 0 && valid) out[(size_t)blockIdx.y * out_ld + sc.coef_off + m] = make_double2(ar, ai);
+        }
+        return;
+    }
+    const int2 cm = coefs[blockIdx.x - nshort_cta];        /* (scale, coefficient) */
+    const tspws_scale_t sc = scales[cm.x];
+    const double2 *__restrict__ w = wall + sc.tap_off;
+    long long pll = ((long long)cm.y * sc.D - sc.c + threadIdx.x) % N;
+    if (pll < 0) pll += N;
+    int p = (int)pll;
+    const int step = 256 % N;
+    double ar = 0.0, ai = 0.0;
+#pragma unroll 8
+    for (int l = threadIdx.x; l < sc.L; l += 256) {
+        const double2 wv = __ldg(w + l);
+        const double  xv = __ldg(xk + p);
+        ar = fma(xv, wv.x, ar);
+        ai = fma(-xv, wv.y, ai);
+        p += step;
+        if (p >= N) p -= N;
+    }
+    ar = block_sum(ar, sh);
+    ai = block_sum(ai, sh);
+    if (threadIdx.x == 0) out[(size_t)blockIdx.y * out_ld + sc.coef_off + cm.y] = make_double2(ar, ai);
+}
+
+extern "C" int tspws_cu_forward_f64(const tspws_devframe_t *f, const double *d_x, int ntr, void *d_y, tspws_stream_t st)
+{
+    if (ntr <= 0) return 0;
+    if (!f->d_w64) return (int)cudaErrorInvalidValue;
+    const int nshort_cta = (f->nitems_short + 7) / 8;
+    if (nshort_cta + f->nlong <= 0) return 0;
+    dim3 grid(nshort_cta + f->nlong, ntr);
+    fwd_f64_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(f->d_scale, (const double2 *)f->d_w64, f->d_items_short, f->nitems_short,
+        nshort_cta, (const int2 *)f->d_long, d_x, f->N, (double2 *)d_y, f->ncoef);
+    TSPWS_LAUNCHED_N("fwd_f64_kernel", (cudaStream_t)st);
+    return 0;
 }
 
 extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, int chunk,
@@ -926,7 +1039,7 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
     }
     if (f->nitems_gen > 0) {
         dim3 grid((f->nitems_gen + FWD_WARPS - 1) / FWD_WARPS, ntr);
-        fwd_pertrace_generic_kernel<<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
+        fwd_pertrace_generic_kernel<float, false><<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
             f->nitems_gen, d_x, f->N, (float2 *)d_ypart, f->ypart_len);
         TSPWS_LAUNCHED_N("fwd_pertrace_generic_kernel", s);
     }
@@ -943,7 +1056,7 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
 __global__ void __launch_bounds__(256)
 phasor_combine_kernel(const int4 *__restrict__ tiles,
                       const float2 *__restrict__ ypart, int ypart_len,
-                      int ncoef, int seg, const tspws_weight_t *__restrict__ rules,
+                      int ncoef, int seg, const tspws_weight_t *__restrict__ rules, const double2 *__restrict__ ymean,
                       float2 *__restrict__ ps, float2 *__restrict__ st, float2 *__restrict__ zout)
 {
     __shared__ float  s_p[4][PC_TILE][2];
@@ -958,13 +1071,17 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
     double sr = 0.0, si = 0.0;
     if (ci < nvalid) {
         const float2 *yp0 = ypart + (size_t)sg * seg * ypart_len + tile.x + ci;
+        /* fp64 transform of the group mean (mean split, see group_post_kernel): Y_k = Ymean + dY_k */
+        double mr = 0.0, mi = 0.0;
+        if (ymean) { const double2 ym = ymean[(size_t)sg * ncoef + tile.y + ci]; mr = ym.x; mi = ym.y; }
         if (nsplit == 1) {
 #pragma unroll 4
             for (int k = slot; k < seg; k += 4) {
                 const float2 y = __ldcg(yp0 + (size_t)k * ypart_len);
+                const double yr = (double)y.x + mr, yi = (double)y.y + mi;
                 float a, b;
-                phasor_fast(y.x, y.y, a, b);
-                pr += a; pi += b; sr += (double)y.x; si += (double)y.y;
+                phasor_fast((float)yr, (float)yi, a, b);
+                pr += a; pi += b; sr += yr; si += yi;
             }
         } else {
             for (int k = slot; k < seg; k += 4) {
@@ -972,9 +1089,10 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
                 float re = 0.f, im = 0.f;
 #pragma unroll 8
                 for (int sp = 0; sp < nsplit; sp++) { const float2 y = __ldcg(yp + (size_t)sp * Ns); re += y.x; im += y.y; }
+                const double yr = (double)re + mr, yi = (double)im + mi;
                 float a, b;
-                phasor_fast(re, im, a, b);
-                pr += a; pi += b; sr += (double)re; si += (double)im;
+                phasor_fast((float)yr, (float)yi, a, b);
+                pr += a; pi += b; sr += yr; si += yi;
             }
         }
     }
@@ -1067,14 +1185,14 @@ extern "C" int tspws_cu_weight(const void *d_ps, const void *d_st, int acc64, in
 }
 
 extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_ypart, int nseg, int seg,
-                                       const tspws_weight_t *d_rules, void *d_ps, void *d_st, void *d_zout,
+                                       const tspws_weight_t *d_rules, const void *d_ymean, void *d_ps, void *d_st, void *d_zout,
                                        tspws_stream_t st)
 {
     if (nseg <= 0 || f->S <= 0) return 0;
     if (f->ntile16 <= 0) return 0;
     dim3 grid(f->ntile16, nseg);
     phasor_combine_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const int4 *)f->d_tile16, (const float2 *)d_ypart, f->ypart_len,
-        f->ncoef, seg, d_rules, (float2 *)d_ps, (float2 *)d_st, (float2 *)d_zout);
+        f->ncoef, seg, d_rules, (const double2 *)d_ymean, (float2 *)d_ps, (float2 *)d_st, (float2 *)d_zout);
     TSPWS_LAUNCHED_N("phasor_combine_kernel", (cudaStream_t)st);
     return 0;
 }

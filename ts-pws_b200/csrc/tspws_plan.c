@@ -53,10 +53,12 @@ struct tspws_plan {
     const void *g_x, *g_ls, *g_ts;
     unsigned long g_kernels;
     int    graph_broken;
-    int    overlap;
-    /* two-stage overlap: the transforms of finished groups run on a side stream under the colsum of later groups */
+    /* side stream: independent pieces of the tail run concurrently (fork / join, also inside the graph) */
     cudaStream_t side;
-    cudaEvent_t  ev_seg[16], ev_join;
+    cudaEvent_t  ev_fork, ev_join;
+    int          mean_split;        /* fp64 transform of the group mean + fp32 transforms of the residuals */
+    double      *d_gmean;           /* [N]      */
+    void        *d_ymean;           /* double2 [ncoef] */
     int         *h_slot_off;        /* [K+1] first work item of every group */
     void  *own_gsum, *own_exch;
 };
@@ -255,6 +257,35 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
     if (cudaMemcpy(d->d_w32, w32, f->ntaps * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_items, items, nitems * sizeof(*items), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_invgrp, grp, d->ninv * sizeof(*grp), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
+    if (want64) {   /* fp64 forward work lists: warp items for short filters, one CTA per coefficient for long ones */
+        const int LONG_T = (int)env_long("TSPWS_F64_LONG", 1024);
+        int ns = 0, nl = 0;
+        for (int s = 0; s < S; s++) {
+            if (sc[s].L >= LONG_T) { nl += sc[s].Ns; continue; }
+            const int opp = 32 / sc[s].G;
+            long run = 1024 / sc[s].L; run -= run % opp; if (run < opp) run = opp;
+            ns += (sc[s].Ns + (int)run - 1) / (int)run;
+        }
+        tspws_fwd_item_t *its = (tspws_fwd_item_t *)calloc(ns ? ns : 1, sizeof(*its));
+        int *lg = (int *)calloc((size_t)(nl ? nl : 1) * 2, sizeof(int));
+        if (!its || !lg) { free(its); free(lg); goto done; }
+        int ks = 0, kl = 0;
+        for (int s = 0; s < S; s++) {
+            if (sc[s].L >= LONG_T) { for (int m = 0; m < sc[s].Ns; m++) { lg[2 * kl] = s; lg[2 * kl + 1] = m; kl++; } continue; }
+            const int opp = 32 / sc[s].G;
+            long run = 1024 / sc[s].L; run -= run % opp; if (run < opp) run = opp;
+            for (int m0 = 0; m0 < sc[s].Ns; m0 += (int)run) {
+                its[ks].s = s; its[ks].m0 = m0; its[ks].nout = (sc[s].Ns - m0 < run) ? sc[s].Ns - m0 : (int)run; ks++;
+            }
+        }
+        int bad = cudaMalloc((void **)&d->d_items_short, (size_t)(ns ? ns : 1) * sizeof(*its)) != cudaSuccess ||
+                  cudaMemcpy(d->d_items_short, its, (size_t)ns * sizeof(*its), cudaMemcpyHostToDevice) != cudaSuccess ||
+                  cudaMalloc((void **)&d->d_long, (size_t)(nl ? nl : 1) * 2 * sizeof(int)) != cudaSuccess ||
+                  cudaMemcpy(d->d_long, lg, (size_t)nl * 2 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess;
+        free(its); free(lg);
+        if (bad) goto done;
+        d->nitems_short = ns; d->nlong = nl;
+    }
     {   /* origin-aligned, zero-padded filters of the 4-sample fp32 inverse */
         size_t nwi = 0;
         for (int s = 0; s < S; s++) {
@@ -367,7 +398,7 @@ void tspws_devframe_free(tspws_devframe_t *d)
 {
     cudaFree(d->d_scale); cudaFree(d->d_w32); cudaFree(d->d_w64);
     cudaFree(d->d_items); cudaFree(d->d_invgrp);
-    cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen); cudaFree(d->d_tile16); cudaFree(d->d_wi32); cudaFree(d->d_gi32); cudaFree(d->d_items_inv2); cudaFree(d->d_invgrp4);
+    cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen); cudaFree(d->d_tile16); cudaFree(d->d_wi32); cudaFree(d->d_gi32); cudaFree(d->d_items_inv2); cudaFree(d->d_invgrp4); cudaFree(d->d_items_short); cudaFree(d->d_long);
     memset(d, 0, sizeof(*d));
 }
 
@@ -435,7 +466,8 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     if (!pl) return;
     if (pl->exch_bound) { pl->d_gsum = (double *)pl->own_gsum; pl->d_exch = pl->own_exch; }
     if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
-    if (pl->side) { cudaStreamDestroy(pl->side); cudaEventDestroy(pl->ev_join); for (int i = 0; i < 16; i++) cudaEventDestroy(pl->ev_seg[i]); }
+    if (pl->side) { cudaStreamDestroy(pl->side); cudaEventDestroy(pl->ev_join); cudaEventDestroy(pl->ev_fork); }
+    cudaFree(pl->d_gmean); cudaFree(pl->d_ymean);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
@@ -464,7 +496,8 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     if (!pl->fr) { fprintf(stderr, "tspws_b200: cannot build the wavelet frame\n"); free(pl); return NULL; }
     for (unsigned int s = 0; s < pl->fr->S; s++)
         if (pl->fr->L[s] > (unsigned int)max) goto fail;          /* cannot happen: L is capped at N */
-    if (tspws_devframe_build(&pl->dev, pl->fr, pl->acc64, pl->two_stage && !pl->acc64)) goto fail;
+    pl->mean_split = pl->two_stage && !pl->acc64 && env_long("TSPWS_MEAN_SPLIT", 1);
+    if (tspws_devframe_build(&pl->dev, pl->fr, pl->acc64 || pl->mean_split, pl->two_stage && !pl->acc64)) goto fail;
 
     CK(cudaMalloc((void **)&pl->d_rule, sizeof(tspws_weight_t)));
     CK(cudaMemcpy(pl->d_rule, &pl->rule, sizeof(tspws_weight_t), cudaMemcpyHostToDevice));
@@ -490,16 +523,19 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
         CK(cudaMalloc(&pl->d_pst, (size_t)pl->nchunk * ncoef * pl->csz));
     }
     CK(cudaMalloc(&pl->d_exch, 2 * ncoef * pl->csz));
+    if (pl->mean_split) {
+        CK(cudaMalloc((void **)&pl->d_gmean, (size_t)max * sizeof(double)));
+        CK(cudaMalloc(&pl->d_ymean, ncoef * 2 * sizeof(double)));
+    }
     CK(cudaMalloc(&pl->d_zout, ncoef * (pl->acc64 ? 2 * sizeof(double) : 4 * sizeof(float))));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.inv_slots ? pl->dev.inv_slots : 1) * max * (pl->csz / 2)));
     CK(cudaMemset(pl->d_exch, 0, 2 * ncoef * pl->csz));
-    pl->overlap = pl->two_stage && pl->dev.per_trace && mtr_local == mtr_total && env_long("TSPWS_OVERLAP", 0);
     if (!pl->acc64 && env_long("TSPWS_SIDE_STREAM", 1)) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         CK(cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi));
         CK(cudaEventCreateWithFlags(&pl->ev_join, cudaEventDisableTiming));
-        for (int i = 0; i < 16; i++) CK(cudaEventCreateWithFlags(&pl->ev_seg[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
     }
     CK(cudaMalloc((void **)&pl->d_inv_tickets, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
     CK(cudaMemset(pl->d_inv_tickets, 0, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
@@ -576,11 +612,20 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     int e;
     tspws_cu_profile_mark(stream);
     if (pl->two_stage) {
-        if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, (int)pl->K, pl->N, pl->d_gtile, pl->ntile,
-                                     pl->p.lrm, pl->p.fold, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, pl->mean_split ? pl->d_gmean : NULL, (int)pl->K, pl->N,
+                                     pl->d_gtile, pl->ntile, pl->p.lrm, pl->p.fold, pl->mean_split, stream))) return TSPWS_ERR_CUDA;
         if (pl->dev.per_trace) {
+            /* fork: fp64 transform of the group mean on the side stream, fp32 transforms of the residuals here */
+            cudaStream_t A = (cudaStream_t)stream;
+            cudaStream_t B = (pl->side && !tspws_cu_profile_enabled() && pl->side != A) ? pl->side : A;
+            if (pl->mean_split) {
+                if (B != A && (cudaEventRecord(pl->ev_fork, A) != cudaSuccess || cudaStreamWaitEvent(B, pl->ev_fork, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
+                if ((e = tspws_cu_forward_f64(&pl->dev, pl->d_gmean, 1, pl->d_ymean, B))) return TSPWS_ERR_CUDA;
+            }
             if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
-            if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule,
+            if (pl->mean_split && B != A &&
+                (cudaEventRecord(pl->ev_join, B) != cudaSuccess || cudaStreamWaitEvent(A, pl->ev_join, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, pl->mean_split ? pl->d_ymean : NULL,
                                              plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
         } else {
             if ((e = tspws_cu_forward(&pl->dev, pl->d_gsum, 1, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
@@ -597,49 +642,8 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     return e ? TSPWS_ERR_CUDA : 0;
 }
 
-/* EXPERIMENT (off by default, TSPWS_OVERLAP=1): two-stage stack with the tail hidden under the stream:
- * the groups are cut into a few segments; as soon as the colsum of a segment has finished, its
- * group_post + forward transforms run on a high-priority side stream while the main stream keeps
- * streaming the next segment.  Measured on B200 (8192 x 16384, Kmax = 10): 1 segment 162 us, 2: 195 us,
- * 4: 199 us, 10: 244 us -- cutting the HBM stream into several launches costs more than the overlap
- * hides (each segment under-fills the SMs and the co-running transforms steal issue slots). */
-static int plan_stack_overlap(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
-{
-    cudaStream_t A = (cudaStream_t)stream, B = pl->side;
-    const int K = (int)pl->K;
-    int nseg = (int)env_long("TSPWS_OVERLAP_SEGS", 4);
-    if (nseg > K) nseg = K;
-    if (nseg > 16) nseg = 16;
-    if (nseg < 1) nseg = 1;
-    const size_t N = (size_t)pl->N;
-    pl->summed_across_ranks = 0;
-    for (int sgm = 0; sgm < nseg; sgm++) {
-        /* later segments are shorter: what they leave exposed after the stream ends is smaller */
-        const int g0 = (int)((long)K * sgm * (2 * nseg - sgm + 1) / ((long)nseg * (nseg + 1)));
-        const int g1 = (int)((long)K * (sgm + 1) * (2 * nseg - sgm) / ((long)nseg * (nseg + 1)));
-        if (g1 <= g0) continue;
-        const int i0 = pl->h_slot_off[g0], i1 = pl->h_slot_off[g1];
-        if (tspws_cu_colsum(d_sigall, pl->N, pl->d_cs + i0, i1 - i0, pl->d_part, pl->d_slot_off, pl->d_tickets,
-                            pl->d_gsum, pl->d_gtile, A)) return TSPWS_ERR_CUDA;
-        if (cudaEventRecord(pl->ev_seg[sgm], A) != cudaSuccess) return TSPWS_ERR_CUDA;
-        if (cudaStreamWaitEvent(B, pl->ev_seg[sgm], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
-        if (tspws_cu_group_post(pl->d_gsum + g0 * N, pl->d_gsum32 + g0 * N, g1 - g0, pl->N, pl->d_gtile + (size_t)g0 * pl->ntile,
-                                pl->ntile, pl->p.lrm, pl->p.fold, B)) return TSPWS_ERR_CUDA;
-        if (tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32 + g0 * N, g1 - g0,
-                                      (float *)pl->d_ypart + 2 * (size_t)g0 * pl->dev.ypart_len, B)) return TSPWS_ERR_CUDA;
-    }
-    if (cudaEventRecord(pl->ev_join, B) != cudaSuccess) return TSPWS_ERR_CUDA;
-    if (cudaStreamWaitEvent(A, pl->ev_join, 0) != cudaSuccess) return TSPWS_ERR_CUDA;
-    if (tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, plan_ps(pl), plan_st(pl), pl->d_zout, A)) return TSPWS_ERR_CUDA;
-    if (tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), 0, 1, pl->d_rule, pl->d_invscratch, pl->d_inv_tickets,
-                         d_tspws, d_ls, A)) return TSPWS_ERR_CUDA;
-    return 0;
-}
-
 static int plan_stack_direct(tspws_plan_t *pl, float *d_sigall, float *d_ls, float *d_tspws, void *stream)
 {
-    if (pl->overlap && pl->side && !tspws_cu_profile_enabled() && !pl->exch_bound)
-        return plan_stack_overlap(pl, d_sigall, d_ls, d_tspws, stream);
     int e = tspws_b200_plan_reduce(pl, d_sigall, stream);
     if (e) return e;
     return tspws_b200_plan_finish(pl, d_ls, d_tspws, stream);
