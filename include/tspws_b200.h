@@ -112,6 +112,14 @@ typedef struct {
  * TSPWS_ERR_CUDA (77) when the GPU path is unusable. Host buffers in, host buffers out. */
 int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in);
 
+/* Additive (BASELINE configs[4]): npairs independent stacks (station pairs) with one
+ * parameter block; same results as tspws_main(tspws, &outs[i], &ins[i]) called in turn -- what the
+ * reference's users do with a shell loop over ts_pws (examples/example.sh).  Pairs that share one
+ * geometry (max, mtr, dt, beg) and ask for the main stack only are pipelined over two device slots
+ * so that the host-to-device copy of pair i+1 runs under the kernels of pair i.  *tspws is mutated
+ * as by the first call; returns the first non-zero code. */
+int tspws_b200_main_batch(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsigned int npairs);
+
 /* ------------------------------------------------------------------------- */
 /* PART 2 -- additive exports                                                 */
 /* ------------------------------------------------------------------------- */

@@ -115,6 +115,8 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_main.argtypes = [C.POINTER(TsPWS), C.POINTER(TsPWSOut), C.POINTER(Data)]
     if not full:
         return lib
+    lib.tspws_b200_main_batch.restype = C.c_int
+    lib.tspws_b200_main_batch.argtypes = [C.POINTER(TsPWS), C.POINTER(TsPWSOut), C.POINTER(Data), C.c_uint]
     lib.tspws_b200_derive_params.restype = C.c_int
     lib.tspws_b200_derive_params.argtypes = [C.POINTER(TsPWS), C.c_uint, C.c_float]
     lib.tspws_b200_frame_create.restype = C.POINTER(Frame)
@@ -185,7 +187,7 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
 
 
 EXPORTS = [
-    "tspws_main", "tspws_b200_derive_params", "tspws_b200_frame_create", "tspws_b200_frame_destroy",
+    "tspws_main", "tspws_b200_main_batch", "tspws_b200_derive_params", "tspws_b200_frame_create", "tspws_b200_frame_destroy",
     "tspws_b200_subsampling_plan", "tspws_b200_jackknife_plans", "tspws_b200_get_coherence",
     "tspws_b200_get_stacks", "tspws_b200_set_selection", "tspws_b200_set_option",
     "tspws_b200_get_option", "tspws_b200_device_count", "tspws_b200_shutdown", "tspws_b200_version",
@@ -296,6 +298,27 @@ def call_tspws_main(lib: C.CDLL, sigall: np.ndarray, params: TsPWS, dt: float = 
     rc = lib.tspws_main(C.byref(p), C.byref(out), C.byref(dat))
     res.update(rc=rc, ls=ls, tsPWS=ts, params=p, sigall=x, M=M)
     return res
+
+
+def call_main_batch(lib: C.CDLL, pairs, params: TsPWS, dt: float = 1.0, out_ls=None, out_ts=None) -> dict:
+    """``tspws_b200_main_batch`` on a sequence of [mtr_i, max_i] float32 arrays (one per station pair).
+    The arrays are used in place when already float32 C-contiguous (pinned torch tensors' numpy views
+    work).  Returns {'rc', 'ls': [..], 'tsPWS': [..], 'params'}."""
+    n = len(pairs)
+    p = TsPWS.from_buffer_copy(params)
+    outs, ins = (TsPWSOut * n)(), (Data * n)()
+    xs, ls, ts = [], [], []
+    for i, a in enumerate(pairs):
+        x = np.ascontiguousarray(a, dtype=np.float32)
+        mtr, nmax = x.shape
+        l = np.zeros(nmax, np.float32) if out_ls is None else out_ls[i]
+        t = np.zeros(nmax, np.float32) if out_ts is None else out_ts[i]
+        ins[i].sigall = _fptr(x)
+        ins[i].hdr.max, ins[i].hdr.mtr, ins[i].hdr.dt, ins[i].hdr.beg = nmax, mtr, dt, -(nmax - 1) * dt / 2.0
+        outs[i].ls, outs[i].tsPWS, outs[i].N, outs[i].mtr = _fptr(l), _fptr(t), nmax, mtr
+        xs.append(x); ls.append(l); ts.append(t)
+    rc = lib.tspws_b200_main_batch(C.byref(p), outs, ins, n)
+    return {"rc": rc, "ls": ls, "tsPWS": ts, "params": p, "_keep": xs}
 
 
 def read_profile(lib) -> dict:

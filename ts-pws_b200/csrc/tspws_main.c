@@ -42,6 +42,18 @@ static struct {
     char         *sel;   unsigned int selM, selmtr;
 } G;
 
+/* double-buffered slots of tspws_b200_main_batch(): each owns a stream, device buffers and a plan */
+#define TSPWS_NSLOT 2
+static struct batch_slot {
+    cudaStream_t  st;
+    tspws_plan_t *plan;
+    t_tsPWS       key;
+    int           max;
+    unsigned int  mtr;
+    float        *d_x;   size_t d_x_cap;
+    float        *d_out; size_t d_out_cap;
+} S[TSPWS_NSLOT];
+
 /* per-kernel timing (CUDA events on the launching stream); see tspws_kernels.cu */
 int tspws_b200_profile(int enable) { return tspws_cu_profile_enable(enable); }
 int tspws_b200_profile_reset(void) { return tspws_cu_profile_reset(); }
@@ -110,6 +122,13 @@ void tspws_b200_shutdown(void)
     if (G.d_out) { cudaFree(G.d_out); G.d_out = NULL; G.d_out_cap = 0; }
     if (G.stream) { cudaStreamDestroy(G.stream); G.stream = NULL; }
     free(G.sel); G.sel = NULL; G.selM = G.selmtr = 0;
+    for (int i = 0; i < TSPWS_NSLOT; i++) {
+        if (S[i].plan)  tspws_b200_plan_destroy(S[i].plan);
+        if (S[i].d_x)   cudaFree(S[i].d_x);
+        if (S[i].d_out) cudaFree(S[i].d_out);
+        if (S[i].st)    cudaStreamDestroy(S[i].st);
+        memset(&S[i], 0, sizeof S[i]);
+    }
     G.cuda_state = 0;
 }
 
@@ -246,6 +265,99 @@ cuda_fail:
     {
         cudaError_t e = cudaGetLastError();
         fprintf(stderr, "tspws_b200: CUDA failure in tspws_main (%s)\n", cudaGetErrorString(e));
+    }
+    return TSPWS_ERR_CUDA;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Batch of independent stacks (station pairs; SURVEY 8b "tspws_main_batch() for C5").
+ * Same results as calling tspws_main(tspws, &outs[i], &ins[i]) for i = 0..npairs-1 in turn.
+ * When the pairs share one geometry and ask for the main stack only, the calls are pipelined over
+ * two slots (stream + device buffers + plan each): the H2D copy of pair i+1 runs under the kernels
+ * of pair i, and the host never waits between pairs.  Anything else runs pair by pair.
+ * ------------------------------------------------------------------------------------ */
+int tspws_b200_main_batch(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsigned int npairs)
+{
+    if (tspws == NULL || outs == NULL || ins == NULL) { printf("tspws_main: NULL input\n"); return -1; }
+    if (!npairs) return 0;
+
+    const int resampling = (tspws->subsmpl_N > 0 && tspws->subsmpl_p > 0) || (tspws->jackknife_n > 0 && tspws->jackknife_d > 0);
+    int uniform = !resampling && !tspws->convergence && !G.opt_writeback && !G.opt_fp64_tail && ins[0].hdr.max > 0;
+    for (unsigned int i = 0; i < npairs && uniform; i++) {
+        const t_hdr *h = &ins[i].hdr;
+        if (h->max != ins[0].hdr.max || h->mtr != ins[0].hdr.mtr || h->dt != ins[0].hdr.dt || h->beg != ins[0].hdr.beg ||
+            !ins[i].sigall || !outs[i].ls || !outs[i].tsPWS) uniform = 0;
+    }
+    if (!uniform || npairs == 1) {
+        /* every call derives from the caller's parameter block as it was on entry, like a loop of CLI runs */
+        const t_tsPWS p0 = *tspws;
+        int first = 0;
+        for (unsigned int i = 0; i < npairs; i++) {
+            t_tsPWS p = p0;
+            int e = tspws_main(&p, &outs[i], &ins[i]);
+            if (i == 0) *tspws = p;
+            if (e && !first) first = e;
+        }
+        return first;
+    }
+
+    /* ---- parameters once (identical for every pair) ---- */
+    const t_hdr *hdr = &ins[0].hdr;
+    const int max = hdr->max;
+    unsigned int mtr = tspws->Nmax ? tspws->Nmax : hdr->mtr;
+    if (mtr > hdr->mtr) mtr = hdr->mtr;
+    if (tspws->fold && !tspws_fold_allowed(hdr->beg, hdr->dt, max)) {
+        printf("Warning: Folding ignored. B = %f, E = %f, nsamp = %u\n", hdr->beg, hdr->beg + (max - 1) * hdr->dt, (unsigned int)max);
+        tspws->fold = 0;
+    }
+    tspws_b200_derive_params(tspws, (unsigned int)max, hdr->dt);
+    if (tspws->verbose) tspws_print_params(tspws, (unsigned int)max, hdr->dt);
+    if (!mtr) return 0;
+    if (tspws->type > -1 || tspws->type < -3 || !tspws->V) {
+        printf("Error: CreateWaveletFamily: Complex wavelet not defined.\n");
+        return TSPWS_ERR_ARG;
+    }
+    int nerr = ensure_cuda();
+    if (nerr) return nerr;
+
+    const size_t nelem = (size_t)mtr * (size_t)max;
+    const int two_stage  = tspws->Kmax && tspws->Kmax <= mtr;
+    const int exact_prep = two_stage && (tspws->fold || tspws->lrm);
+    t_tsPWS pp = *tspws;
+    if (exact_prep) { pp.fold = 0; pp.lrm = 0; }
+
+    const int nslot = npairs < TSPWS_NSLOT ? (int)npairs : TSPWS_NSLOT;
+    for (int k = 0; k < nslot; k++) {
+        struct batch_slot *sl = &S[k];
+        if (!sl->st && cudaStreamCreateWithFlags(&sl->st, cudaStreamNonBlocking) != cudaSuccess) goto cuda_fail;
+        if (grow(&sl->d_x, &sl->d_x_cap, nelem) || grow(&sl->d_out, &sl->d_out_cap, 2 * (size_t)max)) {
+            fprintf(stderr, "tspws_b200: out of device memory\n");
+            return TSPWS_ERR_ALLOC;
+        }
+        if (!sl->plan || !same_plan_key(&sl->key, &pp) || sl->max != max || sl->mtr != mtr) {
+            if (sl->plan) { tspws_b200_plan_destroy(sl->plan); sl->plan = NULL; }
+            sl->plan = tspws_b200_plan_create(&pp, max, mtr, mtr, 0);
+            if (!sl->plan) { fprintf(stderr, "tspws_b200: cannot create the stacking plan\n"); return TSPWS_ERR_ALLOC; }
+            sl->key = pp; sl->max = max; sl->mtr = mtr;
+        }
+    }
+    for (unsigned int i = 0; i < npairs; i++) {
+        struct batch_slot *sl = &S[i % TSPWS_NSLOT];
+        /* stream order makes the slot's buffers safe to reuse: pair i-2 has been queued before */
+        if (cudaMemcpyAsync(sl->d_x, ins[i].sigall, nelem * sizeof(float), cudaMemcpyHostToDevice, sl->st) != cudaSuccess) goto cuda_fail;
+        if (exact_prep && tspws_cu_prep(sl->d_x, (int)mtr, max, tspws->fold, tspws->lrm, sl->st)) goto cuda_fail;
+        if ((nerr = tspws_b200_plan_stack(sl->plan, sl->d_x, sl->d_out, sl->d_out + max, sl->st))) goto cuda_fail;
+        if (cudaMemcpyAsync(outs[i].ls, sl->d_out, (size_t)max * sizeof(float), cudaMemcpyDeviceToHost, sl->st) != cudaSuccess) goto cuda_fail;
+        if (cudaMemcpyAsync(outs[i].tsPWS, sl->d_out + max, (size_t)max * sizeof(float), cudaMemcpyDeviceToHost, sl->st) != cudaSuccess) goto cuda_fail;
+    }
+    for (int k = 0; k < nslot; k++)
+        if (cudaStreamSynchronize(S[k].st) != cudaSuccess) goto cuda_fail;
+    return 0;
+
+cuda_fail:
+    {
+        cudaError_t e = cudaGetLastError();
+        fprintf(stderr, "tspws_b200: CUDA failure in tspws_b200_main_batch (%s)\n", cudaGetErrorString(e));
     }
     return TSPWS_ERR_CUDA;
 }
