@@ -139,6 +139,11 @@ int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t *d_items, i
                     double *d_part, const int *d_slot_off, unsigned int *d_tickets,
                     double *d_gsum, double *d_gtile, tspws_stream_t st);
 /* Mean removal + fold of the group sums (both linear) and the fp32 copy for the transform. */
+int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts /*int4[nparts]*/, int nparts, const int *d_grp_t0,
+                     double *d_slots, double *d_slot_tot, int ntile, tspws_stream_t st);
+int tspws_cu_group_post2(const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
+                         int ntile, int mode, int do_rm, int do_fold, int split, double *d_gsum, double *d_gtile,
+                         float *d_out32, double *d_gmean, tspws_stream_t st);
 int tspws_cu_group_post(double *d_gsum, float *d_out32, double *d_gmean /*[N] or NULL*/, int G, int N,
                         const double *d_gtile, int ntile, int do_rm, int do_fold, int split, tspws_stream_t st);
 /* fp64 transform (generic kernel) of ntr double traces -> [ntr][ncoef] double2 */

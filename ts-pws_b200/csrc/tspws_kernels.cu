@@ -355,6 +355,148 @@ extern "C" int tspws_cu_group_post(double *d_gsum, float *d_out32, double *d_gme
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------- */
+/* Single-wave group sums (N % 4 == 0): grid = column tiles x row parts, sized on the host to  */
+/* 148 SMs x 4 resident CTAs, every CTA streaming the same number of rows (+-1).  A part may   */
+/* cross group boundaries: the running sums are flushed to the next slot at each boundary, so  */
+/* slots are numbered in row order and those of one group are consecutive.  No tickets, fences */
+/* or second pass here -- group_post2_kernel adds a group's slots in slot order (deterministic) */
+/* while it applies mean removal / fold / the mean split.  tools/readbw.cu: this access pattern */
+/* streams at 6.3 TB/s (97 % of the measured copy peak); the ticketed kernel above at 5.6 TB/s. */
+/* part record: (first row, end row, group of the first row, slot of the first flush)          */
+/* ------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(CS_THREADS, 4)
+colsum2_kernel(const float *__restrict__ x, int N, const int4 *__restrict__ parts, const int *__restrict__ grp_t0,
+               double *__restrict__ slots, double *__restrict__ slot_tot, int ntile)
+{
+    __shared__ double sh[33];
+    const int4 pi = parts[blockIdx.y];
+    const int  col = blockIdx.x * CS_TILE + threadIdx.x * 4;
+    const bool active = col < N;
+    const float *p = x + (size_t)pi.x * N + (active ? col : 0);
+    int r = pi.x, g = pi.z, slot = pi.w;
+    while (r < pi.y) {
+        const int rend = min(pi.y, grp_t0[g + 1]);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (; r + CS_UNROLL <= rend; r += CS_UNROLL) {
+            float4 v[CS_UNROLL];
+#pragma unroll
+            for (int j = 0; j < CS_UNROLL; j++) v[j] = ld_stream4(p + (size_t)j * N);
+#pragma unroll
+            for (int j = 0; j < CS_UNROLL; j++) {
+                a0 += (double)v[j].x; a1 += (double)v[j].y; a2 += (double)v[j].z; a3 += (double)v[j].w;
+            }
+            p += (size_t)CS_UNROLL * N;
+        }
+        for (; r < rend; r++) {
+            const float4 v = ld_stream4(p);
+            a0 += (double)v.x; a1 += (double)v.y; a2 += (double)v.z; a3 += (double)v.w;
+            p += N;
+        }
+        if (active) {
+            double2 *o = reinterpret_cast<double2 *>(slots + (size_t)slot * N + col);
+            o[0] = make_double2(a0, a1); o[1] = make_double2(a2, a3);
+        } else {
+            a0 = a1 = a2 = a3 = 0.0;
+        }
+        const double tot = block_sum((a0 + a1) + (a2 + a3), sh);
+        if (threadIdx.x == 0) slot_tot[(size_t)slot * ntile + blockIdx.x] = tot;
+        g++; slot++;
+    }
+}
+
+extern "C" int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts, int nparts, const int *d_grp_t0,
+                                double *d_slots, double *d_slot_tot, int ntile, tspws_stream_t st)
+{
+    if (nparts <= 0) return 0;
+    if ((N & 3) || ((uintptr_t)d_x & 15)) return (int)cudaErrorInvalidValue;
+    dim3 grid(ntile, nparts);
+    colsum2_kernel<<<grid, CS_THREADS, 0, (cudaStream_t)st>>>(d_x, N, (const int4 *)d_parts, d_grp_t0, d_slots, d_slot_tot, ntile);
+    TSPWS_LAUNCHED_N("colsum2_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* Slot sums -> group sums, with the linear post-processing of group_post_kernel fused in.
+ * Block = 32 consecutive samples x 8 group lanes (warp w handles groups w, w+8, ...): every global
+ * access is a coalesced 256 B row, and all groups of a sample are in flight together.
+ *   mode 0  combine only: gsum = sum of slots, gtile = sum of slot totals (the exchange block of a
+ *           sharded plan; mean removal etc. follow the all-reduce, in group_post_kernel)
+ *   mode 1  full: mean removal (from the slot totals), fold, mean split, fp32 copy / residuals    */
+#define GP2_LANES 8
+__global__ void __launch_bounds__(32 * GP2_LANES)
+group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ slot_tot, const int *__restrict__ slot_off,
+                   int N, int K, int ntile, int mode, int do_rm, int do_fold, int split,
+                   double *__restrict__ gsum, double *__restrict__ gtile, float *__restrict__ out32, double *__restrict__ gmean)
+{
+    extern __shared__ double s_c[];                      /* [K] group-mean corrections */
+    __shared__ double s_m[GP2_LANES][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (mode == 0 ? blockIdx.x == 0 : do_rm) {
+        /* totals of every group: lanes stride over (slot, tile) in a fixed pattern, fixed shuffle tree */
+        for (int k = w; k < K; k += GP2_LANES) {
+            const int s0 = slot_off[k], s1 = slot_off[k + 1];
+            if (mode == 0) {
+                for (int t = lane; t < ntile; t += 32) {
+                    double c = 0.0;
+                    for (int sl = s0; sl < s1; sl++) c += slot_tot[(size_t)sl * ntile + t];
+                    gtile[(size_t)k * ntile + t] = c;
+                }
+            } else {
+                double c = 0.0;
+                for (int i = s0 * ntile + lane; i < s1 * ntile; i += 32) c += slot_tot[i];
+                c = warp_sum(c);
+                if (lane == 0) s_c[k] = c / (double)(unsigned int)N;
+            }
+        }
+    }
+    if (mode == 1 && do_rm) __syncthreads();
+    const int n = blockIdx.x * 32 + lane;
+    const bool ok = n < N;
+    const int r = N - 1 - n;
+    double acc = 0.0;
+    for (int k = w; k < K; k += GP2_LANES) {
+        const int s0 = slot_off[k], s1 = slot_off[k + 1];
+        double v = 0.0, vr = 0.0;
+        if (ok) {
+#pragma unroll 4
+            for (int sl = s0; sl < s1; sl++) v += __ldcg(slots + (size_t)sl * N + n);
+            if (mode == 1 && do_fold) {
+#pragma unroll 4
+                for (int sl = s0; sl < s1; sl++) vr += __ldcg(slots + (size_t)sl * N + r);
+                v = 0.5 * (v + vr);                        /* the constant correction is fold-invariant */
+            }
+            if (mode == 1 && do_rm) v -= s_c[k];
+            gsum[(size_t)k * N + n] = v;
+        }
+        acc += v;
+    }
+    if (mode == 0) return;
+    double m = 0.0;
+    if (split) {
+        s_m[w][lane] = acc;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < GP2_LANES; i++) m += s_m[i][lane];
+        m /= (double)K;
+        if (w == 0 && ok && gmean) gmean[n] = m;
+    }
+    if (!ok) return;
+    for (int k = w; k < K; k += GP2_LANES)
+        out32[(size_t)k * N + n] = (float)(gsum[(size_t)k * N + n] - m);
+}
+
+extern "C" int tspws_cu_group_post2(const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
+                                    int ntile, int mode, int do_rm, int do_fold, int split, double *d_gsum, double *d_gtile,
+                                    float *d_out32, double *d_gmean, tspws_stream_t st)
+{
+    const size_t smem = (size_t)K * sizeof(double);
+    if (smem > 40 * 1024) return (int)cudaErrorInvalidValue;
+    group_post2_kernel<<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
+                                                                                  mode, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean);
+    TSPWS_LAUNCHED_N("group_post2_kernel", (cudaStream_t)st);
+    return 0;
+}
+
 /* ===================================================================================== */
 /* forward frame transform fused with the phasor / linear accumulation                   */
 /*   Y_s[m] = sum_l x[(m D_s - c_s + l) mod N] conj(w_s[l])                              */
@@ -1754,7 +1896,7 @@ inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
     float2 gq[8];
 #pragma unroll
     for (int j = 0; j < IV_WS; j++) {
-        const float4 z = __ldg(Z + zi);
+        const float4 z = __ldcg(Z + zi);
         wre[j] = make_float2(z.x, z.z); wim[j] = make_float2(z.y, z.w);
         if (++zi >= Ns) zi = 0;
     }
@@ -1772,7 +1914,7 @@ inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
                     accr[r] = __ffma2_rn(wim[(tt + r) % IV_WS], gy, accr[r]);
                 }
                 if (t0 + tt + IV_WS - IV_R + 1 < Qi) {
-                    const float4 z = __ldg(Z + zi);
+                    const float4 z = __ldcg(Z + zi);
                     wre[tt] = make_float2(z.x, z.z); wim[tt] = make_float2(z.y, z.w);
                     if (++zi >= Ns) zi = 0;
                 }
@@ -1817,10 +1959,10 @@ inv_finish_kernel(const float *__restrict__ scratch, int nslots, int nseg, int N
 #pragma unroll 4
             for (int g = quarter; g < nslots; g += 4) {
                 const size_t o = ((size_t)g * nseg + sg) * N + n0;
-                const float4 p = __ldg(reinterpret_cast<const float4 *>(scratch + o));
+                const float4 p = __ldcg(reinterpret_cast<const float4 *>(scratch + o));
                 a[0] += (double)p.x; a[1] += (double)p.y; a[2] += (double)p.z; a[3] += (double)p.w;
                 if (WITH_ST) {
-                    const float4 q = __ldg(reinterpret_cast<const float4 *>(scratch + (size_t)nslots * nseg * N + o));
+                    const float4 q = __ldcg(reinterpret_cast<const float4 *>(scratch + (size_t)nslots * nseg * N + o));
                     b[0] += (double)q.x; b[1] += (double)q.y; b[2] += (double)q.z; b[3] += (double)q.w;
                 }
             }

@@ -40,6 +40,11 @@ struct tspws_plan {
     int    ncs, ntile;
     tspws_csum_item_t *d_cs;
     int    *d_slot_off, *d_grp_t0;
+    /* single-wave group sums (colsum2_kernel): row parts, their slots, slot totals */
+    int     cs2, cs2_nparts, cs2_nslots, cs2_pending;
+    void   *d_cs2_parts;
+    int    *d_cs2_slot_off;
+    double *d_cs2_slots, *d_cs2_tot;
     double *d_part, *d_gsum, *d_gtile;      /* gsum [K][N] and gtile [K][ntile] are one block */
     float  *d_gsum32;
     unsigned int *d_tickets, *d_inv_tickets;
@@ -455,6 +460,43 @@ static int twostage_build(tspws_plan_t *pl)
     if (cudaMemcpy(pl->d_slot_off, slot_off, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_grp_t0, grp_t0, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     pl->h_slot_off = slot_off; slot_off = NULL;
+
+    /* ---- single-wave variant: ntiles x nparts CTAs = 148 SMs x 4 resident CTAs, equal rows per part ---- */
+    pl->cs2 = 0;
+    if (pl->N % 4 == 0 && n > 0 && !env_long("TSPWS_NO_CS2", 0)) {
+        int nparts = (int)(env_long("TSPWS_CS2_CTAS", 148 * 4) / ntiles);
+        if (nparts > (int)((n + 3) / 4)) nparts = (int)((n + 3) / 4);
+        if (nparts < 1) nparts = 1;
+        int *pr = (int *)calloc((size_t)nparts * 4, sizeof(int));
+        int *so = (int *)calloc(K + 1, sizeof(int));
+        int ok = pr && so, nslots = 0, g = 0;
+        for (unsigned int k = 0; k <= K && ok; k++) so[k] = -1;
+        for (int q = 0; q < nparts && ok; q++) {
+            const int r0 = (int)((unsigned long long)n * q / nparts), r1 = (int)((unsigned long long)n * (q + 1) / nparts);
+            while (g < (int)K && grp_t0[g + 1] <= r0) g++;             /* group of row r0 */
+            pr[4 * q] = r0; pr[4 * q + 1] = r1; pr[4 * q + 2] = g; pr[4 * q + 3] = nslots;
+            /* the kernel's walk: one flush (= one slot) per group the part touches */
+            for (int gg = g, r = r0; r < r1; gg++) {
+                if (so[gg] < 0) so[gg] = nslots;
+                nslots++;
+                r = grp_t0[gg + 1] < r1 ? grp_t0[gg + 1] : r1;
+            }
+        }
+        if (ok) {
+            /* groups without local rows: empty slot range */
+            int next = nslots;
+            for (int k = (int)K; k >= 0; k--) { if (k == (int)K || so[k] < 0) so[k] = next; else next = so[k]; }
+            ok = cudaMalloc(&pl->d_cs2_parts, (size_t)nparts * 4 * sizeof(int)) == cudaSuccess &&
+                 cudaMalloc((void **)&pl->d_cs2_slot_off, (K + 1) * sizeof(int)) == cudaSuccess &&
+                 cudaMalloc((void **)&pl->d_cs2_slots, (size_t)(nslots ? nslots : 1) * N * sizeof(double)) == cudaSuccess &&
+                 cudaMalloc((void **)&pl->d_cs2_tot, (size_t)(nslots ? nslots : 1) * ntiles * sizeof(double)) == cudaSuccess &&
+                 cudaMemcpy(pl->d_cs2_parts, pr, (size_t)nparts * 4 * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+                 cudaMemcpy(pl->d_cs2_slot_off, so, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess;
+            if (ok) { pl->cs2 = 1; pl->cs2_nparts = nparts; pl->cs2_nslots = nslots; }
+            else cudaGetLastError();
+        }
+        free(pr); free(so);
+    }
     rc = 0;
 done:
     free(grp_t0); free(slot_off); free(it);
@@ -470,6 +512,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     cudaFree(pl->d_gmean); cudaFree(pl->d_ymean);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
+    cudaFree(pl->d_cs2_parts); cudaFree(pl->d_cs2_slot_off); cudaFree(pl->d_cs2_slots); cudaFree(pl->d_cs2_tot);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
     cudaFree(pl->d_part); cudaFree(pl->d_tickets); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
     cudaFree(pl->d_pps); cudaFree(pl->d_pst); cudaFree(pl->d_exch);
@@ -554,6 +597,19 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     int e;
     pl->summed_across_ranks = 0;
     tspws_cu_profile_mark(stream);
+    pl->cs2_pending = 0;
+    if (pl->two_stage && pl->cs2 && !((size_t)d_sigall & 15)) {
+        if ((e = tspws_cu_colsum2(d_sigall, pl->N, pl->d_cs2_parts, pl->cs2_nparts, pl->d_grp_t0, pl->d_cs2_slots,
+                                  pl->d_cs2_tot, pl->ntile, stream))) return TSPWS_ERR_CUDA;
+        if (pl->mtr_local != pl->mtr_total || pl->exch_bound) {
+            /* sharded: the exchange block (group sums + tile totals) has to be complete before the all-reduce */
+            if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
+                                          0, 0, 0, 0, pl->d_gsum, pl->d_gtile, NULL, NULL, stream))) return TSPWS_ERR_CUDA;
+        } else {
+            pl->cs2_pending = 1;                   /* the slots are added up inside group_post2 (plan_finish) */
+        }
+        return 0;
+    }
     if (pl->two_stage) {
         if (pl->mtr_local != pl->mtr_total)   /* groups without local traces must contribute zeros */
             if (cudaMemsetAsync(pl->d_gsum, 0, tspws_b200_plan_exchange_bytes(pl), (cudaStream_t)stream) != cudaSuccess) return TSPWS_ERR_CUDA;
@@ -610,10 +666,17 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
 {
     if (!pl || !d_ls || !d_tspws) return TSPWS_ERR_NULL;
     int e;
+    const long stop = env_long("TSPWS_DEBUG_STOP", 0);   /* timing experiments only: cut the tail after stage n */
+    if (stop == 1) return 0;
     tspws_cu_profile_mark(stream);
     if (pl->two_stage) {
-        if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, pl->mean_split ? pl->d_gmean : NULL, (int)pl->K, pl->N,
+        if (pl->cs2_pending) {
+            if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
+                                          1, pl->p.lrm, pl->p.fold, pl->mean_split, pl->d_gsum, pl->d_gtile, pl->d_gsum32,
+                                          pl->mean_split ? pl->d_gmean : NULL, stream))) return TSPWS_ERR_CUDA;
+        } else if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, pl->mean_split ? pl->d_gmean : NULL, (int)pl->K, pl->N,
                                      pl->d_gtile, pl->ntile, pl->p.lrm, pl->p.fold, pl->mean_split, stream))) return TSPWS_ERR_CUDA;
+        if (stop == 2) return 0;
         if (pl->dev.per_trace) {
             /* fork: fp64 transform of the group mean on the side stream, fp32 transforms of the residuals here */
             cudaStream_t A = (cudaStream_t)stream;
@@ -625,6 +688,7 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
             if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
             if (pl->mean_split && B != A &&
                 (cudaEventRecord(pl->ev_join, B) != cudaSuccess || cudaStreamWaitEvent(A, pl->ev_join, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
+            if (stop == 3) return 0;
             if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, pl->mean_split ? pl->d_ymean : NULL,
                                              plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
         } else {
@@ -635,6 +699,7 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     } else if (pl->summed_across_ranks) {
         if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), 0, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     }
+    if (stop == 4) return 0;
     tspws_cu_inverse_side_stream(pl->side);
     e = tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), pl->acc64, 1, pl->d_rule, pl->d_invscratch,
                          pl->d_inv_tickets, d_tspws, d_ls, stream);
