@@ -44,6 +44,11 @@ typedef struct {
     double gain;     /* synthesis gain ln2/(2 Cpsi V scale) * D       */
 } tspws_scale_t;
 
+/* fp64 mean transform: filters on the long list are split over CTAs of at most 4096 taps; the partial
+ * coefficients land in separate slots [split][ncoef] that phasor_combine_kernel adds in slot order */
+#define TSPWS_F64_MAXSPLIT 8
+#define TSPWS_F64_NSPLIT(L) (((L) + 4095) / 4096 < TSPWS_F64_MAXSPLIT ? ((L) + 4095) / 4096 : TSPWS_F64_MAXSPLIT)
+
 /* ---- forward-transform work item of the generic kernel: a run of coefficients of one scale ---- */
 typedef struct {
     int s;           /* scale                           */
@@ -83,6 +88,7 @@ typedef struct {
     int                nitems;
     tspws_fwd_item_t  *d_items_gen; /* [nitems_gen] generic kernel: only scales with lg < 0 */
     int                nitems_gen;
+    int                f64_maxl;  /* mean split: filters at least this long are transformed unsplit in fp32 */
     tspws_fwd_item_t  *d_items_short; /* fp64 mean transform: warp items of the scales with L < 1024 */
     int                nitems_short;
     int               *d_long;    /* [nlong][2] (scale, coefficient) of the scales with L >= 1024   */
@@ -161,7 +167,8 @@ int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, 
                           void *d_part_ps, void *d_part_st, tspws_stream_t st);
 /* Per-trace mode (f->per_trace == 1): raw coefficients of each of the ntr traces (split over
  * phase ranges for coarse scales) go to d_ypart [f->ypart_len * ntr] complex fp32 ... */
-int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, void *d_ypart,
+/* long_row0 > 0: scales with L >= f->f64_maxl read their traces from row long_row0 on (mean split) */
+int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
                               tspws_stream_t st);
 /* ... and are combined here: for segment g (ntr = nseg*seg traces), PS = sum phasor(Y), ST = sum Y,
  * Zout = ST * weight(PS).  Outputs [nseg][ncoef] complex fp32. */

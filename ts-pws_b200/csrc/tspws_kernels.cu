@@ -334,13 +334,20 @@ group_post_kernel(double *__restrict__ gsum, float *__restrict__ out32, double *
         sa += a; sb += b;
     }
     const double ma = split ? sa / (double)K : 0.0, mb = split ? sb / (double)K : 0.0;
-    if (gmean) { gmean[n] = ma; gmean[r] = mb; }
+    if (gmean) {                                   /* three periods: fwd_f64_kernel reads it without wrap tests */
+        gmean[n] = ma; gmean[n + N] = ma; gmean[n + 2 * N] = ma;
+        gmean[r] = mb; gmean[r + N] = mb; gmean[r + 2 * N] = mb;
+    }
 #pragma unroll 4
     for (int k = 0; k < K; k++) {
         const double *g = gsum + (size_t)k * N;
         float *f = out32 + (size_t)k * N;
         f[n] = (float)(g[n] - ma);
         f[r] = (float)(g[r] - mb);
+        if (split > 1) {                           /* rows K..2K-1: the unsplit group sums (long filters) */
+            f[(size_t)K * N + n] = (float)g[n];
+            f[(size_t)K * N + r] = (float)g[r];
+        }
     }
 }
 
@@ -478,11 +485,14 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
 #pragma unroll
         for (int i = 0; i < GP2_LANES; i++) m += s_m[i][lane];
         m /= (double)K;
-        if (w == 0 && ok && gmean) gmean[n] = m;
+        if (w == 0 && ok && gmean) { gmean[n] = m; gmean[n + N] = m; gmean[n + 2 * N] = m; }   /* three periods for fwd_f64_kernel */
     }
     if (!ok) return;
-    for (int k = w; k < K; k += GP2_LANES)
-        out32[(size_t)k * N + n] = (float)(gsum[(size_t)k * N + n] - m);
+    for (int k = w; k < K; k += GP2_LANES) {
+        const double v = gsum[(size_t)k * N + n];
+        out32[(size_t)k * N + n] = (float)(v - m);
+        if (split > 1) out32[(size_t)(K + k) * N + n] = (float)v;  /* rows K..2K-1: unsplit (long filters) */
+    }
 }
 
 extern "C" int tspws_cu_group_post2(const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
@@ -970,29 +980,35 @@ fwd2_acc_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restri
 
 /* per-trace mode: one kernel for all LG (no accumulators -> one register budget fits all).
  * grid = (ceil(items / 8 warps), traces). */
-__global__ void __launch_bounds__(FW_WARPS * 32, FW_MINB)
+#ifndef FW_PT_MINB
+#define FW_PT_MINB FW_MINB
+#endif
+__global__ void __launch_bounds__(FW_WARPS * 32, FW_PT_MINB)
 fwd2_pertrace_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
                      const tspws_fwd2_item_t *__restrict__ items, int nitems,
                      const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len,
-                     int smem_per_warp)
+                     int smem_per_warp, int ntr, int tchunk, int long_L, int long_row0)
 {
     extern __shared__ float fw_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    /* blockIdx.x = trace (fastest): the traces of one item run together -> one code variant and
-     * one set of filter rows live at a time */
+    /* blockIdx.x = run of tchunk traces (fastest): the traces of one item run together -> one code
+     * variant and one set of filter rows live at a time.  Inside a run the item set-up (scale record,
+     * index arithmetic) is paid once and the next trace's window is staged under the FMAs. */
     const int idx = blockIdx.y * FW_WARPS + w;
     if (idx >= nitems) return;
     const tspws_fwd2_item_t it = items[idx];
     const tspws_scale_t sc = scales[it.s];
-    const int k = blockIdx.x;
+    const int k = blockIdx.x * tchunk, k1 = min(ntr, k + tchunk);
     float *xs = fw_smem + (size_t)w * smem_per_warp;
+    /* mean split: scales with long filters read the unsplit traces stored from row long_row0 on */
+    if (sc.L >= long_L) x += (size_t)long_row0 * N;
     switch (sc.lg) {
-    case 0: fwd2_body<0, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
-    case 1: fwd2_body<1, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
-    case 2: fwd2_body<2, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
-    case 3: fwd2_body<3, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
-    case 4: fwd2_body<4, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
-    default: fwd2_body<5, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 0: fwd2_body<0, true>(sc, it, g_all, x, N, k, k1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 1: fwd2_body<1, true>(sc, it, g_all, x, N, k, k1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 2: fwd2_body<2, true>(sc, it, g_all, x, N, k, k1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 3: fwd2_body<3, true>(sc, it, g_all, x, N, k, k1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 4: fwd2_body<4, true>(sc, it, g_all, x, N, k, k1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    default: fwd2_body<5, true>(sc, it, g_all, x, N, k, k1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
     }
 }
 
@@ -1003,7 +1019,8 @@ template <typename T, bool PLAIN>
 __global__ void __launch_bounds__(FWD_WARPS * 32)
 fwd_pertrace_generic_kernel(const tspws_scale_t *__restrict__ scales, const typename cplx<T>::type *__restrict__ wall,
                             const tspws_fwd_item_t *__restrict__ items, int nitems,
-                            const T *__restrict__ x, int N, typename cplx<T>::type *__restrict__ out, int out_ld)
+                            const T *__restrict__ x, int N, typename cplx<T>::type *__restrict__ out, int out_ld,
+                            int long_L, int long_row0)
 {
     typedef typename cplx<T>::type T2;
     const int witem = blockIdx.x * FWD_WARPS + (threadIdx.x >> 5);
@@ -1013,7 +1030,7 @@ fwd_pertrace_generic_kernel(const tspws_scale_t *__restrict__ scales, const type
     const int lane = threadIdx.x & 31;
     const int G = sc.G, g = lane & (G - 1), og = lane / G, opp = 32 / G;
     const T2 *__restrict__ w = wall + sc.tap_off;
-    const T *__restrict__ xk = x + (size_t)blockIdx.y * N;
+    const T *__restrict__ xk = x + ((size_t)blockIdx.y + (sc.L >= long_L ? long_row0 : 0)) * N;
     for (int mb = 0; mb < it.nout; mb += opp) {
         const bool valid = (mb + og) < it.nout;
         const int  m     = it.m0 + (valid ? mb + og : it.nout - 1);
@@ -1041,72 +1058,133 @@ fwd_pertrace_generic_kernel(const tspws_scale_t *__restrict__ scales, const type
     }
 }
 
-/* fp64 transform of ntr double traces -> [ntr][ncoef] double2 in ONE launch of 256-thread CTAs:
- *   CTAs [0, nshort_cta)  : 8 warp items each (short filters, lanes split the taps of a coefficient);
- *   CTAs [nshort_cta, ..) : one coefficient each (long filters: 256 lanes split the taps -- a single
- *                           warp would walk a 16384-tap filter in 128 dependent rounds of L2 latency). */
+/* fp64 forward transform of a few traces (the group mean of the mean split, see group_post2_kernel).
+ *   x: [ntr][3N], every trace stored three times back to back, so that the circular index
+ *      (m D - c + l) mod N is a plain offset base + r D + l < 3N and the tap loop has no wrap test;
+ *   every lane keeps F64_R consecutive coefficients of one scale in registers: a filter tap is loaded
+ *   once per F64_R coefficients, 2 DFMA per loaded sample, ~1.7 instructions per DFMA.
+ *   CTAs [0, nshort_cta): 8 warp items each; G lanes split the taps of a coefficient group and the
+ *   32/G groups of a warp advance through the item's run together (filters shorter than F64_LONG);
+ *   remaining CTAs: the whole CTA splits the taps of one group of F64_R coefficients (long filters). */
+#define F64_R 4
+template <int G, int STRIDE>
+__device__ __forceinline__ void f64_taps(const double2 *__restrict__ pw, const double *__restrict__ px, const int (&off)[F64_R],
+                                         int l, const int L, double (&ar)[F64_R], double (&ai)[F64_R])
+{
+    pw += l; px += l;
+    for (; l + 3 * STRIDE < L; l += 4 * STRIDE) {
+        double2 wv[4];
+        double  xv[4][F64_R];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            wv[j] = __ldg(pw + j * STRIDE);
+#pragma unroll
+            for (int r = 0; r < F64_R; r++) xv[j][r] = __ldg(px + off[r] + j * STRIDE);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int r = 0; r < F64_R; r++) { ar[r] = fma(xv[j][r], wv[j].x, ar[r]); ai[r] = fma(-xv[j][r], wv[j].y, ai[r]); }
+        pw += 4 * STRIDE; px += 4 * STRIDE;
+    }
+    for (; l < L; l += STRIDE) {
+        const double2 wv = __ldg(pw);
+#pragma unroll
+        for (int r = 0; r < F64_R; r++) { const double xv = __ldg(px + off[r]); ar[r] = fma(xv, wv.x, ar[r]); ai[r] = fma(-xv, wv.y, ai[r]); }
+        pw += STRIDE; px += STRIDE;
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void f64_short_item(const tspws_scale_t &sc, const tspws_fwd_item_t &it, const double2 *__restrict__ w,
+                                               const double *__restrict__ xk, int N, double2 *__restrict__ out, int lane)
+{
+    const int g = lane & (G - 1), og = lane / G, opp = 32 / G;
+    for (int mb = 0; mb < it.nout; mb += opp * F64_R) {
+        const int  mrel  = mb + og * F64_R;
+        const bool valid = mrel < it.nout;
+        const int  m     = it.m0 + (valid ? mrel : 0);
+        const int  nr    = valid ? min(F64_R, it.nout - mrel) : 0;
+        long long pll = ((long long)m * sc.D - sc.c) % N;
+        if (pll < 0) pll += N;
+        int off[F64_R];
+#pragma unroll
+        for (int r = 0; r < F64_R; r++) off[r] = min(r, max(nr - 1, 0)) * sc.D;
+        double ar[F64_R], ai[F64_R];
+#pragma unroll
+        for (int r = 0; r < F64_R; r++) ar[r] = ai[r] = 0.0;
+        f64_taps<G, G>(w, xk + (int)pll, off, g, sc.L, ar, ai);
+#pragma unroll
+        for (int o = G >> 1; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < F64_R; r++) {
+                ar[r] += __shfl_xor_sync(0xffffffffu, ar[r], o);
+                ai[r] += __shfl_xor_sync(0xffffffffu, ai[r], o);
+            }
+        if (g == 0)
+#pragma unroll
+            for (int r = 0; r < F64_R; r++)
+                if (r < nr) out[sc.coef_off + m + r] = make_double2(ar[r], ai[r]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restrict__ wall,
                const tspws_fwd_item_t *__restrict__ items, int nitems, int nshort_cta,
                const int2 *__restrict__ coefs, const double *__restrict__ x, int N,
                double2 *__restrict__ out, int out_ld)
 {
-    __shared__ double sh[33];
-    const double *__restrict__ xk = x + (size_t)blockIdx.y * N;
+    __shared__ double sh[8][2 * F64_R];
+    const double *__restrict__ xk = x + (size_t)blockIdx.y * 3 * N;
+    double2 *__restrict__ o = out + (size_t)blockIdx.y * out_ld;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if ((int)blockIdx.x < nshort_cta) {
-        const int witem = blockIdx.x * 8 + (threadIdx.x >> 5);
+        const int witem = blockIdx.x * 8 + warp;
         if (witem >= nitems) return;
         const tspws_fwd_item_t it = items[witem];
         const tspws_scale_t sc = scales[it.s];
-        const int lane = threadIdx.x & 31;
-        const int G = sc.G, g = lane & (G - 1), og = lane / G, opp = 32 / G;
         const double2 *__restrict__ w = wall + sc.tap_off;
-        for (int mb = 0; mb < it.nout; mb += opp) {
-            const bool valid = (mb + og) < it.nout;
-            const int  m     = it.m0 + (valid ? mb + og : it.nout - 1);
-            long long pll = ((long long)m * sc.D - sc.c + g) % N;
-            if (pll < 0) pll += N;
-            int p = (int)pll;
-            double ar = 0.0, ai = 0.0;
-#pragma unroll 8
-            for (int l = g; l < sc.L; l += G) {
-                const double2 wv = __ldg(w + l);
-                const double  xv = __ldg(xk + p);
-                ar = fma(xv, wv.x, ar);
-                ai = fma(-xv, wv.y, ai);
-                p += G;
-                if (p >= N) p -= N;
-            }
-            for (int o = G >> 1; o > 0; o >>= 1) {
-                ar += __shfl_xor_sync(0xffffffffu, ar, o);
-                ai += __shfl_xor_sync(0xffffffffu, ai, o);
-            }
-            if (g == 0 && valid) out[(size_t)blockIdx.y * out_ld + sc.coef_off + m] = make_double2(ar, ai);
+        switch (sc.G) {
+        case 1:  f64_short_item<1>(sc, it, w, xk, N, o, lane); break;
+        case 2:  f64_short_item<2>(sc, it, w, xk, N, o, lane); break;
+        case 4:  f64_short_item<4>(sc, it, w, xk, N, o, lane); break;
+        case 8:  f64_short_item<8>(sc, it, w, xk, N, o, lane); break;
+        case 16: f64_short_item<16>(sc, it, w, xk, N, o, lane); break;
+        default: f64_short_item<32>(sc, it, w, xk, N, o, lane); break;
         }
         return;
     }
-    const int2 cm = coefs[blockIdx.x - nshort_cta];        /* (scale, coefficient) */
-    const tspws_scale_t sc = scales[cm.x];
-    const double2 *__restrict__ w = wall + sc.tap_off;
-    long long pll = ((long long)cm.y * sc.D - sc.c + threadIdx.x) % N;
+    const int2 cm = coefs[blockIdx.x - nshort_cta];        /* (scale | tap split << 16, first coefficient of the group) */
+    const tspws_scale_t sc = scales[cm.x & 0xffff];
+    const int q = cm.x >> 16, nsp = TSPWS_F64_NSPLIT(sc.L), Lq = (sc.L + nsp - 1) / nsp;
+    o += (size_t)q * gridDim.y * out_ld;
+    const int nr = min(F64_R, sc.Ns - cm.y);
+    long long pll = ((long long)cm.y * sc.D - sc.c) % N;
     if (pll < 0) pll += N;
-    int p = (int)pll;
-    const int step = 256 % N;
-    double ar = 0.0, ai = 0.0;
-#pragma unroll 8
-    for (int l = threadIdx.x; l < sc.L; l += 256) {
-        const double2 wv = __ldg(w + l);
-        const double  xv = __ldg(xk + p);
-        ar = fma(xv, wv.x, ar);
-        ai = fma(-xv, wv.y, ai);
-        p += step;
-        if (p >= N) p -= N;
+    int off[F64_R];
+#pragma unroll
+    for (int r = 0; r < F64_R; r++) off[r] = min(r, nr - 1) * sc.D;
+    double ar[F64_R], ai[F64_R];
+#pragma unroll
+    for (int r = 0; r < F64_R; r++) ar[r] = ai[r] = 0.0;
+    f64_taps<256, 256>(wall + sc.tap_off, xk + (int)pll, off, q * Lq + (int)threadIdx.x, min(sc.L, (q + 1) * Lq), ar, ai);
+#pragma unroll
+    for (int r = 0; r < F64_R; r++) { ar[r] = warp_sum(ar[r]); ai[r] = warp_sum(ai[r]); }
+    if (lane == 0)
+#pragma unroll
+        for (int r = 0; r < F64_R; r++) { sh[warp][2 * r] = ar[r]; sh[warp][2 * r + 1] = ai[r]; }
+    __syncthreads();
+    if (threadIdx.x < 2 * F64_R) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t += sh[i][threadIdx.x];
+        sh[0][threadIdx.x] = t;
     }
-    ar = block_sum(ar, sh);
-    ai = block_sum(ai, sh);
-    if (threadIdx.x == 0) out[(size_t)blockIdx.y * out_ld + sc.coef_off + cm.y] = make_double2(ar, ai);
+    __syncthreads();
+    if ((int)threadIdx.x < nr) o[sc.coef_off + cm.y + threadIdx.x] = make_double2(sh[0][2 * threadIdx.x], sh[0][2 * threadIdx.x + 1]);
 }
 
+/* d_x: [ntr][3N] period-padded traces (see above) */
 extern "C" int tspws_cu_forward_f64(const tspws_devframe_t *f, const double *d_x, int ntr, void *d_y, tspws_stream_t st)
 {
     if (ntr <= 0) return 0;
@@ -1164,7 +1242,7 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
     return 0;
 }
 
-extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, void *d_ypart,
+extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
                                          tspws_stream_t st)
 {
     if (ntr <= 0) return 0;
@@ -1174,15 +1252,23 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
         const size_t smem = (size_t)f->fw_smem_per_warp * FW_WARPS * sizeof(float);
         if (smem > 48 * 1024)
             cudaFuncSetAttribute(fwd2_pertrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid(ntr, (f->nitems2 + FW_WARPS - 1) / FW_WARPS);
+        /* traces per CTA.  Measured at K = 10 traces x 16384 (profiles/): 1 trace per CTA 27 us, 2 -> 43 us,
+         * 10 -> 90 us: the kernel is issue bound and wants the widest grid, so the default stays 1. */
+        const int cpt = (f->nitems2 + FW_WARPS - 1) / FW_WARPS;
+        static long env_chunk = -1;
+        if (env_chunk < 0) { const char *e = getenv("TSPWS_PT_CHUNK"); env_chunk = e ? atol(e) : 1; }
+        int tchunk = env_chunk > 0 ? (int)env_chunk : 1;
+        if (tchunk > ntr) tchunk = ntr;
+        dim3 grid((ntr + tchunk - 1) / tchunk, cpt);
         fwd2_pertrace_kernel<<<grid, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, f->d_items2,
-            f->nitems2, d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp);
+            f->nitems2, d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp, ntr, tchunk,
+            long_row0 > 0 ? f->f64_maxl : 0x7fffffff, long_row0);
         TSPWS_LAUNCHED_N("fwd2_pertrace_kernel", s);
     }
     if (f->nitems_gen > 0) {
         dim3 grid((f->nitems_gen + FWD_WARPS - 1) / FWD_WARPS, ntr);
         fwd_pertrace_generic_kernel<float, false><<<grid, FWD_WARPS * 32, 0, s>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items_gen,
-            f->nitems_gen, d_x, f->N, (float2 *)d_ypart, f->ypart_len);
+            f->nitems_gen, d_x, f->N, (float2 *)d_ypart, f->ypart_len, long_row0 > 0 ? f->f64_maxl : 0x7fffffff, long_row0);
         TSPWS_LAUNCHED_N("fwd_pertrace_generic_kernel", s);
     }
     return 0;
@@ -1207,7 +1293,7 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
      * coefficients | nsplit << 8, Ns = stride between phase splits) */
     const int4 tile = tiles[blockIdx.x];
     const int ci = threadIdx.x & (PC_TILE - 1), slot = threadIdx.x / PC_TILE;
-    const int nvalid = tile.z & 255, nsplit = tile.z >> 8, Ns = tile.w;
+    const int nvalid = tile.z & 255, nsplit = (tile.z >> 8) & 255, nsp64 = tile.z >> 16, Ns = tile.w;
     const int sg = blockIdx.y;
     float pr = 0.f, pi = 0.f;
     double sr = 0.0, si = 0.0;
@@ -1215,7 +1301,12 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
         const float2 *yp0 = ypart + (size_t)sg * seg * ypart_len + tile.x + ci;
         /* fp64 transform of the group mean (mean split, see group_post_kernel): Y_k = Ymean + dY_k */
         double mr = 0.0, mi = 0.0;
-        if (ymean) { const double2 ym = ymean[(size_t)sg * ncoef + tile.y + ci]; mr = ym.x; mi = ym.y; }
+        if (ymean) {
+            for (int sp = 0; sp < nsp64; sp++) {            /* tap splits of fwd_f64_kernel, in slot order */
+                const double2 ym = ymean[((size_t)sp * gridDim.y + sg) * ncoef + tile.y + ci];
+                mr += ym.x; mi += ym.y;
+            }
+        }                                                   /* nsp64 == 0: unsplit transform, nothing to add */
         if (nsplit == 1) {
 #pragma unroll 4
             for (int k = slot; k < seg; k += 4) {
@@ -1949,15 +2040,17 @@ __global__ void __launch_bounds__(256)
 inv_finish_kernel(const float *__restrict__ scratch, int nslots, int nseg, int N, const tspws_weight_t *__restrict__ rules,
                   float *__restrict__ out_ts, float *__restrict__ out_ls)
 {
-    __shared__ double sh[4][64][8];
-    const int col = threadIdx.x & 63, quarter = threadIdx.x >> 6;
-    const int n0 = (blockIdx.x * 64 + col) * 4;
+    /* 32 float4 columns x 8 slot lanes: thread (col, sl) adds slots sl, sl+8, ... of its 4 samples in
+     * fp64, then the 8 lanes of a column are added in lane order -- 12 loads per thread at 44 scales */
+    __shared__ double sh[8][8][33];
+    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int n0 = (blockIdx.x * 32 + col) * 4;
     const int sg = blockIdx.y;
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
     if (n0 < N) {
         if ((N & 3) == 0) {
-#pragma unroll 4
-            for (int g = quarter; g < nslots; g += 4) {
+#pragma unroll 3
+            for (int g = sl; g < nslots; g += 8) {
                 const size_t o = ((size_t)g * nseg + sg) * N + n0;
                 const float4 p = __ldcg(reinterpret_cast<const float4 *>(scratch + o));
                 a[0] += (double)p.x; a[1] += (double)p.y; a[2] += (double)p.z; a[3] += (double)p.w;
@@ -1967,7 +2060,7 @@ inv_finish_kernel(const float *__restrict__ scratch, int nslots, int nseg, int N
                 }
             }
         } else {
-            for (int g = quarter; g < nslots; g += 4) {
+            for (int g = sl; g < nslots; g += 8) {
                 const size_t o = ((size_t)g * nseg + sg) * N + n0;
                 for (int i = 0; i < 4 && n0 + i < N; i++) {
                     a[i] += (double)scratch[o + i];
@@ -1977,17 +2070,18 @@ inv_finish_kernel(const float *__restrict__ scratch, int nslots, int nseg, int N
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) { sh[quarter][col][i] = a[i]; sh[quarter][col][4 + i] = b[i]; }
+    for (int i = 0; i < 4; i++) { sh[sl][i][col] = a[i]; sh[sl][4 + i][col] = b[i]; }
     __syncthreads();
-    if (quarter != 0 || n0 >= N) return;
-    for (int i = 0; i < 4 && n0 + i < N; i++) {
-        const double ta = ((sh[0][col][i] + sh[1][col][i]) + sh[2][col][i]) + sh[3][col][i];
-        out_ts[(size_t)sg * N + n0 + i] = (float)ta;
-        if (WITH_ST) {
-            const double tb = ((sh[0][col][4 + i] + sh[1][col][4 + i]) + sh[2][col][4 + i]) + sh[3][col][4 + i];
-            out_ls[(size_t)sg * N + n0 + i] = __fdiv_rn((float)tb, (float)(unsigned int)rules[sg].T);
-        }
-    }
+    /* thread (col, i = sl): value i of the column (i < 4: tsPWS sample n0 + i, else ls sample n0 + i - 4) */
+    const int i = sl;
+    if (!WITH_ST && i >= 4) return;
+    const int n = n0 + (i & 3);
+    if (n >= N) return;
+    double t = 0.0;
+#pragma unroll
+    for (int l = 0; l < 8; l++) t += sh[l][i][col];
+    if (i < 4) out_ts[(size_t)sg * N + n] = (float)t;
+    else       out_ls[(size_t)sg * N + n] = __fdiv_rn((float)t, (float)(unsigned int)rules[sg].T);
 }
 
 template <typename T>
@@ -2060,7 +2154,7 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
         if (cudaEventRecord(g_inv_join, s4) != cudaSuccess || cudaStreamWaitEvent(s, g_inv_join, 0) != cudaSuccess) return (int)cudaGetLastError();
     }
     {
-        dim3 grid((f->N + 255) / 256, nseg);
+        dim3 grid((f->N + 127) / 128, nseg);
         if (d_st) inv_finish_kernel<true><<<grid, 256, 0, s>>>((const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
         else      inv_finish_kernel<false><<<grid, 256, 0, s>>>((const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
         TSPWS_LAUNCHED_N("inv_finish_kernel", s);

@@ -62,8 +62,9 @@ struct tspws_plan {
     cudaStream_t side;
     cudaEvent_t  ev_fork, ev_join;
     int          mean_split;        /* fp64 transform of the group mean + fp32 transforms of the residuals */
-    double      *d_gmean;           /* [N]      */
-    void        *d_ymean;           /* double2 [ncoef] */
+    int          hybrid;            /* TSPWS_F64_MAXL set: long filters transform the unsplit sums instead */
+    double      *d_gmean;           /* [3N]: the group mean, three periods */
+    void        *d_ymean;           /* double2 [TSPWS_F64_MAXSPLIT][ncoef] */
     int         *h_slot_off;        /* [K+1] first work item of every group */
     void  *own_gsum, *own_exch;
 };
@@ -262,23 +263,35 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
     if (cudaMemcpy(d->d_w32, w32, f->ntaps * 2 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_items, items, nitems * sizeof(*items), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(d->d_invgrp, grp, d->ninv * sizeof(*grp), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
-    if (want64) {   /* fp64 forward work lists: warp items for short filters, one CTA per coefficient for long ones */
-        const int LONG_T = (int)env_long("TSPWS_F64_LONG", 1024);
+    if (want64) {   /* fp64 forward work lists: warp items for short filters, one CTA per 4 coefficients for long ones */
+        /* TSPWS_F64_MAXL (default: off) restricts the fp64 mean transform to filters shorter than that;
+         * longer filters then transform the unsplit group sums in fp32.  Measured at the headline
+         * configuration: 6 us faster with 160, but the coherence error of single coarse
+         * coefficients rises from 4.5e-6 to 1.8e-5, beyond the 1e-5 tolerance -- so every scale is split. */
+        const int LONG_T = (int)env_long("TSPWS_F64_LONG", 1024), R64 = 4, MAXL = (int)env_long("TSPWS_F64_MAXL", 0x7fffffff);
+        d->f64_maxl = MAXL;
+        const long TAPS = env_long("TSPWS_F64_TAPS", 2048);
         int ns = 0, nl = 0;
         for (int s = 0; s < S; s++) {
-            if (sc[s].L >= LONG_T) { nl += sc[s].Ns; continue; }
-            const int opp = 32 / sc[s].G;
-            long run = 1024 / sc[s].L; run -= run % opp; if (run < opp) run = opp;
+            if (sc[s].L >= MAXL) continue;
+            if (sc[s].L >= LONG_T) { nl += ((sc[s].Ns + R64 - 1) / R64) * TSPWS_F64_NSPLIT(sc[s].L); continue; }
+            const int pass = (32 / sc[s].G) * R64;
+            long run = TAPS / sc[s].L; run -= run % pass; if (run < pass) run = pass;
             ns += (sc[s].Ns + (int)run - 1) / (int)run;
         }
         tspws_fwd_item_t *its = (tspws_fwd_item_t *)calloc(ns ? ns : 1, sizeof(*its));
         int *lg = (int *)calloc((size_t)(nl ? nl : 1) * 2, sizeof(int));
         if (!its || !lg) { free(its); free(lg); goto done; }
         int ks = 0, kl = 0;
-        for (int s = 0; s < S; s++) {
-            if (sc[s].L >= LONG_T) { for (int m = 0; m < sc[s].Ns; m++) { lg[2 * kl] = s; lg[2 * kl + 1] = m; kl++; } continue; }
-            const int opp = 32 / sc[s].G;
-            long run = 1024 / sc[s].L; run -= run % opp; if (run < opp) run = opp;
+        for (int s = S - 1; s >= 0; s--) {          /* longest filters first */
+            if (sc[s].L >= MAXL) continue;
+            if (sc[s].L >= LONG_T) {
+                for (int m = 0; m < sc[s].Ns; m += R64)
+                    for (int q = 0; q < TSPWS_F64_NSPLIT(sc[s].L); q++) { lg[2 * kl] = s | (q << 16); lg[2 * kl + 1] = m; kl++; }
+                continue;
+            }
+            const int pass = (32 / sc[s].G) * R64;
+            long run = TAPS / sc[s].L; run -= run % pass; if (run < pass) run = pass;
             for (int m0 = 0; m0 < sc[s].Ns; m0 += (int)run) {
                 its[ks].s = s; its[ks].m0 = m0; its[ks].nout = (sc[s].Ns - m0 < run) ? sc[s].Ns - m0 : (int)run; ks++;
             }
@@ -370,7 +383,11 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
             for (int m0 = 0; m0 < sc[s].Ns; m0 += 64) {
                 const int nv = sc[s].Ns - m0 < 64 ? sc[s].Ns - m0 : 64;
                 tl[4 * k] = sc[s].ypart_off + m0; tl[4 * k + 1] = sc[s].coef_off + m0;
-                tl[4 * k + 2] = nv | (sc[s].nsplit << 8); tl[4 * k + 3] = sc[s].Ns;
+                /* valid coefficients | phase splits of the fp32 partials << 8 | tap splits of the fp64 mean
+                 * transform << 16 (0: the mean of this scale is the extra fp32 trace) */
+                const int nsp64 = sc[s].L >= (int)env_long("TSPWS_F64_MAXL", 0x7fffffff) ? 0 :
+                                  sc[s].L >= (int)env_long("TSPWS_F64_LONG", 1024) ? TSPWS_F64_NSPLIT(sc[s].L) : 1;
+                tl[4 * k + 2] = nv | (sc[s].nsplit << 8) | (nsp64 << 16); tl[4 * k + 3] = sc[s].Ns;
                 k++;
             }
         int bad = cudaMalloc((void **)&d->d_tile16, (size_t)(nt ? nt : 1) * 4 * sizeof(int)) != cudaSuccess ||
@@ -455,7 +472,7 @@ static int twostage_build(tspws_plan_t *pl)
     if (cudaMalloc((void **)&pl->d_gsum, (K * N + (size_t)K * ntiles) * sizeof(double)) != cudaSuccess) goto done;
     if (cudaMemset(pl->d_gsum, 0, (K * N + (size_t)K * ntiles) * sizeof(double)) != cudaSuccess) goto done;
     pl->d_gtile = pl->d_gsum + K * N;
-    if (cudaMalloc((void **)&pl->d_gsum32, K * N * sizeof(float)) != cudaSuccess) goto done;
+    if (cudaMalloc((void **)&pl->d_gsum32, 2 * K * N * sizeof(float)) != cudaSuccess) goto done;   /* rows K..2K-1: unsplit sums (mean split) */
     if (cudaMemcpy(pl->d_cs, it, ni * sizeof(*it), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_slot_off, slot_off, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_grp_t0, grp_t0, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
@@ -540,6 +557,7 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     for (unsigned int s = 0; s < pl->fr->S; s++)
         if (pl->fr->L[s] > (unsigned int)max) goto fail;          /* cannot happen: L is capped at N */
     pl->mean_split = pl->two_stage && !pl->acc64 && env_long("TSPWS_MEAN_SPLIT", 1);
+    pl->hybrid = pl->mean_split && env_long("TSPWS_F64_MAXL", 0x7fffffff) != 0x7fffffff;
     if (tspws_devframe_build(&pl->dev, pl->fr, pl->acc64 || pl->mean_split, pl->two_stage && !pl->acc64)) goto fail;
 
     CK(cudaMalloc((void **)&pl->d_rule, sizeof(tspws_weight_t)));
@@ -567,8 +585,9 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     }
     CK(cudaMalloc(&pl->d_exch, 2 * ncoef * pl->csz));
     if (pl->mean_split) {
-        CK(cudaMalloc((void **)&pl->d_gmean, (size_t)max * sizeof(double)));
-        CK(cudaMalloc(&pl->d_ymean, ncoef * 2 * sizeof(double)));
+        CK(cudaMalloc((void **)&pl->d_gmean, (size_t)max * 3 * sizeof(double)));      /* period-padded, see fwd_f64_kernel */
+        CK(cudaMalloc(&pl->d_ymean, (size_t)TSPWS_F64_MAXSPLIT * ncoef * 2 * sizeof(double)));   /* [split][ncoef] */
+        CK(cudaMemset(pl->d_ymean, 0, (size_t)TSPWS_F64_MAXSPLIT * ncoef * 2 * sizeof(double)));
     }
     CK(cudaMalloc(&pl->d_zout, ncoef * (pl->acc64 ? 2 * sizeof(double) : 4 * sizeof(float))));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.inv_slots ? pl->dev.inv_slots : 1) * max * (pl->csz / 2)));
@@ -672,10 +691,10 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     if (pl->two_stage) {
         if (pl->cs2_pending) {
             if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
-                                          1, pl->p.lrm, pl->p.fold, pl->mean_split, pl->d_gsum, pl->d_gtile, pl->d_gsum32,
+                                          1, pl->p.lrm, pl->p.fold, pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gsum, pl->d_gtile, pl->d_gsum32,
                                           pl->mean_split ? pl->d_gmean : NULL, stream))) return TSPWS_ERR_CUDA;
         } else if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, pl->mean_split ? pl->d_gmean : NULL, (int)pl->K, pl->N,
-                                     pl->d_gtile, pl->ntile, pl->p.lrm, pl->p.fold, pl->mean_split, stream))) return TSPWS_ERR_CUDA;
+                                     pl->d_gtile, pl->ntile, pl->p.lrm, pl->p.fold, pl->mean_split ? 1 + pl->hybrid : 0, stream))) return TSPWS_ERR_CUDA;
         if (stop == 2) return 0;
         if (pl->dev.per_trace) {
             /* fork: fp64 transform of the group mean on the side stream, fp32 transforms of the residuals here */
@@ -685,7 +704,8 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
                 if (B != A && (cudaEventRecord(pl->ev_fork, A) != cudaSuccess || cudaStreamWaitEvent(B, pl->ev_fork, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
                 if ((e = tspws_cu_forward_f64(&pl->dev, pl->d_gmean, 1, pl->d_ymean, B))) return TSPWS_ERR_CUDA;
             }
-            if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
+            /* with the mean split, rows K..2K-1 of d_gsum32 are the unsplit group sums (for the long filters) */
+            if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, pl->mean_split && pl->hybrid ? pl->ntr_fwd : 0, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
             if (pl->mean_split && B != A &&
                 (cudaEventRecord(pl->ev_join, B) != cudaSuccess || cudaStreamWaitEvent(A, pl->ev_join, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
             if (stop == 3) return 0;

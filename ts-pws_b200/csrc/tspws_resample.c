@@ -199,7 +199,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     /* phase stacks: PS_m = sum_t sel[m][t] phasor(Y_t); every trace is transformed once */
     for (unsigned int t0 = 0; t0 < mtr; t0 += TR_BATCH) {
         const int nt = (int)((mtr - t0 < TR_BATCH) ? mtr - t0 : TR_BATCH);
-        CKK(tspws_cu_forward_pertrace(&F->pt, d_x + (size_t)t0 * N, nt, d_ypart, st));
+        CKK(tspws_cu_forward_pertrace(&F->pt, d_x + (size_t)t0 * N, nt, 0, d_ypart, st));
         CKK(tspws_cu_coef_matrix(&F->pt, d_ypart, nt, NULL, d_P, st));
         CKK(tspws_cu_select_sum(d_P, nt, (int)F->fr->ncoef, d_sel, (int)mtr, (int)t0, (int)M, d_ps64, st));
     }
@@ -332,7 +332,7 @@ int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, 
         const int nb = (int)((n_single - t0 < (unsigned int)B) ? n_single - t0 : (unsigned int)B);
         for (int b = 0; b < nb; b++) h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, t0 + b + 1, t0 + b + 1);
         CKR(cudaMemcpyAsync(d_rules, h_rules, nb * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
-        CKK(tspws_cu_forward_pertrace(&F.pt, d_x + (size_t)t0 * N, nb, d_ypart, st));
+        CKK(tspws_cu_forward_pertrace(&F.pt, d_x + (size_t)t0 * N, nb, 0, d_ypart, st));
         CKK(tspws_cu_coef_matrix(&F.pt, d_ypart, nb, d_Y, d_P, st));
         CKK(tspws_cu_prefix_weight(d_Y, d_P, (int)F.fr->ncoef, nb, d_sst, d_sps, d_rules, d_zout, st));
         CKK(tspws_cu_inverse(&F.acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st));
