@@ -52,6 +52,27 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "two_stage_morlet"
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """Libraries (NCCL's version banner, torch elastic) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the rest of the run and keep the real stdout for emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    fd = _JSON_FD if _JSON_FD is not None else 1
+    while data:
+        n = os.write(fd, data)
+        data = data[n:]
+
+
 def load_pkg():
     spec = importlib.util.spec_from_file_location("ts_pws_b200", os.path.join(ROOT, "ts-pws_b200", "__init__.py"))
     m = importlib.util.module_from_spec(spec)
@@ -172,7 +193,7 @@ def run_reference_arm(args, wl, name):
     ref_steps = max(1, min(args.steps, 5))       # each step is seconds of CPU work: keep the run within minutes
     r = reference_time(B, wl, sample, steps=ref_steps, warmup=min(args.warmup, 1))
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libtspws_ref.so missing (build with make -C oracle)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libtspws_ref.so missing (build with make -C oracle)"})
         return
     line = {
         "impl": "reference", "metric": "stacked trace-samples/s", "value": r["value"], "unit": "trace-samples/s",
@@ -184,7 +205,7 @@ def run_reference_arm(args, wl, name):
                          "sample": f"reference tspws_main (gcc -O3 -fopenmp, x86-64-v3) on {sample} traces x {wl['n']} samples"},
         "e2e": {"value": r["value"], "unit": "trace-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -204,6 +225,7 @@ def run_ours(args, wl, name):
     torch.cuda.set_device(local)
     lib.tspws_b200_set_option(B.OPT_DEVICE, local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     mtr, n = wl["mtr"], wl["n"]
@@ -242,6 +264,29 @@ def run_ours(args, wl, name):
         if rc:
             raise SystemExit(f"stack failed rc={rc}")
 
+    # N > 1: the whole step (reduce kernels, NCCL all-reduce, tail kernels) replayed as one CUDA graph,
+    # like tspws_b200_plan_stack does on one GPU; falls back to direct launches if capture fails
+    step_graph = None
+    def capture_step():
+        nonlocal step_graph
+        if world == 1 or os.environ.get("TSPWS_BENCH_NO_GRAPH"):
+            return
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                step()
+            step_graph = g
+        except Exception as e:                      # noqa: BLE001
+            print(f"[bench] rank {rank}: graph capture of the multi-GPU step failed ({e}); direct launches", file=sys.stderr)
+            step_graph = None
+            torch.cuda.synchronize()
+
+    def fast_step():
+        if step_graph is not None:
+            step_graph.replay()
+        else:
+            step()
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -249,6 +294,15 @@ def run_ours(args, wl, name):
 
     for _ in range(max(3, args.warmup)):
         step()
+    barrier()
+    capture_step()
+    ok = torch.tensor([1 if (world == 1 or step_graph is not None) else 0], device="cuda")
+    if world > 1:
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks replay the graph, or none does
+        if int(ok[0]) == 0:
+            step_graph = None
+    for _ in range(2):
+        fast_step()
     barrier()
 
     # ---- timed region: K steps, device-resident inputs (512 MiB per rank > 126 MB L2) ----
@@ -275,7 +329,7 @@ def run_ours(args, wl, name):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        step()
+        fast_step()
     ev1.record()
     barrier()
     ms_clean = ev0.elapsed_time(ev1)
@@ -357,7 +411,26 @@ def run_ours(args, wl, name):
         e2e["max_abs_diff_vs_device_path"] = float(np.max(np.abs(ts_h.numpy() - d_ts.cpu().numpy())))
 
     clocks = sampler.finish() if sampler else None      # sampled over the timed region and the e2e loop
+
+    def teardown():
+        nonlocal step_graph
+        step_graph = None                               # the captured step holds NCCL work: drop it first
+        torch.cuda.synchronize()
+        lib.tspws_b200_plan_destroy(plan)
+        if world > 1:
+            # never let process-group teardown outlive the measurement: the JSON line is already out
+            t = threading.Timer(30.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
+            try:
+                dist.barrier()
+                dist.destroy_process_group()
+            except Exception:                           # noqa: BLE001
+                pass
+            t.cancel()
+
     if rank != 0:
+        teardown()
         return
 
     # ---- roofline of the dominant kernel ----
@@ -415,13 +488,12 @@ def run_ours(args, wl, name):
                    "scales": int(p.J * p.V), "parallelism": f"traces sharded x{world}, NCCL all-reduce of the "
                    f"{'group sums' if two_stage else 'phasor/linear sums'}" if world > 1 else "single GPU",
                    "l2_note": "per-step input 512 MiB per GPU > 126 MB L2 (no flush needed)",
-                   "ms_per_step_with_kernel_events": ms / args.steps},
+                   "ms_per_step_with_kernel_events": ms / args.steps,
+                   "step_replayed_as_cuda_graph": bool(world == 1 or step_graph is not None)},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line))
-    lib.tspws_b200_plan_destroy(plan)
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
+    teardown()
 
 
 def main():
@@ -433,6 +505,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    protect_stdout()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, wl, args.workload)
