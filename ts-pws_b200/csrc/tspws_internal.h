@@ -150,8 +150,6 @@ int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts /*int4[nparts]
 int tspws_cu_group_post2(const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
                          int ntile, int mode, int do_rm, int do_fold, int split, double *d_gsum, double *d_gtile,
                          float *d_out32, double *d_gmean, tspws_stream_t st);
-int tspws_cu_group_post(double *d_gsum, float *d_out32, double *d_gmean /*[N] or NULL*/, int G, int N,
-                        const double *d_gtile, int ntile, int do_rm, int do_fold, int split, tspws_stream_t st);
 /* fp64 transform (generic kernel) of ntr double traces -> [ntr][ncoef] double2 */
 int tspws_cu_forward_f64(const tspws_devframe_t *f, const double *d_x, int ntr, void *d_y, tspws_stream_t st);
 

@@ -5,7 +5,7 @@
  * ------------------------  -----------------------------------------------------  -------
  * prep_kernel               fold src/ts_pws1f_lib.c:76-86, mean removal :160-168   HBM
  * colsum_kernel             partial_linear_stacks src/ts_pws1f_lib.c:866-881       HBM  (headline)
- * group_post_kernel         mean + fold applied to the Kmax group sums (linear)    tiny
+ * group_post2_kernel        slot sums + mean / fold / mean split of the group sums   tiny
  * fwd_kernel                complex_1D_wavelet_dec src/FWTa/wavelet_v7.c:43-64 ->
  *                           cdotx_dc src/FWTa/cdotx.c:35-72, fused with the phasor
  *                           accumulate of src/ts_pws1f_lib.c:486-494 / :897-904    FP32/LSU
@@ -290,7 +290,7 @@ extern "C" int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t 
     return 0;
 }
 
-/* Group post-processing on the (already reduced, possibly all-reduced) group sums:
+/* Group post-processing on the group sums (group_post2_kernel below):
  *   mean removal : the reference subtracts every trace's mean from its samples
  *                  (src/ts_pws1f_lib.c:160-168); summed over a group that is the constant
  *                  sum_t mean_t = (1/N) sum_n G[n], taken here from the tile totals;
@@ -300,67 +300,8 @@ extern "C" int tspws_cu_colsum(const float *d_x, int N, const tspws_csum_item_t 
  *                  residuals G_k - M go through the fp32 transform: Y_k = T64(M) + T32(G_k - M).
  *                  The phase of a coefficient that is small in one group is then no longer limited
  *                  by the fp32 rounding of the large common part (headline config: coherence error
- *                  2e-5 -> 1e-6 against the reference's double).
- * Emits the fp32 traces the fp32 transform reads.  grid = tiles over ceil(N/2). */
-__global__ void __launch_bounds__(64)
-group_post_kernel(double *__restrict__ gsum, float *__restrict__ out32, double *__restrict__ gmean, int N, int K,
-                  const double *__restrict__ gtile, int ntile, int do_rm, int do_fold, int split, int corr_in_smem)
-{
-    extern __shared__ double s_corr[];
-    if (do_rm && corr_in_smem) {
-        for (int k = threadIdx.x; k < K; k += blockDim.x) {
-            double c = 0.0;
-            for (int i = 0; i < ntile; i++) c += gtile[k * ntile + i];     /* same order in every CTA */
-            s_corr[k] = c / (double)(unsigned int)N;
-        }
-        __syncthreads();
-    }
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    const int half = (N + 1) / 2;
-    if (n >= half) return;
-    const int r = N - 1 - n;
-    double sa = 0.0, sb = 0.0;
-#pragma unroll 4
-    for (int k = 0; k < K; k++) {
-        double corr = 0.0;
-        if (do_rm) {
-            if (corr_in_smem) corr = s_corr[k];
-            else { for (int i = 0; i < ntile; i++) corr += gtile[k * ntile + i]; corr /= (double)(unsigned int)N; }
-        }
-        double *g = gsum + (size_t)k * N;
-        double a = g[n] - corr, b = g[r] - corr;
-        if (do_fold && r != n) { a = 0.5 * (a + b); b = a; }
-        g[n] = a; g[r] = b;
-        sa += a; sb += b;
-    }
-    const double ma = split ? sa / (double)K : 0.0, mb = split ? sb / (double)K : 0.0;
-    if (gmean) {                                   /* three periods: fwd_f64_kernel reads it without wrap tests */
-        gmean[n] = ma; gmean[n + N] = ma; gmean[n + 2 * N] = ma;
-        gmean[r] = mb; gmean[r + N] = mb; gmean[r + 2 * N] = mb;
-    }
-#pragma unroll 4
-    for (int k = 0; k < K; k++) {
-        const double *g = gsum + (size_t)k * N;
-        float *f = out32 + (size_t)k * N;
-        f[n] = (float)(g[n] - ma);
-        f[r] = (float)(g[r] - mb);
-        if (split > 1) {                           /* rows K..2K-1: the unsplit group sums (long filters) */
-            f[(size_t)K * N + n] = (float)g[n];
-            f[(size_t)K * N + r] = (float)g[r];
-        }
-    }
-}
-
-extern "C" int tspws_cu_group_post(double *d_gsum, float *d_out32, double *d_gmean, int G, int N, const double *d_gtile,
-                                   int ntile, int do_rm, int do_fold, int split, tspws_stream_t st)
-{
-    const int in_smem = (size_t)G * sizeof(double) <= 40 * 1024;
-    const size_t smem = (do_rm && in_smem) ? (size_t)G * sizeof(double) : 0;
-    group_post_kernel<<<((N + 1) / 2 + 63) / 64, 64, smem, (cudaStream_t)st>>>(d_gsum, d_out32, d_gmean, N, G, d_gtile, ntile,
-                                                                                  do_rm, do_fold, split, in_smem);
-    TSPWS_LAUNCHED_N("group_post_kernel", (cudaStream_t)st);
-    return 0;
-}
+ *                  2e-5 -> 4.5e-6 against the reference's double).
+ * Emits the fp32 traces the fp32 transform reads. */
 
 /* ------------------------------------------------------------------------------------- */
 /* Single-wave group sums (N % 4 == 0): grid = column tiles x row parts, sized on the host to  */
@@ -423,11 +364,11 @@ extern "C" int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts, in
     return 0;
 }
 
-/* Slot sums -> group sums, with the linear post-processing of group_post_kernel fused in.
+/* Slot sums -> group sums, with the linear post-processing described above fused in.
  * Block = 32 consecutive samples x 8 group lanes (warp w handles groups w, w+8, ...): every global
  * access is a coalesced 256 B row, and all groups of a sample are in flight together.
  *   mode 0  combine only: gsum = sum of slots, gtile = sum of slot totals (the exchange block of a
- *           sharded plan; mean removal etc. follow the all-reduce, in group_post_kernel)
+ *           sharded plan; mean removal etc. follow the all-reduce, in a mode-1 launch over the block)
  *   mode 1  full: mean removal (from the slot totals), fold, mean split, fp32 copy / residuals    */
 #define GP2_LANES 8
 __global__ void __launch_bounds__(32 * GP2_LANES)
@@ -1299,7 +1240,7 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
     double sr = 0.0, si = 0.0;
     if (ci < nvalid) {
         const float2 *yp0 = ypart + (size_t)sg * seg * ypart_len + tile.x + ci;
-        /* fp64 transform of the group mean (mean split, see group_post_kernel): Y_k = Ymean + dY_k */
+        /* fp64 transform of the group mean (mean split, see group_post2_kernel): Y_k = Ymean + dY_k */
         double mr = 0.0, mi = 0.0;
         if (ymean) {
             for (int sp = 0; sp < nsp64; sp++) {            /* tap splits of fwd_f64_kernel, in slot order */

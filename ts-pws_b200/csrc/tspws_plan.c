@@ -42,6 +42,8 @@ struct tspws_plan {
     int    *d_slot_off, *d_grp_t0;
     /* single-wave group sums (colsum2_kernel): row parts, their slots, slot totals */
     int     cs2, cs2_nparts, cs2_nslots, cs2_pending;
+    double *d_gfin;                 /* [K][N] post-processed group sums when the input is the exchange block */
+    int    *d_ident;                /* [K+1] 0..K: the exchange block seen as one slot per group */
     void   *d_cs2_parts;
     int    *d_cs2_slot_off;
     double *d_cs2_slots, *d_cs2_tot;
@@ -477,6 +479,16 @@ static int twostage_build(tspws_plan_t *pl)
     if (cudaMemcpy(pl->d_slot_off, slot_off, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     if (cudaMemcpy(pl->d_grp_t0, grp_t0, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     pl->h_slot_off = slot_off; slot_off = NULL;
+    {
+        int *id = (int *)malloc((K + 1) * sizeof(int));
+        if (!id) goto done;
+        for (unsigned int k = 0; k <= K; k++) id[k] = (int)k;
+        const int bad = cudaMalloc((void **)&pl->d_ident, (K + 1) * sizeof(int)) != cudaSuccess ||
+                        cudaMemcpy(pl->d_ident, id, (K + 1) * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                        cudaMalloc((void **)&pl->d_gfin, K * N * sizeof(double)) != cudaSuccess;
+        free(id);
+        if (bad) goto done;
+    }
 
     /* ---- single-wave variant: ntiles x nparts CTAs = 148 SMs x 4 resident CTAs, equal rows per part ---- */
     pl->cs2 = 0;
@@ -529,6 +541,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     cudaFree(pl->d_gmean); cudaFree(pl->d_ymean);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
+    cudaFree(pl->d_gfin); cudaFree(pl->d_ident);
     cudaFree(pl->d_cs2_parts); cudaFree(pl->d_cs2_slot_off); cudaFree(pl->d_cs2_slots); cudaFree(pl->d_cs2_tot);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
     cudaFree(pl->d_part); cudaFree(pl->d_tickets); cudaFree(pl->d_gsum); cudaFree(pl->d_gsum32);
@@ -689,12 +702,19 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
     if (stop == 1) return 0;
     tspws_cu_profile_mark(stream);
     if (pl->two_stage) {
+        /* post-processed fp64 group sums: from the slots of colsum2 (unsharded), or from the exchange block
+         * (sharded / bound / N % 4 != 0) seen as one slot per group, written to a separate buffer */
+        const double *gfin = pl->d_gsum;
         if (pl->cs2_pending) {
             if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
                                           1, pl->p.lrm, pl->p.fold, pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gsum, pl->d_gtile, pl->d_gsum32,
                                           pl->mean_split ? pl->d_gmean : NULL, stream))) return TSPWS_ERR_CUDA;
-        } else if ((e = tspws_cu_group_post(pl->d_gsum, pl->d_gsum32, pl->mean_split ? pl->d_gmean : NULL, (int)pl->K, pl->N,
-                                     pl->d_gtile, pl->ntile, pl->p.lrm, pl->p.fold, pl->mean_split ? 1 + pl->hybrid : 0, stream))) return TSPWS_ERR_CUDA;
+        } else {
+            if ((e = tspws_cu_group_post2(pl->d_gsum, pl->d_gtile, pl->d_ident, pl->N, (int)pl->K, pl->ntile,
+                                          1, pl->p.lrm, pl->p.fold, pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gfin, NULL, pl->d_gsum32,
+                                          pl->mean_split ? pl->d_gmean : NULL, stream))) return TSPWS_ERR_CUDA;
+            gfin = pl->d_gfin;
+        }
         if (stop == 2) return 0;
         if (pl->dev.per_trace) {
             /* fork: fp64 transform of the group mean on the side stream, fp32 transforms of the residuals here */
@@ -712,7 +732,7 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
             if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, pl->mean_split ? pl->d_ymean : NULL,
                                              plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
         } else {
-            if ((e = tspws_cu_forward(&pl->dev, pl->d_gsum, 1, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_forward(&pl->dev, gfin, 1, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
             if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, 1, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
                                             plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
         }
