@@ -165,6 +165,8 @@ int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, 
                           void *d_part_ps, void *d_part_st, tspws_stream_t st);
 /* Per-trace mode (f->per_trace == 1): raw coefficients of each of the ntr traces (split over
  * phase ranges for coarse scales) go to d_ypart [f->ypart_len * ntr] complex fp32 ... */
+int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
+                          const double *d_x64, void *d_y64, tspws_stream_t st);
 /* long_row0 > 0: scales with L >= f->f64_maxl read their traces from row long_row0 on (mean split) */
 int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
                               tspws_stream_t st);

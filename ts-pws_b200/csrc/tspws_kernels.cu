@@ -1069,18 +1069,17 @@ __device__ __forceinline__ void f64_short_item(const tspws_scale_t &sc, const ts
     }
 }
 
-__global__ void __launch_bounds__(256)
-fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restrict__ wall,
-               const tspws_fwd_item_t *__restrict__ items, int nitems, int nshort_cta,
-               const int2 *__restrict__ coefs, const double *__restrict__ x, int N,
-               double2 *__restrict__ out, int out_ld)
+/* body of one CTA of NT threads; bid = CTA index within the fp64 work list, xk / o = this trace */
+template <int NT>
+__device__ __forceinline__ void f64_cta_body(const tspws_scale_t *__restrict__ scales, const double2 *__restrict__ wall,
+                                             const tspws_fwd_item_t *__restrict__ items, int nitems, int nshort_cta,
+                                             const int2 *__restrict__ coefs, const double *__restrict__ xk, int N,
+                                             double2 *__restrict__ o, size_t split_stride, int bid, double (*sh)[2 * F64_R])
 {
-    __shared__ double sh[8][2 * F64_R];
-    const double *__restrict__ xk = x + (size_t)blockIdx.y * 3 * N;
-    double2 *__restrict__ o = out + (size_t)blockIdx.y * out_ld;
+    constexpr int NW = NT / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if ((int)blockIdx.x < nshort_cta) {
-        const int witem = blockIdx.x * 8 + warp;
+    if (bid < nshort_cta) {
+        const int witem = bid * NW + warp;
         if (witem >= nitems) return;
         const tspws_fwd_item_t it = items[witem];
         const tspws_scale_t sc = scales[it.s];
@@ -1095,10 +1094,10 @@ fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restri
         }
         return;
     }
-    const int2 cm = coefs[blockIdx.x - nshort_cta];        /* (scale | tap split << 16, first coefficient of the group) */
+    const int2 cm = coefs[bid - nshort_cta];               /* (scale | tap split << 16, first coefficient of the group) */
     const tspws_scale_t sc = scales[cm.x & 0xffff];
     const int q = cm.x >> 16, nsp = TSPWS_F64_NSPLIT(sc.L), Lq = (sc.L + nsp - 1) / nsp;
-    o += (size_t)q * gridDim.y * out_ld;
+    o += (size_t)q * split_stride;
     const int nr = min(F64_R, sc.Ns - cm.y);
     long long pll = ((long long)cm.y * sc.D - sc.c) % N;
     if (pll < 0) pll += N;
@@ -1108,7 +1107,7 @@ fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restri
     double ar[F64_R], ai[F64_R];
 #pragma unroll
     for (int r = 0; r < F64_R; r++) ar[r] = ai[r] = 0.0;
-    f64_taps<256, 256>(wall + sc.tap_off, xk + (int)pll, off, q * Lq + (int)threadIdx.x, min(sc.L, (q + 1) * Lq), ar, ai);
+    f64_taps<NT, NT>(wall + sc.tap_off, xk + (int)pll, off, q * Lq + (int)threadIdx.x, min(sc.L, (q + 1) * Lq), ar, ai);
 #pragma unroll
     for (int r = 0; r < F64_R; r++) { ar[r] = warp_sum(ar[r]); ai[r] = warp_sum(ai[r]); }
     if (lane == 0)
@@ -1118,11 +1117,60 @@ fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restri
     if (threadIdx.x < 2 * F64_R) {
         double t = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) t += sh[i][threadIdx.x];
+        for (int i = 0; i < NW; i++) t += sh[i][threadIdx.x];
         sh[0][threadIdx.x] = t;
     }
     __syncthreads();
     if ((int)threadIdx.x < nr) o[sc.coef_off + cm.y + threadIdx.x] = make_double2(sh[0][2 * threadIdx.x], sh[0][2 * threadIdx.x + 1]);
+}
+
+__global__ void __launch_bounds__(256)
+fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restrict__ wall,
+               const tspws_fwd_item_t *__restrict__ items, int nitems, int nshort_cta,
+               const int2 *__restrict__ coefs, const double *__restrict__ x, int N,
+               double2 *__restrict__ out, int out_ld)
+{
+    __shared__ double sh[8][2 * F64_R];
+    f64_cta_body<256>(scales, wall, items, nitems, nshort_cta, coefs, x + (size_t)blockIdx.y * 3 * N, N,
+                      out + (size_t)blockIdx.y * out_ld, (size_t)gridDim.y * out_ld, (int)blockIdx.x, sh);
+}
+
+/* Mean-split tail in ONE launch: the fp64 transform of the group mean (CTAs [0, nf64), one trace) and
+ * the fp32 per-trace transforms of the residuals (the rest: run of traces fastest, then item group).
+ * Launched separately the two kernels exclude each other -- either one fills the register files -- and
+ * their times add; in one grid their CTAs share the SMs and the issue slots. */
+__global__ void __launch_bounds__(FW_WARPS * 32, FW_PT_MINB)
+fwd_tail_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
+                const tspws_fwd2_item_t *__restrict__ items, int nitems,
+                const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len,
+                int smem_per_warp, int ntr, int long_L, int long_row0,
+                const double2 *__restrict__ w64, const tspws_fwd_item_t *__restrict__ items64, int nitems64, int nshort_cta,
+                const int2 *__restrict__ coefs64, int nf64, const double *__restrict__ x64, double2 *__restrict__ y64, int y64_ld)
+{
+    extern __shared__ float fw_smem[];
+    __shared__ double sh64[FW_WARPS][2 * F64_R];
+    if ((int)blockIdx.x < nf64) {
+        f64_cta_body<FW_WARPS * 32>(scales, w64, items64, nitems64, nshort_cta, coefs64, x64, N, y64, (size_t)y64_ld,
+                                    (int)blockIdx.x, sh64);
+        return;
+    }
+    const int b = blockIdx.x - nf64;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int idx = (b / ntr) * FW_WARPS + w;
+    if (idx >= nitems) return;
+    const tspws_fwd2_item_t it = items[idx];
+    const tspws_scale_t sc = scales[it.s];
+    const int k = b % ntr;
+    float *xs = fw_smem + (size_t)w * smem_per_warp;
+    if (sc.L >= long_L) x += (size_t)long_row0 * N;
+    switch (sc.lg) {
+    case 0: fwd2_body<0, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 1: fwd2_body<1, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 2: fwd2_body<2, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 3: fwd2_body<3, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    case 4: fwd2_body<4, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    default: fwd2_body<5, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
+    }
 }
 
 /* d_x: [ntr][3N] period-padded traces (see above) */
@@ -1183,6 +1231,27 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
     return 0;
 }
 
+/* fp64 transform of one period-padded trace d_x64 -> d_y64 [split][ncoef] together with the per-trace fp32
+ * transforms of ntr traces (see fwd_tail_kernel); only for frames fully covered by the polyphase kernel */
+extern "C" int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
+                                     const double *d_x64, void *d_y64, tspws_stream_t st)
+{
+    if (ntr <= 0 || !f->per_trace || !f->d_w64 || f->nitems2 <= 0 || f->nitems_gen > 0) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)st;
+    const size_t smem = (size_t)f->fw_smem_per_warp * FW_WARPS * sizeof(float);
+    if (smem > 40 * 1024)
+        cudaFuncSetAttribute(fwd_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int cpt = (f->nitems2 + FW_WARPS - 1) / FW_WARPS;
+    const int nshort_cta = (f->nitems_short + FW_WARPS - 1) / FW_WARPS;
+    const int nf64 = nshort_cta + f->nlong;
+    fwd_tail_kernel<<<nf64 + ntr * cpt, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, f->d_items2, f->nitems2,
+        d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp, ntr, long_row0 > 0 ? f->f64_maxl : 0x7fffffff, long_row0,
+        (const double2 *)f->d_w64, f->d_items_short, f->nitems_short, nshort_cta, (const int2 *)f->d_long, nf64, d_x64,
+        (double2 *)d_y64, f->ncoef);
+    TSPWS_LAUNCHED_N("fwd_tail_kernel", s);
+    return 0;
+}
+
 extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
                                          tspws_stream_t st)
 {
@@ -1232,7 +1301,7 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
     __shared__ double s_s[4][PC_TILE][2];
     /* tile = (offset in a trace's partial-Y block, offset in the coefficient arrays, valid
      * coefficients | nsplit << 8, Ns = stride between phase splits) */
-    const int4 tile = tiles[blockIdx.x];
+    const int4 tile = tiles[gridDim.x - 1 - blockIdx.x];   /* coarsest scales (most splits per coefficient) first */
     const int ci = threadIdx.x & (PC_TILE - 1), slot = threadIdx.x / PC_TILE;
     const int nvalid = tile.z & 255, nsplit = (tile.z >> 8) & 255, nsp64 = tile.z >> 16, Ns = tile.w;
     const int sg = blockIdx.y;

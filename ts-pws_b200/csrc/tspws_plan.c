@@ -717,6 +717,11 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
         }
         if (stop == 2) return 0;
         if (pl->dev.per_trace) {
+            const int long_row0 = pl->mean_split && pl->hybrid ? pl->ntr_fwd : 0;
+            if (pl->mean_split && pl->dev.nitems_gen == 0 && pl->dev.nitems2 > 0 && env_long("TSPWS_FUSED_TAIL", 1)) {
+                /* one launch: fp64 transform of the group mean + fp32 transforms of the residuals */
+                if ((e = tspws_cu_forward_tail(&pl->dev, pl->d_gsum32, pl->ntr_fwd, long_row0, pl->d_ypart, pl->d_gmean, pl->d_ymean, stream))) return TSPWS_ERR_CUDA;
+            } else {
             /* fork: fp64 transform of the group mean on the side stream, fp32 transforms of the residuals here */
             cudaStream_t A = (cudaStream_t)stream;
             cudaStream_t B = (pl->side && !tspws_cu_profile_enabled() && pl->side != A) ? pl->side : A;
@@ -724,10 +729,10 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
                 if (B != A && (cudaEventRecord(pl->ev_fork, A) != cudaSuccess || cudaStreamWaitEvent(B, pl->ev_fork, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
                 if ((e = tspws_cu_forward_f64(&pl->dev, pl->d_gmean, 1, pl->d_ymean, B))) return TSPWS_ERR_CUDA;
             }
-            /* with the mean split, rows K..2K-1 of d_gsum32 are the unsplit group sums (for the long filters) */
-            if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, pl->mean_split && pl->hybrid ? pl->ntr_fwd : 0, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_forward_pertrace(&pl->dev, pl->d_gsum32, pl->ntr_fwd, long_row0, pl->d_ypart, stream))) return TSPWS_ERR_CUDA;
             if (pl->mean_split && B != A &&
                 (cudaEventRecord(pl->ev_join, B) != cudaSuccess || cudaStreamWaitEvent(A, pl->ev_join, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
+            }
             if (stop == 3) return 0;
             if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, pl->mean_split ? pl->d_ymean : NULL,
                                              plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
