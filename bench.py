@@ -246,7 +246,23 @@ def run_ours(args, wl, name):
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
     exch = None
-    if world > 1:
+    peer = False
+    if world > 1 and two_stage and not os.environ.get("TSPWS_BENCH_NCCL"):
+        # peer exchange: every rank maps the others' exchange blocks (CUDA IPC) and the sum over ranks is
+        # fused into the first tail kernel (NVLink loads) -- no collective call in the step
+        h = (C.c_ubyte * 64)()
+        ok = lib.tspws_b200_plan_peer_export(plan, h) == 0
+        mine = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        buf = (C.c_ubyte * (64 * world))(*torch.cat(allh).cpu().tolist())
+        ok = ok and lib.tspws_b200_plan_peer_import(plan, rank, world, buf) == 0
+        okt = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        if int(okt[0]) == 0:
+            raise SystemExit("peer exchange set-up failed (set TSPWS_BENCH_NCCL=1 for the NCCL all-reduce path)")
+        peer = True
+    if world > 1 and not peer:
         nbytes = lib.tspws_b200_plan_exchange_bytes(plan)
         is64 = lib.tspws_b200_plan_exchange_is_f64(plan)
         dt = torch.float64 if is64 else torch.float32
@@ -254,7 +270,7 @@ def run_ours(args, wl, name):
         assert lib.tspws_b200_plan_bind_exchange(plan, exch.data_ptr()) == 0
 
     def step():
-        if world == 1:
+        if world == 1 or peer:
             rc = lib.tspws_b200_plan_stack(plan, d_x.data_ptr(), d_ls.data_ptr(), d_ts.data_ptr(), stream)
         else:
             rc = lib.tspws_b200_plan_reduce(plan, d_x.data_ptr(), stream)
@@ -269,8 +285,8 @@ def run_ours(args, wl, name):
     step_graph = None
     def capture_step():
         nonlocal step_graph
-        if world == 1 or os.environ.get("TSPWS_BENCH_NO_GRAPH"):
-            return
+        if world == 1 or peer or os.environ.get("TSPWS_BENCH_NO_GRAPH"):
+            return                                      # plan_stack replays its own graph
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
@@ -296,7 +312,7 @@ def run_ours(args, wl, name):
         step()
     barrier()
     capture_step()
-    ok = torch.tensor([1 if (world == 1 or step_graph is not None) else 0], device="cuda")
+    ok = torch.tensor([1 if (world == 1 or peer or step_graph is not None) else 0], device="cuda")
     if world > 1:
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks replay the graph, or none does
         if int(ok[0]) == 0:
@@ -384,7 +400,8 @@ def run_ours(args, wl, name):
         e2e = {"value": total_samples / float(te[0]), "unit": "trace-samples/s",
                "h2d_bytes_per_step": int(mtr) * n * 4 * world, "d2h_bytes_per_step": 2 * n * 4 * world,
                "ms_per_step": float(te[0]) * 1e3, "steps": e_steps,
-               "api": "tspws_b200_plan_reduce / all-reduce / tspws_b200_plan_finish with pinned host shards"}
+               "api": "tspws_b200_plan_stack (peer exchange) with pinned host shards" if peer else
+                      "tspws_b200_plan_reduce / all-reduce / tspws_b200_plan_finish with pinned host shards"}
     else:
         out, dat = B.TsPWSOut(), B.Data()
         ls_h = torch.empty(n, dtype=torch.float32).pin_memory()
@@ -411,19 +428,26 @@ def run_ours(args, wl, name):
         e2e["max_abs_diff_vs_device_path"] = float(np.max(np.abs(ts_h.numpy() - d_ts.cpu().numpy())))
 
     clocks = sampler.finish() if sampler else None      # sampled over the timed region and the e2e loop
+    if peer and lib.tspws_b200_plan_peer_error(plan):
+        raise SystemExit(f"rank {rank}: a peer wait timed out -- the measurement is invalid")
 
     def teardown():
         nonlocal step_graph
         step_graph = None                               # the captured step holds NCCL work: drop it first
         torch.cuda.synchronize()
-        lib.tspws_b200_plan_destroy(plan)
+        t = None
         if world > 1:
-            # never let process-group teardown outlive the measurement: the JSON line is already out
+            # never let teardown outlive the measurement: the JSON line is already out
             t = threading.Timer(30.0, lambda: os._exit(0))
             t.daemon = True
             t.start()
             try:
-                dist.barrier()
+                dist.barrier()                          # nobody unmaps its exchange block while a peer may read it
+            except Exception:                           # noqa: BLE001
+                pass
+        lib.tspws_b200_plan_destroy(plan)
+        if world > 1:
+            try:
                 dist.destroy_process_group()
             except Exception:                           # noqa: BLE001
                 pass
@@ -485,11 +509,13 @@ def run_ours(args, wl, name):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": name, "desc": wl["desc"], "traces_per_gpu": mtr, "samples": n,
-                   "scales": int(p.J * p.V), "parallelism": f"traces sharded x{world}, NCCL all-reduce of the "
+                   "scales": int(p.J * p.V), "parallelism": f"traces sharded x{world}, {'peer-memory sum' if peer else 'NCCL all-reduce'} of the "
                    f"{'group sums' if two_stage else 'phasor/linear sums'}" if world > 1 else "single GPU",
                    "l2_note": "per-step input 512 MiB per GPU > 126 MB L2 (no flush needed)",
                    "ms_per_step_with_kernel_events": ms / args.steps,
-                   "step_replayed_as_cuda_graph": bool(world == 1 or step_graph is not None)},
+                   "step_replayed_as_cuda_graph": bool(world == 1 or peer or step_graph is not None),
+                   "exchange": ("none" if world == 1 else "peer memory over NVLink, fused into group_post2_kernel" if peer
+                                else "NCCL all-reduce")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     emit(line)

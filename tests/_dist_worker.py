@@ -107,6 +107,29 @@ def nccl_plan():
         e_c = O.nerr(np.hypot(ps[0::2], ps[1::2]) / lib.tspws_b200_plan_K(plan), o["coherence"])
         assert e_ts <= 1e-4 and e_ls <= 1e-4 and e_c <= 1e-5, (rank, kw, e_ts, e_ls, e_c)
         lib.tspws_b200_plan_destroy(plan)
+        if not p.Kmax:
+            continue
+        # ---- the same stack with the peer exchange (CUDA IPC mappings, sum over ranks fused into the
+        # first kernel of plan_finish) instead of the NCCL all-reduce: same result to fp64 rounding ----
+        ref_ts, ref_ls = ts.clone(), ls.clone()
+        plan = lib.tspws_b200_plan_create(C.byref(p), n, hi - lo, mtr, lo)
+        h = (C.c_ubyte * 64)()
+        assert lib.tspws_b200_plan_peer_export(plan, h) == 0
+        mine = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        buf = (C.c_ubyte * (64 * world))(*torch.cat(allh).cpu().tolist())
+        assert lib.tspws_b200_plan_peer_import(plan, rank, world, buf) == 0
+        side = torch.cuda.Stream()
+        dist.barrier()
+        for it in range(3):                                          # step parity, re-arming, graph replay
+            assert lib.tspws_b200_plan_stack(plan, dx.data_ptr(), ls.data_ptr(), ts.data_ptr(), side.cuda_stream) == 0
+            side.synchronize()
+            assert lib.tspws_b200_plan_peer_error(plan) == 0
+            d_ts, d_ls = O.nerr(ts.cpu().numpy(), ref_ts.cpu().numpy()), O.nerr(ls.cpu().numpy(), ref_ls.cpu().numpy())
+            assert d_ts <= 1e-6 and d_ls <= 1e-6, (rank, kw, it, d_ts, d_ls)
+        dist.barrier()                                               # nobody unmaps while a peer still reads
+        lib.tspws_b200_plan_destroy(plan)
     dist.barrier()
     if rank == 0:
         print("NCCL_PLAN_OK")

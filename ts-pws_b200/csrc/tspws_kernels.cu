@@ -371,27 +371,86 @@ extern "C" int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts, in
  *           sharded plan; mean removal etc. follow the all-reduce, in a mode-1 launch over the block)
  *   mode 1  full: mean removal (from the slot totals), fold, mean split, fp32 copy / residuals    */
 #define GP2_LANES 8
+/* PEER = true: the "slots" of group k are the exchange blocks of all ranks of the node, read in rank
+ * order straight from the peers' memory (NVLink / NVSwitch loads through CUDA IPC mappings): the
+ * cross-GPU sum of the group sums is fused into this kernel instead of an all-reduce before it.
+ * Every rank publishes its block (mode 0 launch), then peer_signal_kernel stores the step number into
+ * every peer's flag word; here one thread per CTA waits until all ranks have reached this step.
+ * Blocks are double-buffered by step parity, so a rank that runs ahead never overwrites a block that a
+ * slower rank still reads (it cannot pass its next wait before the slower rank has published). */
+struct tspws_peer_args {
+    const double *const *blocks;     /* [world] base of every rank's region: 2 blocks of block_len doubles */
+    const unsigned int  *flags;      /* [world] own flag words, written by the peers */
+    unsigned int        *step;       /* own step counter (advanced by peer_signal_kernel) */
+    unsigned int        *err;        /* set when a wait timed out */
+    int world;
+    long long block_len;             /* doubles per block = K*N + K*ntile */
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+/* peer memory is written by other GPUs between steps: system-scope loads, never a stale cached line */
+__device__ __forceinline__ double ld_sys_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool PEER>
 __global__ void __launch_bounds__(32 * GP2_LANES)
 group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ slot_tot, const int *__restrict__ slot_off,
                    int N, int K, int ntile, int mode, int do_rm, int do_fold, int split,
-                   double *__restrict__ gsum, double *__restrict__ gtile, float *__restrict__ out32, double *__restrict__ gmean)
+                   double *__restrict__ gsum, double *__restrict__ gtile, float *__restrict__ out32, double *__restrict__ gmean,
+                   const tspws_peer_args pa)
 {
     extern __shared__ double s_c[];                      /* [K] group-mean corrections */
     __shared__ double s_m[GP2_LANES][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    size_t par_off = 0;
+    if (PEER) {
+        const unsigned int step = *pa.step;              /* already advanced for this step */
+        par_off = (size_t)((step - 1) & 1) * (size_t)pa.block_len;
+        if (threadIdx.x < pa.world) {
+            long long spins = 0;
+            while (ld_acquire_sys(pa.flags + threadIdx.x) < step) {
+                __nanosleep(200);
+                if (++spins > 20000000LL) { *pa.err = 1; break; }      /* ~4 s: a rank is gone; never hang the GPU */
+            }
+        }
+        __syncthreads();
+    } else if (mode == 0 && pa.step) {
+        /* publishing launch of a peer plan: write into the block of this step's parity */
+        const size_t o = (size_t)(*pa.step & 1) * (size_t)pa.block_len;
+        gsum += o; gtile += o;
+    }
+    /* slot j of group k: value at sample n, total of tile t */
+    auto cnt = [&](int k) { return PEER ? pa.world : slot_off[k + 1] - slot_off[k]; };
+    auto sval = [&](int k, int j, int n) {
+        return PEER ? ld_sys_f64(pa.blocks[j] + par_off + (size_t)k * N + n) : __ldcg(slots + (size_t)(slot_off[k] + j) * N + n);
+    };
+    auto tval = [&](int k, int j, int t) {
+        return PEER ? ld_sys_f64(pa.blocks[j] + par_off + (size_t)K * N + (size_t)k * ntile + t)
+                    : slot_tot[(size_t)(slot_off[k] + j) * ntile + t];
+    };
     if (mode == 0 ? blockIdx.x == 0 : do_rm) {
         /* totals of every group: lanes stride over (slot, tile) in a fixed pattern, fixed shuffle tree */
         for (int k = w; k < K; k += GP2_LANES) {
-            const int s0 = slot_off[k], s1 = slot_off[k + 1];
+            const int c_k = cnt(k);
             if (mode == 0) {
                 for (int t = lane; t < ntile; t += 32) {
                     double c = 0.0;
-                    for (int sl = s0; sl < s1; sl++) c += slot_tot[(size_t)sl * ntile + t];
+                    for (int j = 0; j < c_k; j++) c += tval(k, j, t);
                     gtile[(size_t)k * ntile + t] = c;
                 }
             } else {
                 double c = 0.0;
-                for (int i = s0 * ntile + lane; i < s1 * ntile; i += 32) c += slot_tot[i];
+                for (int i = lane; i < c_k * ntile; i += 32) c += tval(k, i / ntile, i % ntile);
                 c = warp_sum(c);
                 if (lane == 0) s_c[k] = c / (double)(unsigned int)N;
             }
@@ -403,14 +462,14 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     const int r = N - 1 - n;
     double acc = 0.0;
     for (int k = w; k < K; k += GP2_LANES) {
-        const int s0 = slot_off[k], s1 = slot_off[k + 1];
+        const int c_k = cnt(k);
         double v = 0.0, vr = 0.0;
         if (ok) {
 #pragma unroll 4
-            for (int sl = s0; sl < s1; sl++) v += __ldcg(slots + (size_t)sl * N + n);
+            for (int j = 0; j < c_k; j++) v += sval(k, j, n);
             if (mode == 1 && do_fold) {
 #pragma unroll 4
-                for (int sl = s0; sl < s1; sl++) vr += __ldcg(slots + (size_t)sl * N + r);
+                for (int j = 0; j < c_k; j++) vr += sval(k, j, r);
                 v = 0.5 * (v + vr);                        /* the constant correction is fold-invariant */
             }
             if (mode == 1 && do_rm) v -= s_c[k];
@@ -436,14 +495,57 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     }
 }
 
+/* after the publishing launch: advance the own step counter and store it into every peer's flag word */
+__global__ void peer_signal_kernel(unsigned int *step, unsigned int *const *peer_flags, int rank, int world)
+{
+    __shared__ unsigned int s;
+    if (threadIdx.x == 0) s = *step + 1;
+    __syncthreads();
+    __threadfence_system();                              /* the block published by the previous kernel first */
+    if ((int)threadIdx.x < world)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[threadIdx.x] + rank), "r"(s) : "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) *step = s;
+}
+
+extern "C" int tspws_cu_peer_signal(unsigned int *d_step, void *d_peer_flags, int rank, int world, tspws_stream_t st)
+{
+    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)st>>>(d_step, (unsigned int *const *)d_peer_flags, rank, world);
+    TSPWS_LAUNCHED_N("peer_signal_kernel", (cudaStream_t)st);
+    return 0;
+}
+
+/* peer variants of the two group_post2 launches: publish (mode 0 into the parity block) and fused sum over ranks */
+extern "C" int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
+                                         int ntile, int do_rm, int do_fold, int split, double *d_gsum, double *d_gtile,
+                                         float *d_out32, double *d_gmean, const void *d_peer_blocks, const unsigned int *d_flags,
+                                         unsigned int *d_step, unsigned int *d_err, int world, tspws_stream_t st)
+{
+    const size_t smem = (size_t)K * sizeof(double);
+    if (smem > 40 * 1024 || world > 32 * GP2_LANES) return (int)cudaErrorInvalidValue;
+    tspws_peer_args pa;
+    pa.blocks = (const double *const *)d_peer_blocks; pa.flags = d_flags; pa.step = d_step; pa.err = d_err;
+    pa.world = world; pa.block_len = (long long)K * N + (long long)K * ntile;
+    if (publish)
+        group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
+            0, 0, 0, 0, d_gsum, d_gtile, nullptr, nullptr, pa);
+    else
+        group_post2_kernel<true><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(nullptr, nullptr, nullptr, N, K, ntile,
+            1, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean, pa);
+    TSPWS_LAUNCHED_N(publish ? "group_post2_kernel" : "group_post2_peer_kernel", (cudaStream_t)st);
+    return 0;
+}
+
 extern "C" int tspws_cu_group_post2(const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
                                     int ntile, int mode, int do_rm, int do_fold, int split, double *d_gsum, double *d_gtile,
                                     float *d_out32, double *d_gmean, tspws_stream_t st)
 {
     const size_t smem = (size_t)K * sizeof(double);
     if (smem > 40 * 1024) return (int)cudaErrorInvalidValue;
-    group_post2_kernel<<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
-                                                                                  mode, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean);
+    tspws_peer_args pa;
+    memset(&pa, 0, sizeof pa);
+    group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
+                                                                                         mode, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean, pa);
     TSPWS_LAUNCHED_N("group_post2_kernel", (cudaStream_t)st);
     return 0;
 }

@@ -69,7 +69,17 @@ struct tspws_plan {
     void        *d_ymean;           /* double2 [TSPWS_F64_MAXSPLIT][ncoef] */
     int         *h_slot_off;        /* [K+1] first work item of every group */
     void  *own_gsum, *own_exch;
+    /* peer exchange over CUDA IPC (two-stage, sharded): see tspws_b200_plan_peer_export / _import */
+    int           peer_on, peer_rank, peer_world, peer_pending;
+    void         *d_peer_region;    /* own: 2 exchange blocks (step parity) + flag words + error word */
+    size_t        peer_flag_off, peer_bytes;
+    void        **h_peer_ptr;       /* [world] mapped regions (own entry = d_peer_region) */
+    void         *d_peer_blocks;    /* device array [world] of const double * */
+    void         *d_peer_flags;     /* device array [world] of unsigned int * (every rank's flag words) */
+    unsigned int *d_peer_step;
 };
+
+#define TSPWS_PEER_MAXW 64          /* flag words per rank region (ranks of one node) */
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fprintf(stderr, "tspws_b200: CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
@@ -541,6 +551,12 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     cudaFree(pl->d_gmean); cudaFree(pl->d_ymean);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
+    if (pl->h_peer_ptr) {
+        for (int r = 0; r < pl->peer_world; r++)
+            if (r != pl->peer_rank && pl->h_peer_ptr[r]) cudaIpcCloseMemHandle(pl->h_peer_ptr[r]);
+        free(pl->h_peer_ptr);
+    }
+    cudaFree(pl->d_peer_region); cudaFree(pl->d_peer_blocks); cudaFree(pl->d_peer_flags); cudaFree(pl->d_peer_step);
     cudaFree(pl->d_gfin); cudaFree(pl->d_ident);
     cudaFree(pl->d_cs2_parts); cudaFree(pl->d_cs2_slot_off); cudaFree(pl->d_cs2_slots); cudaFree(pl->d_cs2_tot);
     cudaFree(pl->d_rule); cudaFree(pl->d_cs); cudaFree(pl->d_slot_off); cudaFree(pl->d_grp_t0);
@@ -630,10 +646,21 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     pl->summed_across_ranks = 0;
     tspws_cu_profile_mark(stream);
     pl->cs2_pending = 0;
+    pl->peer_pending = 0;
+    if (pl->peer_on && ((size_t)d_sigall & 15)) return TSPWS_ERR_ARG;    /* peers would wait for a block that never comes */
     if (pl->two_stage && pl->cs2 && !((size_t)d_sigall & 15)) {
         if ((e = tspws_cu_colsum2(d_sigall, pl->N, pl->d_cs2_parts, pl->cs2_nparts, pl->d_grp_t0, pl->d_cs2_slots,
                                   pl->d_cs2_tot, pl->ntile, stream))) return TSPWS_ERR_CUDA;
-        if (pl->mtr_local != pl->mtr_total || pl->exch_bound) {
+        if (pl->peer_on) {
+            /* publish this rank's block (parity of the step) and tell every peer */
+            double *blk = (double *)pl->d_peer_region;
+            unsigned int *flags = (unsigned int *)((char *)pl->d_peer_region + pl->peer_flag_off);
+            if ((e = tspws_cu_group_post2_peer(1, pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
+                                               0, 0, 0, blk, blk + (size_t)pl->K * pl->N, NULL, NULL, pl->d_peer_blocks, flags,
+                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_peer_signal(pl->d_peer_step, pl->d_peer_flags, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+            pl->peer_pending = 1;
+        } else if (pl->mtr_local != pl->mtr_total || pl->exch_bound) {
             /* sharded: the exchange block (group sums + tile totals) has to be complete before the all-reduce */
             if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
                                           0, 0, 0, 0, pl->d_gsum, pl->d_gtile, NULL, NULL, stream))) return TSPWS_ERR_CUDA;
@@ -694,6 +721,66 @@ size_t tspws_b200_plan_exchange_bytes(tspws_plan_t *pl)
 }
 int tspws_b200_plan_exchange_is_f64(tspws_plan_t *pl) { return pl && pl->two_stage; }
 
+/* ---- peer exchange: the ranks of one node map each other's exchange blocks (CUDA IPC) and the sum over
+ * ranks is read straight from peer memory inside group_post2_kernel<true>; no collective call ---- */
+int tspws_b200_plan_peer_export(tspws_plan_t *pl, void *handle64)
+{
+    if (!pl || !handle64) return TSPWS_ERR_NULL;
+    if (!pl->two_stage || !pl->cs2 || sizeof(cudaIpcMemHandle_t) != 64) return TSPWS_ERR_ARG;
+    if (!pl->d_peer_region) {
+        const size_t blk = tspws_b200_plan_exchange_bytes(pl);
+        pl->peer_flag_off = (2 * blk + 255) & ~(size_t)255;
+        pl->peer_bytes = pl->peer_flag_off + (TSPWS_PEER_MAXW + 1) * sizeof(unsigned int);
+        if (cudaMalloc(&pl->d_peer_region, pl->peer_bytes) != cudaSuccess ||
+            cudaMemset(pl->d_peer_region, 0, pl->peer_bytes) != cudaSuccess ||
+            cudaMalloc((void **)&pl->d_peer_step, sizeof(unsigned int)) != cudaSuccess ||
+            cudaMemset(pl->d_peer_step, 0, sizeof(unsigned int)) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return TSPWS_ERR_ALLOC; }
+    }
+    if (cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, pl->d_peer_region) != cudaSuccess) { cudaGetLastError(); return TSPWS_ERR_CUDA; }
+    return 0;
+}
+
+int tspws_b200_plan_peer_import(tspws_plan_t *pl, int rank, int world, const void *handles)
+{
+    if (!pl || !handles) return TSPWS_ERR_NULL;
+    if (!pl->d_peer_region || world < 1 || world > TSPWS_PEER_MAXW || rank < 0 || rank >= world || pl->h_peer_ptr) return TSPWS_ERR_ARG;
+    void **ptr = (void **)calloc(world, sizeof(void *));
+    void **blocks = (void **)calloc(world, sizeof(void *)), **flags = (void **)calloc(world, sizeof(void *));
+    int rc = TSPWS_ERR_CUDA;
+    if (!ptr || !blocks || !flags) { rc = TSPWS_ERR_ALLOC; goto out; }
+    for (int r = 0; r < world; r++) {
+        if (r == rank) ptr[r] = pl->d_peer_region;
+        else if (cudaIpcOpenMemHandle(&ptr[r], ((const cudaIpcMemHandle_t *)handles)[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            fprintf(stderr, "tspws_b200: cannot map the exchange block of rank %d (%s)\n", r, cudaGetErrorString(cudaGetLastError()));
+            goto out;
+        }
+        blocks[r] = ptr[r];
+        flags[r]  = (char *)ptr[r] + pl->peer_flag_off;
+    }
+    if (cudaMalloc(&pl->d_peer_blocks, world * sizeof(void *)) != cudaSuccess ||
+        cudaMalloc(&pl->d_peer_flags, world * sizeof(void *)) != cudaSuccess ||
+        cudaMemcpy(pl->d_peer_blocks, blocks, world * sizeof(void *), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(pl->d_peer_flags, flags, world * sizeof(void *), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); goto out; }
+    pl->h_peer_ptr = ptr; ptr = NULL;
+    pl->peer_rank = rank; pl->peer_world = world; pl->peer_on = 1;
+    if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
+    rc = 0;
+out:
+    free(ptr); free(blocks); free(flags);
+    return rc;
+}
+
+/* 1 if a peer wait timed out since the plan was created (a rank died or never arrived) */
+int tspws_b200_plan_peer_error(tspws_plan_t *pl)
+{
+    if (!pl || !pl->d_peer_region) return 0;
+    unsigned int e = 0;
+    if (cudaMemcpy(&e, (char *)pl->d_peer_region + pl->peer_flag_off + TSPWS_PEER_MAXW * sizeof(unsigned int), sizeof e,
+                   cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return 1; }
+    return e != 0;
+}
+
 int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *stream)
 {
     if (!pl || !d_ls || !d_tspws) return TSPWS_ERR_NULL;
@@ -705,7 +792,15 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
         /* post-processed fp64 group sums: from the slots of colsum2 (unsharded), or from the exchange block
          * (sharded / bound / N % 4 != 0) seen as one slot per group, written to a separate buffer */
         const double *gfin = pl->d_gsum;
-        if (pl->cs2_pending) {
+        if (pl->peer_pending) {
+            /* the sum over ranks is fused in: every rank's block is read over NVLink in rank order */
+            unsigned int *flags = (unsigned int *)((char *)pl->d_peer_region + pl->peer_flag_off);
+            if ((e = tspws_cu_group_post2_peer(0, NULL, NULL, NULL, pl->N, (int)pl->K, pl->ntile, pl->p.lrm, pl->p.fold,
+                                               pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gfin, NULL, pl->d_gsum32,
+                                               pl->mean_split ? pl->d_gmean : NULL, pl->d_peer_blocks, flags, pl->d_peer_step,
+                                               flags + TSPWS_PEER_MAXW, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+            gfin = pl->d_gfin;
+        } else if (pl->cs2_pending) {
             if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
                                           1, pl->p.lrm, pl->p.fold, pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gsum, pl->d_gtile, pl->d_gsum32,
                                           pl->mean_split ? pl->d_gmean : NULL, stream))) return TSPWS_ERR_CUDA;
