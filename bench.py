@@ -251,7 +251,7 @@ def run_ours(args, wl, name):
         # peer exchange: every rank maps the others' exchange blocks (CUDA IPC) and the sum over ranks is
         # fused into the first tail kernel (NVLink loads) -- no collective call in the step
         h = (C.c_ubyte * 64)()
-        ok = lib.tspws_b200_plan_peer_export(plan, h) == 0
+        ok = lib.tspws_b200_plan_peer_export(plan, world, h) == 0
         mine = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)

@@ -241,11 +241,11 @@ int    tspws_b200_plan_mark_exchanged(tspws_plan_t *plan);
 /* Peer exchange instead of a collective (two-stage plans, ranks of ONE node, one process per GPU): every
  * rank exports the CUDA IPC handle (64 bytes) of its exchange region, the handles are gathered by any
  * means (bench.py: torch.distributed.all_gather) and imported; from then on plan_reduce publishes the rank's
- * block and plan_finish sums the blocks of all ranks straight from peer memory (NVLink / NVSwitch loads)
- * inside its first kernel -- no all-reduce call, no plan_mark_exchanged, and tspws_b200_plan_stack replays
- * the whole multi-GPU step as one CUDA graph.  Ranks must call the same sequence of steps.
+ * block into every rank's region (stores over NVLink / NVSwitch) and plan_finish sums the blocks of all
+ * ranks inside its first kernel -- no all-reduce call, no plan_mark_exchanged, and tspws_b200_plan_stack
+ * replays the whole multi-GPU step as one CUDA graph.  Ranks must call the same sequence of steps.
  * plan_peer_error: 1 if a wait for a peer ever timed out (~4 s; the step's result is then invalid). */
-int tspws_b200_plan_peer_export(tspws_plan_t *plan, void *handle64);
+int tspws_b200_plan_peer_export(tspws_plan_t *plan, int world, void *handle64);
 int tspws_b200_plan_peer_import(tspws_plan_t *plan, int rank, int world, const void *handles /* world x 64 bytes */);
 int tspws_b200_plan_peer_error(tspws_plan_t *plan);
 int tspws_b200_plan_finish(tspws_plan_t *plan, float *d_ls, float *d_tspws, void *stream);

@@ -114,7 +114,7 @@ def nccl_plan():
         ref_ts, ref_ls = ts.clone(), ls.clone()
         plan = lib.tspws_b200_plan_create(C.byref(p), n, hi - lo, mtr, lo)
         h = (C.c_ubyte * 64)()
-        assert lib.tspws_b200_plan_peer_export(plan, h) == 0
+        assert lib.tspws_b200_plan_peer_export(plan, world, h) == 0
         mine = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)

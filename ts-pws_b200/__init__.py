@@ -170,7 +170,7 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_plan_mark_exchanged.restype = C.c_int
     lib.tspws_b200_plan_mark_exchanged.argtypes = [C.c_void_p]
     lib.tspws_b200_plan_peer_export.restype = C.c_int
-    lib.tspws_b200_plan_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.tspws_b200_plan_peer_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.tspws_b200_plan_peer_import.restype = C.c_int
     lib.tspws_b200_plan_peer_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.tspws_b200_plan_peer_error.restype = C.c_int

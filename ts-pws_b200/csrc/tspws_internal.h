@@ -168,9 +168,9 @@ int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, 
 /* peer exchange (CUDA IPC mappings of the other ranks' exchange blocks), see group_post2_kernel<true> */
 int tspws_cu_peer_signal(unsigned int *d_step, void *d_peer_flags, int rank, int world, tspws_stream_t st);
 int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
-                              int ntile, int do_rm, int do_fold, int split, double *d_gsum, double *d_gtile,
-                              float *d_out32, double *d_gmean, const void *d_peer_blocks, const unsigned int *d_flags,
-                              unsigned int *d_step, unsigned int *d_err, int world, tspws_stream_t st);
+                              int ntile, int do_rm, int do_fold, int split, double *d_gsum,
+                              float *d_out32, double *d_gmean, void *d_regions, double *d_own, const unsigned int *d_flags,
+                              unsigned int *d_step, unsigned int *d_err, int rank, int world, tspws_stream_t st);
 int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
                           const double *d_x64, void *d_y64, tspws_stream_t st);
 /* long_row0 > 0: scales with L >= f->f64_maxl read their traces from row long_row0 on (mean split) */

@@ -371,19 +371,23 @@ extern "C" int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts, in
  *           sharded plan; mean removal etc. follow the all-reduce, in a mode-1 launch over the block)
  *   mode 1  full: mean removal (from the slot totals), fold, mean split, fp32 copy / residuals    */
 #define GP2_LANES 8
-/* PEER = true: the "slots" of group k are the exchange blocks of all ranks of the node, read in rank
- * order straight from the peers' memory (NVLink / NVSwitch loads through CUDA IPC mappings): the
- * cross-GPU sum of the group sums is fused into this kernel instead of an all-reduce before it.
- * Every rank publishes its block (mode 0 launch), then peer_signal_kernel stores the step number into
- * every peer's flag word; here one thread per CTA waits until all ranks have reached this step.
+/* Peer exchange (one process per GPU, ranks of one node, regions mapped with CUDA IPC): the cross-GPU sum
+ * of the group sums is fused into the two group_post2 launches instead of an all-reduce between them.
+ *   publish (mode 0 with peer args): the rank's block (group sums + tile totals of its shard) is PUSHED
+ *       into slot [parity][rank] of every rank's region with plain stores over NVLink / NVSwitch (remote
+ *       stores pipeline; remote loads measured 10x slower at 8 GPUs: 124 us for 9 MB);
+ *   peer_signal_kernel: system fence, then the step number into every rank's flag word;
+ *   PEER = true launch: waits until the flags of all ranks have reached this step, then treats the world
+ *       blocks of its OWN region as the slots of every group (rank order: deterministic).
  * Blocks are double-buffered by step parity, so a rank that runs ahead never overwrites a block that a
- * slower rank still reads (it cannot pass its next wait before the slower rank has published). */
+ * slower rank still reads (it cannot pass its next wait before the slower rank has signalled). */
 struct tspws_peer_args {
-    const double *const *blocks;     /* [world] base of every rank's region: 2 blocks of block_len doubles */
+    double *const *regions;          /* [world] base of every rank's region: [2][world][block_len] doubles */
+    double              *own;        /* base of the own region */
     const unsigned int  *flags;      /* [world] own flag words, written by the peers */
     unsigned int        *step;       /* own step counter (advanced by peer_signal_kernel) */
     unsigned int        *err;        /* set when a wait timed out */
-    int world;
+    int world, rank;
     long long block_len;             /* doubles per block = K*N + K*ntile */
 };
 
@@ -412,10 +416,10 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     extern __shared__ double s_c[];                      /* [K] group-mean corrections */
     __shared__ double s_m[GP2_LANES][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    size_t par_off = 0;
+    size_t par_off = 0;                                  /* first block of this step's parity */
     if (PEER) {
         const unsigned int step = *pa.step;              /* already advanced for this step */
-        par_off = (size_t)((step - 1) & 1) * (size_t)pa.block_len;
+        par_off = (size_t)((step - 1) & 1) * (size_t)pa.world * (size_t)pa.block_len;
         if (threadIdx.x < pa.world) {
             long long spins = 0;
             while (ld_acquire_sys(pa.flags + threadIdx.x) < step) {
@@ -425,17 +429,18 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
         }
         __syncthreads();
     } else if (mode == 0 && pa.step) {
-        /* publishing launch of a peer plan: write into the block of this step's parity */
-        const size_t o = (size_t)(*pa.step & 1) * (size_t)pa.block_len;
-        gsum += o; gtile += o;
+        /* publishing launch of a peer plan: slot [parity][rank] of every region */
+        par_off = ((size_t)(*pa.step & 1) * (size_t)pa.world + (size_t)pa.rank) * (size_t)pa.block_len;
     }
+    const bool push = !PEER && mode == 0 && pa.step;
     /* slot j of group k: value at sample n, total of tile t */
     auto cnt = [&](int k) { return PEER ? pa.world : slot_off[k + 1] - slot_off[k]; };
     auto sval = [&](int k, int j, int n) {
-        return PEER ? ld_sys_f64(pa.blocks[j] + par_off + (size_t)k * N + n) : __ldcg(slots + (size_t)(slot_off[k] + j) * N + n);
+        return PEER ? ld_sys_f64(pa.own + par_off + (size_t)j * pa.block_len + (size_t)k * N + n)
+                    : __ldcg(slots + (size_t)(slot_off[k] + j) * N + n);
     };
     auto tval = [&](int k, int j, int t) {
-        return PEER ? ld_sys_f64(pa.blocks[j] + par_off + (size_t)K * N + (size_t)k * ntile + t)
+        return PEER ? ld_sys_f64(pa.own + par_off + (size_t)j * pa.block_len + (size_t)K * N + (size_t)k * ntile + t)
                     : slot_tot[(size_t)(slot_off[k] + j) * ntile + t];
     };
     if (mode == 0 ? blockIdx.x == 0 : do_rm) {
@@ -446,7 +451,8 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
                 for (int t = lane; t < ntile; t += 32) {
                     double c = 0.0;
                     for (int j = 0; j < c_k; j++) c += tval(k, j, t);
-                    gtile[(size_t)k * ntile + t] = c;
+                    if (push) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)K * N + (size_t)k * ntile + t] = c;
+                    else gtile[(size_t)k * ntile + t] = c;
                 }
             } else {
                 double c = 0.0;
@@ -473,7 +479,8 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
                 v = 0.5 * (v + vr);                        /* the constant correction is fold-invariant */
             }
             if (mode == 1 && do_rm) v -= s_c[k];
-            gsum[(size_t)k * N + n] = v;
+            if (push) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)k * N + n] = v;
+            else gsum[(size_t)k * N + n] = v;
         }
         acc += v;
     }
@@ -515,23 +522,23 @@ extern "C" int tspws_cu_peer_signal(unsigned int *d_step, void *d_peer_flags, in
     return 0;
 }
 
-/* peer variants of the two group_post2 launches: publish (mode 0 into the parity block) and fused sum over ranks */
+/* peer variants of the two group_post2 launches: publish (push into every region) and the sum over ranks */
 extern "C" int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
-                                         int ntile, int do_rm, int do_fold, int split, double *d_gsum, double *d_gtile,
-                                         float *d_out32, double *d_gmean, const void *d_peer_blocks, const unsigned int *d_flags,
-                                         unsigned int *d_step, unsigned int *d_err, int world, tspws_stream_t st)
+                                         int ntile, int do_rm, int do_fold, int split, double *d_gsum,
+                                         float *d_out32, double *d_gmean, void *d_regions, double *d_own, const unsigned int *d_flags,
+                                         unsigned int *d_step, unsigned int *d_err, int rank, int world, tspws_stream_t st)
 {
     const size_t smem = (size_t)K * sizeof(double);
     if (smem > 40 * 1024 || world > 32 * GP2_LANES) return (int)cudaErrorInvalidValue;
     tspws_peer_args pa;
-    pa.blocks = (const double *const *)d_peer_blocks; pa.flags = d_flags; pa.step = d_step; pa.err = d_err;
-    pa.world = world; pa.block_len = (long long)K * N + (long long)K * ntile;
+    pa.regions = (double *const *)d_regions; pa.own = d_own; pa.flags = d_flags; pa.step = d_step; pa.err = d_err;
+    pa.world = world; pa.rank = rank; pa.block_len = (long long)K * N + (long long)K * ntile;
     if (publish)
         group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
-            0, 0, 0, 0, d_gsum, d_gtile, nullptr, nullptr, pa);
+            0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, pa);
     else
         group_post2_kernel<true><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(nullptr, nullptr, nullptr, N, K, ntile,
-            1, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean, pa);
+            1, do_rm, do_fold, split, d_gsum, nullptr, d_out32, d_gmean, pa);
     TSPWS_LAUNCHED_N(publish ? "group_post2_kernel" : "group_post2_peer_kernel", (cudaStream_t)st);
     return 0;
 }

@@ -652,12 +652,11 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
         if ((e = tspws_cu_colsum2(d_sigall, pl->N, pl->d_cs2_parts, pl->cs2_nparts, pl->d_grp_t0, pl->d_cs2_slots,
                                   pl->d_cs2_tot, pl->ntile, stream))) return TSPWS_ERR_CUDA;
         if (pl->peer_on) {
-            /* publish this rank's block (parity of the step) and tell every peer */
-            double *blk = (double *)pl->d_peer_region;
+            /* push this rank's block into every rank's region (slot [parity][rank]) and tell every peer */
             unsigned int *flags = (unsigned int *)((char *)pl->d_peer_region + pl->peer_flag_off);
             if ((e = tspws_cu_group_post2_peer(1, pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
-                                               0, 0, 0, blk, blk + (size_t)pl->K * pl->N, NULL, NULL, pl->d_peer_blocks, flags,
-                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+                                               0, 0, 0, NULL, NULL, NULL, pl->d_peer_blocks, (double *)pl->d_peer_region, flags,
+                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
             if ((e = tspws_cu_peer_signal(pl->d_peer_step, pl->d_peer_flags, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
             pl->peer_pending = 1;
         } else if (pl->mtr_local != pl->mtr_total || pl->exch_bound) {
@@ -723,13 +722,15 @@ int tspws_b200_plan_exchange_is_f64(tspws_plan_t *pl) { return pl && pl->two_sta
 
 /* ---- peer exchange: the ranks of one node map each other's exchange blocks (CUDA IPC) and the sum over
  * ranks is read straight from peer memory inside group_post2_kernel<true>; no collective call ---- */
-int tspws_b200_plan_peer_export(tspws_plan_t *pl, void *handle64)
+int tspws_b200_plan_peer_export(tspws_plan_t *pl, int world, void *handle64)
 {
     if (!pl || !handle64) return TSPWS_ERR_NULL;
-    if (!pl->two_stage || !pl->cs2 || sizeof(cudaIpcMemHandle_t) != 64) return TSPWS_ERR_ARG;
+    if (!pl->two_stage || !pl->cs2 || sizeof(cudaIpcMemHandle_t) != 64 || world < 1 || world > TSPWS_PEER_MAXW) return TSPWS_ERR_ARG;
+    if (pl->d_peer_region && pl->peer_world != world) return TSPWS_ERR_ARG;
     if (!pl->d_peer_region) {
         const size_t blk = tspws_b200_plan_exchange_bytes(pl);
-        pl->peer_flag_off = (2 * blk + 255) & ~(size_t)255;
+        pl->peer_world = world;
+        pl->peer_flag_off = (2 * (size_t)world * blk + 255) & ~(size_t)255;     /* [parity][rank][block] */
         pl->peer_bytes = pl->peer_flag_off + (TSPWS_PEER_MAXW + 1) * sizeof(unsigned int);
         if (cudaMalloc(&pl->d_peer_region, pl->peer_bytes) != cudaSuccess ||
             cudaMemset(pl->d_peer_region, 0, pl->peer_bytes) != cudaSuccess ||
@@ -744,7 +745,7 @@ int tspws_b200_plan_peer_export(tspws_plan_t *pl, void *handle64)
 int tspws_b200_plan_peer_import(tspws_plan_t *pl, int rank, int world, const void *handles)
 {
     if (!pl || !handles) return TSPWS_ERR_NULL;
-    if (!pl->d_peer_region || world < 1 || world > TSPWS_PEER_MAXW || rank < 0 || rank >= world || pl->h_peer_ptr) return TSPWS_ERR_ARG;
+    if (!pl->d_peer_region || world != pl->peer_world || rank < 0 || rank >= world || pl->h_peer_ptr) return TSPWS_ERR_ARG;
     void **ptr = (void **)calloc(world, sizeof(void *));
     void **blocks = (void **)calloc(world, sizeof(void *)), **flags = (void **)calloc(world, sizeof(void *));
     int rc = TSPWS_ERR_CUDA;
@@ -793,12 +794,12 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
          * (sharded / bound / N % 4 != 0) seen as one slot per group, written to a separate buffer */
         const double *gfin = pl->d_gsum;
         if (pl->peer_pending) {
-            /* the sum over ranks is fused in: every rank's block is read over NVLink in rank order */
+            /* the sum over ranks is fused in: the blocks every rank pushed into this region, in rank order */
             unsigned int *flags = (unsigned int *)((char *)pl->d_peer_region + pl->peer_flag_off);
             if ((e = tspws_cu_group_post2_peer(0, NULL, NULL, NULL, pl->N, (int)pl->K, pl->ntile, pl->p.lrm, pl->p.fold,
-                                               pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gfin, NULL, pl->d_gsum32,
-                                               pl->mean_split ? pl->d_gmean : NULL, pl->d_peer_blocks, flags, pl->d_peer_step,
-                                               flags + TSPWS_PEER_MAXW, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+                                               pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gfin, pl->d_gsum32,
+                                               pl->mean_split ? pl->d_gmean : NULL, pl->d_peer_blocks, (double *)pl->d_peer_region, flags,
+                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
             gfin = pl->d_gfin;
         } else if (pl->cs2_pending) {
             if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
