@@ -259,9 +259,14 @@ def run_ours(args, wl, name):
         ok = ok and lib.tspws_b200_plan_peer_import(plan, rank, world, buf) == 0
         okt = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-        if int(okt[0]) == 0:
-            raise SystemExit("peer exchange set-up failed (set TSPWS_BENCH_NCCL=1 for the NCCL all-reduce path)")
-        peer = True
+        peer = int(okt[0]) == 1
+        if not peer:
+            if rank == 0:
+                print("[bench] peer exchange set-up failed on some rank: using the NCCL all-reduce path", file=sys.stderr)
+            lib.tspws_b200_plan_destroy(plan)           # a fresh plan without half-mapped peer state
+            plan = lib.tspws_b200_plan_create(C.byref(p), n, mtr, mtr * world, rank * mtr)
+            if not plan:
+                raise SystemExit("tspws_b200_plan_create failed")
     if world > 1 and not peer:
         nbytes = lib.tspws_b200_plan_exchange_bytes(plan)
         is64 = lib.tspws_b200_plan_exchange_is_f64(plan)

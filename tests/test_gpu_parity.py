@@ -265,3 +265,48 @@ def test_large_single_stage_two_independent_kernel_paths_agree(pkg, gpu_lib):
     o = O.tspws_main(O.Params(w0=6.0, w0set=4), x[:48])
     assert O.nerr(s_coh, o["coherence"]) <= TOL_COH
     assert O.nerr(s_ts, o["tsPWS"]) <= TOL_STACK and O.nerr(s_ls, o["ls"]) <= TOL_STACK
+
+
+@pytest.mark.parametrize("mtr,n,kmax,fold", [(3000, 2048, 127, 1), (37, 1024, 37, 0), (1000, 4096, 3, 1), (513, 1028, 64, 0)])
+def test_group_sum_slots_across_many_group_boundaries(pkg, gpu_lib, mtr, n, kmax, fold):
+    """colsum2_kernel row parts that cross several group boundaries (groups shorter than a part), one
+    trace per group, few huge groups, and a column count that is not a multiple of the 1024 tile:
+    device plan (fused mean / fold on the slot sums) and host path against the oracle."""
+    x = O.synthetic_traces(mtr, n, seed=4000 + kmax) + np.float32(0.05)
+    kw = dict(Kmax=kmax, unbiased=1, lrm=1, fold=fold)
+    o = O.tspws_main(O.Params(**kw), x)
+    ls, ts, coh = _plan_stack(pkg, gpu_lib, x, **kw)
+    assert O.nerr(ts, o["tsPWS"]) <= TOL_STACK and O.nerr(ls, o["ls"]) <= TOL_STACK
+    assert O.nerr(coh, o["coherence"]) <= TOL_COH
+    r = gpu_run(pkg, gpu_lib, x, **kw)
+    assert O.nerr(r["tsPWS"], o["tsPWS"]) <= TOL_STACK and O.nerr(r["coherence"], o["coherence"]) <= TOL_COH
+
+
+def test_peer_exchange_api_argument_checks(pkg, gpu_lib):
+    """Peer exchange is a two-stage feature; a world of one is the degenerate but legal case and must
+    give the plain result."""
+    import torch
+    x = O.synthetic_traces(64, 2048, seed=8)
+    p = pkg.default_params(lrm=1)
+    gpu_lib.tspws_b200_derive_params(C.byref(p), 2048, 1.0)
+    plan = gpu_lib.tspws_b200_plan_create(C.byref(p), 2048, 64, 64, 0)
+    h = (C.c_ubyte * 64)()
+    assert gpu_lib.tspws_b200_plan_peer_export(plan, 1, h) != 0          # single-stage: refused
+    gpu_lib.tspws_b200_plan_destroy(plan)
+    kw = dict(Kmax=8, unbiased=1, lrm=1)
+    ref = _plan_stack(pkg, gpu_lib, x, **kw)
+    p = pkg.default_params(**kw)
+    gpu_lib.tspws_b200_derive_params(C.byref(p), 2048, 1.0)
+    plan = gpu_lib.tspws_b200_plan_create(C.byref(p), 2048, 64, 64, 0)
+    assert gpu_lib.tspws_b200_plan_peer_export(plan, 0, h) != 0 and gpu_lib.tspws_b200_plan_peer_import(plan, 0, 1, h) != 0
+    assert gpu_lib.tspws_b200_plan_peer_export(plan, 1, h) == 0
+    assert gpu_lib.tspws_b200_plan_peer_import(plan, 0, 1, h) == 0
+    dx = torch.from_numpy(x).cuda()
+    ls, ts = torch.empty(2048, device="cuda"), torch.empty(2048, device="cuda")
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        assert gpu_lib.tspws_b200_plan_stack(plan, dx.data_ptr(), ls.data_ptr(), ts.data_ptr(), side.cuda_stream) == 0
+        side.synchronize()
+        assert gpu_lib.tspws_b200_plan_peer_error(plan) == 0
+        assert O.nerr(ts.cpu().numpy(), ref[1]) <= 1e-6 and O.nerr(ls.cpu().numpy(), ref[0]) <= 1e-6
+    gpu_lib.tspws_b200_plan_destroy(plan)
