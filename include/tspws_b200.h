@@ -179,8 +179,12 @@ int tspws_b200_set_selection(const char *sel, unsigned int M, unsigned int mtr);
  *  TSPWS_OPT_WRITEBACK  1: copy the folded / mean-removed traces back into in->sigall
  *                          like the reference's in-place mutation (src/ts_pws1f_lib.c:77-86,167).
  *  TSPWS_OPT_FP64_TAIL  1: run the two-stage transforms in fp64 instead of fp32.
- *  TSPWS_OPT_DEVICE     n: CUDA device ordinal to use. */
-enum { TSPWS_OPT_WRITEBACK = 1, TSPWS_OPT_FP64_TAIL = 2, TSPWS_OPT_DEVICE = 3 };
+ *  TSPWS_OPT_DEVICE     n: CUDA device ordinal to use.
+ *  TSPWS_OPT_SS_JACKKNIFE 1: EXTENSION: compute the single-stage delete-d jackknife,
+ *                          which the reference leaves as an empty stub (src/ts_pws1f_lib.c:711-716): realisation
+ *                          c keeps the K_c traces outside its d deleted bins, weights with (K_c, K_c) like
+ *                          tspws_subsmpl_float, ls_c in the time domain; writes mtr_subsmpl[c] = K_c. */
+enum { TSPWS_OPT_WRITEBACK = 1, TSPWS_OPT_FP64_TAIL = 2, TSPWS_OPT_DEVICE = 3, TSPWS_OPT_SS_JACKKNIFE = 4 };
 int tspws_b200_set_option(int option, long value);
 long tspws_b200_get_option(int option);
 

@@ -375,8 +375,8 @@ def subsample_single_stage(fr: Frame, x: np.ndarray, sel: np.ndarray, wu: float,
     ST_m = Sel.Y, PS_m = Sel.phasor(Y); weights with (K, K); ls_m in the TIME domain with
     float32 accumulators (:537-542, :579-583).  x: [mtr, max] float32 (already folded / rm)."""
     M, mtr = sel.shape
-    K = int(sel[0].sum())
-    st = np.zeros((M, fr.ncoef), dtype=np.complex128)
+    Ks = (sel == 1).sum(axis=1)            # the reference has one K for all rows; the per-row form also
+    st = np.zeros((M, fr.ncoef), dtype=np.complex128)   # serves the single-stage jackknife extension
     ps = np.zeros((M, fr.ncoef), dtype=np.complex128)
     ls = np.zeros((M, x.shape[1]), dtype=np.float32)
     for t in range(mtr):
@@ -386,9 +386,10 @@ def subsample_single_stage(fr: Frame, x: np.ndarray, sel: np.ndarray, wu: float,
         st[use] += Y
         ps[use] += ph
         ls[use] = (ls[use] + x[t].astype(np.float64)).astype(np.float32)   # float += double
-    ls = (ls * np.float32(1.0 / K)).astype(np.float32)
     ts = np.empty_like(ls)
     for m in range(M):
+        K = int(Ks[m])
+        ls[m] = (ls[m] * np.float32(1.0 / K)).astype(np.float32)
         ts[m] = synthesis(fr, weight(st[m], ps[m], K, K, wu, unbiased)).astype(np.float32)
     return ls, ts
 

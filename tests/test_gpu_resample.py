@@ -102,3 +102,23 @@ def test_medium_two_stage_subsampling_vs_oracle(pkg, gpu_lib):
     o = O.tspws_main(O.Params(**kw), x)
     ls, ts, _ = O.resample_two_stage(o["frame"], o["sigall"], sel, 10, 2.0, True)
     assert O.nerr(r["tsPWS_subsmpl"], ts) <= TOL and O.nerr(r["ls_subsmpl"], ls) <= TOL
+
+
+def test_single_stage_jackknife_extension(pkg, gpu_lib):
+    """TSPWS_OPT_SS_JACKKNIFE: the single-stage delete-d jackknife the reference leaves as a stub
+    (SURVEY.md 8f rank 3), against the oracle's single-stage resampling with per-row trace counts."""
+    case = CS.RESAMPLE_CASES["jackknife_two_stage_60x400"]
+    kw = dict(case["params"]); kw["Kmax"] = 0
+    x = CS.make_input(case)
+    times = CS.jackknife_times(case["mtr"])
+    assert gpu_lib.tspws_b200_set_option(pkg.OPT_SS_JACKKNIFE, 1) == 0
+    try:
+        r = pkg.call_tspws_main(gpu_lib, x, pkg.default_params(**kw), times=times)
+    finally:
+        gpu_lib.tspws_b200_set_option(pkg.OPT_SS_JACKKNIFE, 0)
+    assert r["rc"] == 0
+    sel = O.jackknife_plans(times, kw["jackknife_n"], kw["jackknife_d"])
+    np.testing.assert_array_equal(r["mtr_subsmpl"], sel.sum(axis=1))
+    o = O.tspws_main(O.Params(**{k: v for k, v in kw.items() if k in ("lrm", "fold", "wu", "unbiased", "type")}), x)
+    ls, ts = O.subsample_single_stage(o["frame"], o["sigall"], sel, o["params"].wu, bool(o["params"].unbiased))
+    assert O.nerr(r["tsPWS_subsmpl"], ts) <= TOL and O.nerr(r["ls_subsmpl"], ls) <= TOL

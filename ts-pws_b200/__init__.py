@@ -24,7 +24,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libtspws_b200.so")
 
 TSPWS_ERR_CUDA = 77
-OPT_WRITEBACK, OPT_FP64_TAIL, OPT_DEVICE = 1, 2, 3
+OPT_WRITEBACK, OPT_FP64_TAIL, OPT_DEVICE, OPT_SS_JACKKNIFE = 1, 2, 3, 4
 
 W0_DEFAULT = math.pi * math.sqrt(2.0 / math.log(2.0))
 

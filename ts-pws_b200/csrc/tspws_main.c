@@ -21,12 +21,12 @@ const tspws_devframe_t *tspws_plan_devframe(tspws_plan_t *pl);
 /* from tspws_resample.c */
 int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
                        unsigned int mtr, int max, const char *sel_override, unsigned int selM,
-                       cudaStream_t stream);
+                       int ss_jackknife, cudaStream_t stream);
 int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
                           unsigned int mtr, int max, cudaStream_t stream);
 
 static struct {
-    long          opt_writeback, opt_fp64_tail, opt_device;
+    long          opt_writeback, opt_fp64_tail, opt_device, opt_ss_jackknife;
     int           cuda_state;              /* 0 unknown, 1 ok, -1 unusable */
     cudaStream_t  stream;
     /* cached plan of the last main stack */
@@ -68,6 +68,7 @@ int tspws_b200_set_option(int option, long value)
     case TSPWS_OPT_WRITEBACK: G.opt_writeback = value; return 0;
     case TSPWS_OPT_FP64_TAIL: G.opt_fp64_tail = value; return 0;
     case TSPWS_OPT_DEVICE:    G.opt_device = value; G.cuda_state = 0; return 0;
+    case TSPWS_OPT_SS_JACKKNIFE: G.opt_ss_jackknife = value; return 0;
     default: return TSPWS_ERR_ARG;
     }
 }
@@ -77,6 +78,7 @@ long tspws_b200_get_option(int option)
     case TSPWS_OPT_WRITEBACK: return G.opt_writeback;
     case TSPWS_OPT_FP64_TAIL: return G.opt_fp64_tail;
     case TSPWS_OPT_DEVICE:    return G.opt_device;
+    case TSPWS_OPT_SS_JACKKNIFE: return G.opt_ss_jackknife;
     default: return -1;
     }
 }
@@ -256,7 +258,7 @@ int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
     /* ---- resampling (src/ts_pws1f_lib.c:324-345) ---- */
     if (resampling) {
         int e = tspws_resample_run(tspws, out, in, G.d_x, mtr, max, G.sel,
-                                   (G.sel && G.selmtr == mtr) ? G.selM : 0, st);
+                                   (G.sel && G.selmtr == mtr) ? G.selM : 0, G.opt_ss_jackknife != 0, st);
         if (e) return e;
     }
     return 0;

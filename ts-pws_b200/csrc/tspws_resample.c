@@ -153,9 +153,11 @@ done:
 /* single-stage sub-sampling                                                             */
 /* ------------------------------------------------------------------------------------ */
 static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float *d_x, unsigned int mtr, int max,
-                                  const char *sel, unsigned int M, unsigned int K,
+                                  const char *sel, unsigned int M, unsigned int K, unsigned int *k_rows /* out or NULL */,
                                   float **ls_rows, float **ts_rows, cudaStream_t st)
 {
+    /* K != 0: every realisation keeps exactly K traces (sub-sampling); K == 0: realisation m keeps the
+     * traces its selection row marks, K_m of them (jackknife), written to k_rows[m] */
     int rc = 0;
     const size_t N = (size_t)max, ncoef = F->fr->ncoef ? F->fr->ncoef : 1;
     const int B = RS_BATCH, ntk = (max + 255) / 256;
@@ -172,7 +174,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
     if (!h_gid || !h_scale || !h_rules || !h_buf) { rc = TSPWS_ERR_ALLOC; goto done; }
     for (size_t i = 0; i < (size_t)M * mtr; i++) h_gid[i] = (sel[i] == 1) ? 0 : -1;
-    for (int b = 0; b < B; b++) { h_scale[b] = 1.0 / (double)K; h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, K, K); }
+    for (int b = 0; b < B; b++) { h_scale[b] = 1.0 / (double)(K ? K : 1); h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, K ? K : 1, K ? K : 1); }
 
     CKR(cudaMalloc((void **)&d_gid, (size_t)M * mtr));
     CKR(cudaMalloc((void **)&d_sel, (size_t)M * mtr));
@@ -206,6 +208,18 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     /* per batch of resamples: time-domain sums -> ls, ST by linearity, weights, inverse */
     for (unsigned int m0 = 0; m0 < M; m0 += B) {
         const int nb = (int)((M - m0 < (unsigned int)B) ? M - m0 : (unsigned int)B);
+        if (!K) {                                  /* per-realisation trace counts */
+            for (int b = 0; b < nb; b++) {
+                unsigned int km = 0;
+                for (unsigned int t = 0; t < mtr; t++) km += sel[(size_t)(m0 + b) * mtr + t] == 1;
+                if (k_rows) k_rows[m0 + b] = km;
+                if (!km) km = 1;
+                h_scale[b] = 1.0 / (double)km;
+                h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, km, km);
+            }
+            CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
+            CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+        }
         CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, nb, 1, d_S, st));
         CKK(tspws_cu_group_total(d_S, nb, 1, max, d_scale, d_ls, st));
         CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, st));
@@ -230,7 +244,7 @@ done:
 /* ------------------------------------------------------------------------------------ */
 int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
                        unsigned int mtr, int max, const char *sel_override, unsigned int selM,
-                       cudaStream_t stream)
+                       int ss_jackknife, cudaStream_t stream)
 {
     int rc = 0;
     const int two_stage = p->Kmax && p->Kmax <= mtr;
@@ -250,14 +264,16 @@ int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, flo
         if (K == 0 || K > mtr) { fprintf(stderr, "tspws_b200: subsmpl_p out of range\n"); rc = TSPWS_ERR_ARG; goto done; }
         if (two_stage) rc = two_stage_rows(p, &F, d_x, mtr, max, sel, M, p->Kmax, out->ls_subsmpl, out->tsPWS_subsmpl,
                                            NULL, NULL, NULL, NULL, stream);
-        else           rc = single_stage_subsample(p, &F, d_x, mtr, max, sel, M, K, out->ls_subsmpl, out->tsPWS_subsmpl, stream);
+        else           rc = single_stage_subsample(p, &F, d_x, mtr, max, sel, M, K, NULL, out->ls_subsmpl, out->tsPWS_subsmpl, stream);
         free(sel); sel = NULL;
         if (rc) goto done;
     }
     /* ---- delete-d jackknife over day-of-year bins (src/ts_pws1f_lib.c:335-345) ---- */
     if (p->jackknife_n > 0 && p->jackknife_d > 0) {
         const unsigned int Cn = out->M;
-        if (!two_stage) goto done;                    /* reference: empty stub, outputs untouched (:711-716) */
+        /* single-stage: the reference is an empty stub that leaves the outputs untouched (:711-716);
+         * TSPWS_OPT_SS_JACKKNIFE turns the extension of SURVEY 8(f) rank 3 on */
+        if (!two_stage && !ss_jackknife) goto done;
         if (!Cn) goto done;
         sel = (char *)malloc((size_t)Cn * mtr);
         if (!sel) { rc = TSPWS_ERR_ALLOC; goto done; }
@@ -269,8 +285,10 @@ int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, flo
                 goto done;
             }
         }
-        rc = two_stage_rows(p, &F, d_x, mtr, max, sel, Cn, p->Kmax, out->ls_subsmpl, out->tsPWS_subsmpl,
-                            out->mtr_subsmpl, NULL, NULL, NULL, stream);
+        if (two_stage) rc = two_stage_rows(p, &F, d_x, mtr, max, sel, Cn, p->Kmax, out->ls_subsmpl, out->tsPWS_subsmpl,
+                                           out->mtr_subsmpl, NULL, NULL, NULL, stream);
+        else           rc = single_stage_subsample(p, &F, d_x, mtr, max, sel, Cn, 0, out->mtr_subsmpl, out->ls_subsmpl,
+                                                   out->tsPWS_subsmpl, stream);
     }
 done:
     free(sel);
