@@ -422,6 +422,8 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
     /* the scale records go up last: every block above fills some of their fields */
     if (cudaMemcpy(d->d_scale, sc, S * sizeof(*sc), cudaMemcpyHostToDevice) != cudaSuccess) goto done;
     d->nitems = nitems;
+    /* uploads above used the legacy stream; callers launch on non-blocking streams */
+    if (cudaDeviceSynchronize() != cudaSuccess) goto done;
     ok = 1;
 done:
     free(sc); free(w32); free(items); free(grp); free(items2); free(items_gen); free(g32);
@@ -630,6 +632,9 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     }
     CK(cudaMalloc((void **)&pl->d_inv_tickets, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
     CK(cudaMemset(pl->d_inv_tickets, 0, (size_t)((max + 255) / 256) * sizeof(unsigned int)));
+    /* the uploads / memsets above went through the legacy stream; the plan runs on caller streams that do
+     * not synchronise with it (cudaStreamNonBlocking), so finish them here, once */
+    CK(cudaDeviceSynchronize());
     return pl;
 fail:
     tspws_b200_plan_destroy(pl);
