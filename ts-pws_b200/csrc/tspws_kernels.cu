@@ -375,7 +375,9 @@ extern "C" int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts, in
  * of the group sums is fused into the two group_post2 launches instead of an all-reduce between them.
  *   publish (mode 0 with peer args): the rank's block (group sums + tile totals of its shard) is PUSHED
  *       into slot [parity][rank] of every rank's region with plain stores over NVLink / NVSwitch (remote
- *       stores pipeline; remote loads measured 10x slower at 8 GPUs: 124 us for 9 MB);
+ *       stores pipeline; remote loads measured 10x slower at 8 GPUs: 124 us for 9 MB).  A shard is a
+ *       contiguous trace range, so it touches only a few of the K groups: only those are pushed, and a
+ *       presence mark per group tells the readers which ranks to add (at 8 GPUs 2-3 of 10 groups);
  *   peer_signal_kernel: system fence, then the step number into every rank's flag word;
  *   PEER = true launch: waits until the flags of all ranks have reached this step, then treats the world
  *       blocks of its OWN region as the slots of every group (rank order: deterministic).
@@ -388,7 +390,7 @@ struct tspws_peer_args {
     unsigned int        *step;       /* own step counter (advanced by peer_signal_kernel) */
     unsigned int        *err;        /* set when a wait timed out */
     int world, rank;
-    long long block_len;             /* doubles per block = K*N + K*ntile */
+    long long block_len;             /* doubles per block = K*N group sums + K*ntile tile totals + K presence marks */
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
@@ -413,8 +415,9 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
                    double *__restrict__ gsum, double *__restrict__ gtile, float *__restrict__ out32, double *__restrict__ gmean,
                    const tspws_peer_args pa)
 {
-    extern __shared__ double s_c[];                      /* [K] group-mean corrections */
+    extern __shared__ double s_c[];                      /* [K] group-mean corrections, then [K][world] presence bytes */
     __shared__ double s_m[GP2_LANES][32];
+    unsigned char *s_pres = reinterpret_cast<unsigned char *>(s_c + K);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     size_t par_off = 0;                                  /* first block of this step's parity */
     if (PEER) {
@@ -428,6 +431,12 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
             }
         }
         __syncthreads();
+        /* which rank contributes to which group (marks pushed with the blocks) */
+        for (int i = threadIdx.x; i < K * pa.world; i += blockDim.x) {
+            const int k = i / pa.world, j = i % pa.world;
+            s_pres[i] = ld_sys_f64(pa.own + par_off + (size_t)j * pa.block_len + (size_t)K * N + (size_t)K * ntile + k) != 0.0;
+        }
+        __syncthreads();
     } else if (mode == 0 && pa.step) {
         /* publishing launch of a peer plan: slot [parity][rank] of every region */
         par_off = ((size_t)(*pa.step & 1) * (size_t)pa.world + (size_t)pa.rank) * (size_t)pa.block_len;
@@ -436,22 +445,24 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     /* slot j of group k: value at sample n, total of tile t */
     auto cnt = [&](int k) { return PEER ? pa.world : slot_off[k + 1] - slot_off[k]; };
     auto sval = [&](int k, int j, int n) {
-        return PEER ? ld_sys_f64(pa.own + par_off + (size_t)j * pa.block_len + (size_t)k * N + n)
-                    : __ldcg(slots + (size_t)(slot_off[k] + j) * N + n);
+        if (PEER) return s_pres[k * pa.world + j] ? ld_sys_f64(pa.own + par_off + (size_t)j * pa.block_len + (size_t)k * N + n) : 0.0;
+        return __ldcg(slots + (size_t)(slot_off[k] + j) * N + n);
     };
     auto tval = [&](int k, int j, int t) {
-        return PEER ? ld_sys_f64(pa.own + par_off + (size_t)j * pa.block_len + (size_t)K * N + (size_t)k * ntile + t)
-                    : slot_tot[(size_t)(slot_off[k] + j) * ntile + t];
+        if (PEER) return s_pres[k * pa.world + j] ? ld_sys_f64(pa.own + par_off + (size_t)j * pa.block_len + (size_t)K * N + (size_t)k * ntile + t) : 0.0;
+        return slot_tot[(size_t)(slot_off[k] + j) * ntile + t];
     };
     if (mode == 0 ? blockIdx.x == 0 : do_rm) {
         /* totals of every group: lanes stride over (slot, tile) in a fixed pattern, fixed shuffle tree */
         for (int k = w; k < K; k += GP2_LANES) {
             const int c_k = cnt(k);
             if (mode == 0) {
+                if (push && lane == 0)                     /* presence mark of group k, rewritten every step */
+                    for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)K * N + (size_t)K * ntile + k] = c_k ? 1.0 : 0.0;
                 for (int t = lane; t < ntile; t += 32) {
                     double c = 0.0;
                     for (int j = 0; j < c_k; j++) c += tval(k, j, t);
-                    if (push) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)K * N + (size_t)k * ntile + t] = c;
+                    if (push) { if (c_k) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)K * N + (size_t)k * ntile + t] = c; }
                     else gtile[(size_t)k * ntile + t] = c;
                 }
             } else {
@@ -479,7 +490,7 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
                 v = 0.5 * (v + vr);                        /* the constant correction is fold-invariant */
             }
             if (mode == 1 && do_rm) v -= s_c[k];
-            if (push) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)k * N + n] = v;
+            if (push) { if (c_k) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)k * N + n] = v; }
             else gsum[(size_t)k * N + n] = v;
         }
         acc += v;
@@ -528,11 +539,11 @@ extern "C" int tspws_cu_group_post2_peer(int publish, const double *d_slots, con
                                          float *d_out32, double *d_gmean, void *d_regions, double *d_own, const unsigned int *d_flags,
                                          unsigned int *d_step, unsigned int *d_err, int rank, int world, tspws_stream_t st)
 {
-    const size_t smem = (size_t)K * sizeof(double);
+    const size_t smem = (size_t)K * sizeof(double) + (size_t)K * world;
     if (smem > 40 * 1024 || world > 32 * GP2_LANES) return (int)cudaErrorInvalidValue;
     tspws_peer_args pa;
     pa.regions = (double *const *)d_regions; pa.own = d_own; pa.flags = d_flags; pa.step = d_step; pa.err = d_err;
-    pa.world = world; pa.rank = rank; pa.block_len = (long long)K * N + (long long)K * ntile;
+    pa.world = world; pa.rank = rank; pa.block_len = (long long)K * N + (long long)K * ntile + K;
     if (publish)
         group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
             0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, pa);

@@ -733,7 +733,7 @@ int tspws_b200_plan_peer_export(tspws_plan_t *pl, int world, void *handle64)
     if (!pl->two_stage || !pl->cs2 || sizeof(cudaIpcMemHandle_t) != 64 || world < 1 || world > TSPWS_PEER_MAXW) return TSPWS_ERR_ARG;
     if (pl->d_peer_region && pl->peer_world != world) return TSPWS_ERR_ARG;
     if (!pl->d_peer_region) {
-        const size_t blk = tspws_b200_plan_exchange_bytes(pl);
+        const size_t blk = tspws_b200_plan_exchange_bytes(pl) + pl->K * sizeof(double);   /* + presence marks */
         pl->peer_world = world;
         pl->peer_flag_off = (2 * (size_t)world * blk + 255) & ~(size_t)255;     /* [parity][rank][block] */
         pl->peer_bytes = pl->peer_flag_off + (TSPWS_PEER_MAXW + 1) * sizeof(unsigned int);
