@@ -775,15 +775,18 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
  * Arithmetic is Blackwell's packed FFMA2 (fma.rn.f32x2): one instruction updates (Re, Im) of a
  * coefficient, acc[r] += x * (g.re, g.im). */
 #define FW_WS 32
-template <typename LoadX, typename LoadG, typename Advance>
+#ifndef FW_GQ5
+#define FW_GQ5 4          /* filter taps in flight per lane when D >= 32; 8 measured no faster (450 vs 462 us, 64 traces) */
+#endif
+template <int GQ, typename LoadX, typename LoadG, typename Advance>
 __device__ __forceinline__ void fw_taps(float2 (&acc)[FW_R], const int Qs, LoadX loadx, LoadG loadg, Advance advance)
 {
     float2 win[FW_WS];
-    float2 gq[4];
+    float2 gq[GQ];
 #pragma unroll
     for (int j = 0; j < FW_WS; j++) { const float t = loadx(j); win[j] = make_float2(t, t); }
 #pragma unroll
-    for (int q = 0; q < 4; q++) gq[q] = loadg(q);
+    for (int q = 0; q < GQ; q++) gq[q] = loadg(q);
     for (int t0 = 0; t0 < Qs; t0 += FW_WS) {
 #pragma unroll
         for (int tq = 0; tq < FW_WS; tq += 4) {
@@ -791,12 +794,12 @@ __device__ __forceinline__ void fw_taps(float2 (&acc)[FW_R], const int Qs, LoadX
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int tt = tq + u;
-                    const float2 gv = gq[tt & 3];
+                    const float2 gv = gq[tt & (GQ - 1)];
 #pragma unroll
                     for (int r = 0; r < FW_R; r++) acc[r] = __ffma2_rn(win[(tt + r) % FW_WS], gv, acc[r]);
                     const float t = loadx(tt + FW_WS);
                     win[tt]    = make_float2(t, t);
-                    gq[tt & 3] = loadg(tt + 4);
+                    gq[tt & (GQ - 1)] = loadg(tt + GQ);
                 }
             }
         }
@@ -914,7 +917,7 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
             const int a = lane >> LGS, rho = lane & (LP - 1);
             const float  *xb = cur + a * ((FW_R + 1) * LP) + rho;      /* sample j of the block at (j + (j >> 4)) LP */
             const float2 *gb = g + rho;
-            fw_taps(acc, Qs,
+            fw_taps<4>(acc, Qs,
                     [&](const int j) { return xb[(j + (j >> 4)) * LP]; },
                     [&](const int q) { return __ldg(gb + q * LP); },
                     [&]() { xb += 34 * LP; gb += 32 * LP; });
@@ -937,7 +940,7 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
                 __syncwarp();
                 const float  *xb = cur + lane;
                 const float2 *gp = g + pb * 32 + lane;                  /* taps are consumed strictly in order */
-                fw_taps(acc, Qs,
+                fw_taps<FW_GQ5>(acc, Qs,
                         [&](const int j) { return xb[j * 32]; },
                         [&](const int) { const float2 v = __ldg(gp); gp += GS; return v; },
                         [&]() { xb += 32 * 32; });
