@@ -118,6 +118,9 @@ typedef struct {
     double wu;
     double K;         /* Kmax (two-stage) or number of stacked traces */
     double T;         /* mtr (divisor of the linear stack)            */
+    /* host-side reciprocals (always filled by tspws_weight_rule): no fp64 division on the device */
+    double inv_k;     /* 1 / K                                                                 */
+    double inv_f;     /* mode 0: 1/(K K T), mode 1: 1/(K T), mode 2: 1/T, mode 3: 1/((K-1) T)    */
 } tspws_weight_t;
 
 /* ---------------------------------------------------------------------------------- */

@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(32 * GP2_LANES)
 group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ slot_tot, const int *__restrict__ slot_off,
                    int N, int K, int ntile, int mode, int do_rm, int do_fold, int split,
                    double *__restrict__ gsum, double *__restrict__ gtile, float *__restrict__ out32, double *__restrict__ gmean,
-                   const tspws_peer_args pa)
+                   const tspws_peer_args pa, const double inv_n, const double inv_k)
 {
     extern __shared__ double s_c[];                      /* [K] group-mean corrections, then [K][world] presence bytes */
     __shared__ double s_m[GP2_LANES][32];
@@ -467,9 +467,14 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
                 }
             } else {
                 double c = 0.0;
-                for (int i = lane; i < c_k * ntile; i += 32) c += tval(k, i / ntile, i % ntile);
+                if (PEER) {
+                    for (int i = lane; i < c_k * ntile; i += 32) c += tval(k, i / ntile, i % ntile);
+                } else {                                   /* the totals of a group's slots are contiguous */
+                    const double *t0 = slot_tot + (size_t)slot_off[k] * ntile;
+                    for (int i = lane; i < c_k * ntile; i += 32) c += t0[i];
+                }
                 c = warp_sum(c);
-                if (lane == 0) s_c[k] = c / (double)(unsigned int)N;
+                if (lane == 0) s_c[k] = c * inv_n;         /* host-side reciprocal: no fp64 division chain here */
             }
         }
     }
@@ -477,23 +482,34 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     const int n = blockIdx.x * 32 + lane;
     const bool ok = n < N;
     const int r = N - 1 - n;
+    /* the first GP2_KR rounds of this warp's groups stay in registers between the two passes */
+    constexpr int GP2_KR = 4;
+    double vreg[GP2_KR];
     double acc = 0.0;
-    for (int k = w; k < K; k += GP2_LANES) {
+#pragma unroll
+    for (int kk = 0; kk < GP2_KR; kk++) vreg[kk] = 0.0;
+    auto group_value = [&](int k) {
         const int c_k = cnt(k);
         double v = 0.0, vr = 0.0;
-        if (ok) {
 #pragma unroll 4
-            for (int j = 0; j < c_k; j++) v += sval(k, j, n);
-            if (mode == 1 && do_fold) {
+        for (int j = 0; j < c_k; j++) v += sval(k, j, n);
+        if (mode == 1 && do_fold) {
 #pragma unroll 4
-                for (int j = 0; j < c_k; j++) vr += sval(k, j, r);
-                v = 0.5 * (v + vr);                        /* the constant correction is fold-invariant */
-            }
-            if (mode == 1 && do_rm) v -= s_c[k];
-            if (push) { if (c_k) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)k * N + n] = v; }
-            else gsum[(size_t)k * N + n] = v;
+            for (int j = 0; j < c_k; j++) vr += sval(k, j, r);
+            v = 0.5 * (v + vr);                            /* the constant correction is fold-invariant */
         }
-        acc += v;
+        if (mode == 1 && do_rm) v -= s_c[k];
+        if (push) { if (c_k) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)k * N + n] = v; }
+        else gsum[(size_t)k * N + n] = v;
+        return v;
+    };
+    if (ok) {
+#pragma unroll
+        for (int kk = 0; kk < GP2_KR; kk++) {
+            const int k = w + kk * GP2_LANES;
+            if (k < K) { vreg[kk] = group_value(k); acc += vreg[kk]; }
+        }
+        for (int k = w + GP2_KR * GP2_LANES; k < K; k += GP2_LANES) acc += group_value(k);
     }
     if (mode == 0) return;
     double m = 0.0;
@@ -502,14 +518,22 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < GP2_LANES; i++) m += s_m[i][lane];
-        m /= (double)K;
+        m *= inv_k;
         if (w == 0 && ok && gmean) { gmean[n] = m; gmean[n + N] = m; gmean[n + 2 * N] = m; }   /* three periods for fwd_f64_kernel */
     }
     if (!ok) return;
-    for (int k = w; k < K; k += GP2_LANES) {
+#pragma unroll
+    for (int kk = 0; kk < GP2_KR; kk++) {
+        const int k = w + kk * GP2_LANES;
+        if (k < K) {
+            out32[(size_t)k * N + n] = (float)(vreg[kk] - m);
+            if (split > 1) out32[(size_t)(K + k) * N + n] = (float)vreg[kk];   /* rows K..2K-1: unsplit (long filters) */
+        }
+    }
+    for (int k = w + GP2_KR * GP2_LANES; k < K; k += GP2_LANES) {
         const double v = gsum[(size_t)k * N + n];
         out32[(size_t)k * N + n] = (float)(v - m);
-        if (split > 1) out32[(size_t)(K + k) * N + n] = (float)v;  /* rows K..2K-1: unsplit (long filters) */
+        if (split > 1) out32[(size_t)(K + k) * N + n] = (float)v;
     }
 }
 
@@ -546,10 +570,10 @@ extern "C" int tspws_cu_group_post2_peer(int publish, const double *d_slots, con
     pa.world = world; pa.rank = rank; pa.block_len = (long long)K * N + (long long)K * ntile + K;
     if (publish)
         group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
-            0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, pa);
+            0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, pa, 1.0 / (double)N, 1.0 / (double)K);
     else
         group_post2_kernel<true><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(nullptr, nullptr, nullptr, N, K, ntile,
-            1, do_rm, do_fold, split, d_gsum, nullptr, d_out32, d_gmean, pa);
+            1, do_rm, do_fold, split, d_gsum, nullptr, d_out32, d_gmean, pa, 1.0 / (double)N, 1.0 / (double)K);
     TSPWS_LAUNCHED_N(publish ? "group_post2_kernel" : "group_post2_peer_kernel", (cudaStream_t)st);
     return 0;
 }
@@ -563,7 +587,8 @@ extern "C" int tspws_cu_group_post2(const double *d_slots, const double *d_slot_
     tspws_peer_args pa;
     memset(&pa, 0, sizeof pa);
     group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
-                                                                                         mode, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean, pa);
+                                                                                         mode, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean, pa,
+                                                                                         1.0 / (double)N, 1.0 / (double)K);
     TSPWS_LAUNCHED_N("group_post2_kernel", (cudaStream_t)st);
     return 0;
 }
@@ -1485,14 +1510,13 @@ __device__ __forceinline__ double weight_factor(const tspws_weight_t r, double p
 {
     const double a2 = pr * pr + pi * pi;
     switch (r.mode) {
-    case 0:  return a2 * (1.0 / (r.K * r.K * r.T));                       /* nu = 2          */
-    case 1:  return sqrt(a2) * (1.0 / (r.K * r.T));                       /* nu = 1          */
+    case 0:  return a2 * r.inv_f;                                         /* nu = 2          */
+    case 1:  return sqrt(a2) * r.inv_f;                                   /* nu = 1          */
     case 3: {                                                             /* unbiased, nu = 2 */
-        const double ik = 1.0 / r.K;
-        const double c  = (pr * ik) * (pr * ik) + (pi * ik) * (pi * ik);
-        return (r.K * c - 1.0) * (1.0 / (r.K - 1.0)) * (1.0 / r.T);
+        const double c = (pr * r.inv_k) * (pr * r.inv_k) + (pi * r.inv_k) * (pi * r.inv_k);
+        return (r.K * c - 1.0) * r.inv_f;
     }
-    default: return pow(sqrt(a2) / r.K, r.wu) / r.T;                      /* general nu      */
+    default: return pow(sqrt(a2) * r.inv_k, r.wu) * r.inv_f;              /* general nu      */
     }
 }
 

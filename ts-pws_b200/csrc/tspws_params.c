@@ -99,6 +99,9 @@ tspws_weight_t tspws_weight_rule(double wu, int unbiased, unsigned int K, unsign
     else if (wu == 2)                 r.mode = 0;
     else if (wu == 1)                 r.mode = 1;
     else                              r.mode = 2;
+    r.inv_k = 1.0 / r.K;
+    r.inv_f = r.mode == 0 ? 1.0 / (r.K * r.K * r.T) : r.mode == 1 ? 1.0 / (r.K * r.T)
+            : r.mode == 3 ? 1.0 / ((r.K - 1.0) * r.T) : 1.0 / r.T;
     return r;
 }
 
