@@ -89,10 +89,29 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def synthetic_signal(nmax):
+    """Windowed exponential chirp in the style of the reference's src/FWTa/FWT_Test.m:38-47: f 0.005 -> 0.03
+    cycles/sample over the central 80 %, Hann-tapered 40 % / 40 %.  Kept here so that the
+    measured arm imports nothing from oracle/."""
+    n0, n1 = int(0.1 * nmax), int(0.9 * nmax)
+    L = n1 - n0
+    t = np.arange(L, dtype=np.float64)
+    f0, f1 = 0.005, 0.03
+    k = (f1 / f0) ** (1.0 / L)
+    phase = 2 * np.pi * f0 * (k ** t - 1) / np.log(k)
+    win = np.ones(L)
+    e = int(0.4 * L)
+    h = 0.5 * (1 - np.cos(np.pi * np.arange(e) / e))
+    win[:e] = h
+    win[L - e:] = h[::-1]
+    s = np.zeros(nmax)
+    s[n0:n1] = np.sin(phase) * win
+    return s
+
+
 def make_traces(mtr, n, first=0):
     """x = 0.5*chirp + N(0,1), counter-based per global trace index, fp32."""
-    from oracle import tspws_oracle as O          # input generator only (not the oracle path)
-    sig = (O.synthetic_signal(n) * 0.5).astype(np.float32)
+    sig = (synthetic_signal(n) * 0.5).astype(np.float32)
     out = np.empty((mtr, n), dtype=np.float32)
     rng = np.random.Generator(np.random.Philox(key=20171 + first))
     blk = 256

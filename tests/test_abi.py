@@ -37,9 +37,28 @@ def test_null_arguments(pkg, lib):
     assert lib.tspws_main(C.byref(p), None, None) == -1
 
 
+def test_null_arguments_of_the_additive_entry_points(pkg, lib):
+    """Argument checks that come before any CUDA call (so they run without a GPU)."""
+    p = pkg.default_params()
+    assert lib.tspws_b200_main_batch(None, None, None, 3) == -1
+    assert lib.tspws_b200_main_batch(C.byref(p), None, None, 0) == -1
+    h = (C.c_ubyte * 64)()
+    assert lib.tspws_b200_plan_peer_export(None, 2, h) != 0
+    assert lib.tspws_b200_plan_peer_import(None, 0, 2, h) != 0
+    assert lib.tspws_b200_plan_peer_error(None) == 0
+    assert lib.tspws_b200_plan_reduce(None, None, None) != 0
+    assert lib.tspws_b200_plan_finish(None, None, None, None) != 0
+    assert lib.tspws_b200_plan_exchange_bytes(None) == 0
+    assert not lib.tspws_b200_plan_create(None, 16, 1, 1, 0)
+    assert not lib.tspws_b200_plan_create(C.byref(p), 0, 1, 1, 0)          # max <= 0
+    assert not lib.tspws_b200_plan_create(C.byref(p), 16, 2, 1, 0)         # more local than total traces
+
+
 def test_version_and_options(pkg, lib):
     assert b"tspws_b200" in lib.tspws_b200_version()
     assert lib.tspws_b200_set_option(pkg.OPT_WRITEBACK, 1) == 0
     assert lib.tspws_b200_get_option(pkg.OPT_WRITEBACK) == 1
     assert lib.tspws_b200_set_option(pkg.OPT_WRITEBACK, 0) == 0
     assert lib.tspws_b200_set_option(99, 0) != 0
+    assert lib.tspws_b200_set_option(pkg.OPT_SS_JACKKNIFE, 1) == 0 and lib.tspws_b200_get_option(pkg.OPT_SS_JACKKNIFE) == 1
+    assert lib.tspws_b200_set_option(pkg.OPT_SS_JACKKNIFE, 0) == 0
