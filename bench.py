@@ -466,7 +466,10 @@ def run_ours(args, wl, name):
             t.daemon = True
             t.start()
             try:
-                dist.barrier()                          # nobody unmaps its exchange block while a peer may read it
+                dist.barrier()                          # every rank is done with the peers' blocks
+                if peer:
+                    lib.tspws_b200_plan_peer_close(plan)    # unmap first ...
+                    dist.barrier()                          # ... free only when nobody maps the region any more
             except Exception:                           # noqa: BLE001
                 pass
         lib.tspws_b200_plan_destroy(plan)

@@ -252,6 +252,9 @@ int    tspws_b200_plan_mark_exchanged(tspws_plan_t *plan);
 int tspws_b200_plan_peer_export(tspws_plan_t *plan, int world, void *handle64);
 int tspws_b200_plan_peer_import(tspws_plan_t *plan, int rank, int world, const void *handles /* world x 64 bytes */);
 int tspws_b200_plan_peer_error(tspws_plan_t *plan);
+/* Teardown order (CUDA IPC rule: never free an exported allocation that another process still maps):
+ * every rank calls plan_peer_close, the ranks synchronise (barrier), then every rank calls plan_destroy. */
+int tspws_b200_plan_peer_close(tspws_plan_t *plan);
 int tspws_b200_plan_finish(tspws_plan_t *plan, float *d_ls, float *d_tspws, void *stream);
 /* A+B on one GPU. */
 int tspws_b200_plan_stack(tspws_plan_t *plan, float *d_sigall, float *d_ls, float *d_tspws,

@@ -129,6 +129,8 @@ def nccl_plan():
             d_ts, d_ls = O.nerr(ts.cpu().numpy(), ref_ts.cpu().numpy()), O.nerr(ls.cpu().numpy(), ref_ls.cpu().numpy())
             assert d_ts <= 1e-6 and d_ls <= 1e-6, (rank, kw, it, d_ts, d_ls)
         dist.barrier()                                               # nobody unmaps while a peer still reads
+        assert lib.tspws_b200_plan_peer_close(plan) == 0
+        dist.barrier()                                               # nobody frees while a peer still maps
         lib.tspws_b200_plan_destroy(plan)
     dist.barrier()
     if rank == 0:

@@ -544,6 +544,8 @@ done:
     return rc;
 }
 
+int tspws_b200_plan_peer_close(tspws_plan_t *pl);
+
 void tspws_b200_plan_destroy(tspws_plan_t *pl)
 {
     if (!pl) return;
@@ -553,11 +555,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     cudaFree(pl->d_gmean); cudaFree(pl->d_ymean);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
-    if (pl->h_peer_ptr) {
-        for (int r = 0; r < pl->peer_world; r++)
-            if (r != pl->peer_rank && pl->h_peer_ptr[r]) cudaIpcCloseMemHandle(pl->h_peer_ptr[r]);
-        free(pl->h_peer_ptr);
-    }
+    tspws_b200_plan_peer_close(pl);
     cudaFree(pl->d_peer_region); cudaFree(pl->d_peer_blocks); cudaFree(pl->d_peer_flags); cudaFree(pl->d_peer_step);
     cudaFree(pl->d_gfin); cudaFree(pl->d_ident);
     cudaFree(pl->d_cs2_parts); cudaFree(pl->d_cs2_slot_off); cudaFree(pl->d_cs2_slots); cudaFree(pl->d_cs2_tot);
@@ -775,6 +773,25 @@ int tspws_b200_plan_peer_import(tspws_plan_t *pl, int rank, int world, const voi
 out:
     free(ptr); free(blocks); free(flags);
     return rc;
+}
+
+/* Unmap the other ranks' regions (the own region stays allocated until plan_destroy).  CUDA requires that an
+ * exported allocation is not freed while another process still maps it: ranks call this, synchronise among
+ * themselves (barrier), and only then destroy their plans.  The plan falls back to the collective-free
+ * single-rank behaviour afterwards only in the sense that peer mode is off: do not stack with it again. */
+int tspws_b200_plan_peer_close(tspws_plan_t *pl)
+{
+    if (!pl) return TSPWS_ERR_NULL;
+    if (pl->h_peer_ptr) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < pl->peer_world; r++)
+            if (r != pl->peer_rank && pl->h_peer_ptr[r]) cudaIpcCloseMemHandle(pl->h_peer_ptr[r]);
+        free(pl->h_peer_ptr);
+        pl->h_peer_ptr = NULL;
+        pl->peer_on = 0;
+        if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
+    }
+    return 0;
 }
 
 /* 1 if a peer wait timed out since the plan was created (a rank died or never arrived) */
