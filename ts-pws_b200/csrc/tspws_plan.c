@@ -777,8 +777,8 @@ out:
 
 /* Unmap the other ranks' regions (the own region stays allocated until plan_destroy).  CUDA requires that an
  * exported allocation is not freed while another process still maps it: ranks call this, synchronise among
- * themselves (barrier), and only then destroy their plans.  The plan falls back to the collective-free
- * single-rank behaviour afterwards only in the sense that peer mode is off: do not stack with it again. */
+ * themselves (barrier), and only then destroy their plans.  Peer mode is off afterwards; the plan is only
+ * good for plan_destroy (or the NCCL-style reduce / exchange / finish sequence). */
 int tspws_b200_plan_peer_close(tspws_plan_t *pl)
 {
     if (!pl) return TSPWS_ERR_NULL;
