@@ -213,6 +213,7 @@ int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
 
     if ((nerr = ensure_cuda())) return nerr;
     cudaStream_t st = G.stream;
+    cudaGetLastError();                          /* a stale error of an earlier call must not fail this one */
 
     /* ---- traces to the device ---- */
     const size_t nelem = (size_t)mtr * (size_t)max;
@@ -321,6 +322,7 @@ int tspws_b200_main_batch(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsign
     }
     int nerr = ensure_cuda();
     if (nerr) return nerr;
+    cudaGetLastError();                          /* a stale error of an earlier call must not fail this one */
 
     const size_t nelem = (size_t)mtr * (size_t)max;
     const int two_stage  = tspws->Kmax && tspws->Kmax <= mtr;

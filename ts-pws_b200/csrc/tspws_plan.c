@@ -550,7 +550,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
 {
     if (!pl) return;
     if (pl->exch_bound) { pl->d_gsum = (double *)pl->own_gsum; pl->d_exch = pl->own_exch; }
-    if (pl->gexec) cudaGraphExecDestroy(pl->gexec);
+    if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
     if (pl->side) { cudaStreamDestroy(pl->side); cudaEventDestroy(pl->ev_join); cudaEventDestroy(pl->ev_fork); }
     cudaFree(pl->d_gmean); cudaFree(pl->d_ymean);
     free(pl->h_slot_off);
