@@ -1,18 +1,35 @@
 /*
  * tspws_kernels.cu -- sm_100a kernels of the ts-PWS stacking path and their C launchers.
  *
- * Kernel                    replaces (reference file:line)                         bound
- * ------------------------  -----------------------------------------------------  -------
- * prep_kernel               fold src/ts_pws1f_lib.c:76-86, mean removal :160-168   HBM
- * colsum_kernel             partial_linear_stacks src/ts_pws1f_lib.c:866-881       HBM  (headline)
- * group_post2_kernel        slot sums + mean / fold / mean split of the group sums   tiny
- * fwd_kernel                complex_1D_wavelet_dec src/FWTa/wavelet_v7.c:43-64 ->
- *                           cdotx_dc src/FWTa/cdotx.c:35-72, fused with the phasor
- *                           accumulate of src/ts_pws1f_lib.c:486-494 / :897-904    FP32/LSU
- * reduce_weight_kernel      tspws_biased / tspws_unbiased src/ts_pws1f_lib.c:909-984 tiny
- * inv_kernel / inv_finish   Re_complex_1D_wavelet_rec src/FWTa/wavelet_v7.c:124-150
- *                           -> re_cdotx_upsampling_cc / re_cdotx_cc
- *                           src/FWTa/cdotx.c:305-340, :176-211; cast :233-241      L2/LSU
+ * Kernel                       replaces (reference file:line)                            bound
+ * ---------------------------  --------------------------------------------------------  ---------
+ * prep_kernel                  fold src/ts_pws1f_lib.c:76-86, mean removal :160-168      HBM
+ * colsum2_kernel (colsum_kernel when N % 4 != 0)
+ *                              partial_linear_stacks src/ts_pws1f_lib.c:866-881          HBM (headline)
+ * group_post2_kernel<PEER>     slot sums + mean removal / fold (:76-86, :160-168 applied
+ *                              to the group sums) + fp64 mean split; PEER: the sum over
+ *                              the ranks of a node, read from blocks pushed over NVLink  latency
+ * peer_signal_kernel           step flag of the peer exchange                            latency
+ * fwd2_acc_kernel<LG>          complex_1D_wavelet_dec src/FWTa/wavelet_v7.c:43-64 ->
+ *   fwd2_pertrace_kernel         cdotx_dc src/FWTa/cdotx.c:35-72 (polyphase register
+ *   fwd_tail_kernel              tile, FFMA2), fused with the phasor accumulate of
+ *                                src/ts_pws1f_lib.c:486-494 / :897-904 (acc), or one
+ *                                coefficient set per trace (pertrace / tail)             FP32 issue
+ * fwd_f64_kernel / f64_cta_body  the same transform in fp64 for the group mean           issue
+ * fwd_kernel, fwd_pertrace_generic_kernel
+ *                              lane-split form for any geometry (D = 7, 15, 31 ..., fp64) LSU
+ * phasor_combine_kernel        tspws_stacks_double src/ts_pws1f_lib.c:885-906 + weights  latency
+ * reduce_weight_kernel, weight_* kernels
+ *                              tspws_biased / tspws_unbiased src/ts_pws1f_lib.c:909-984  tiny
+ * inv2_kernel, inv4_kernel, inv_finish_kernel (fp32); inv_kernel (fp64 / generic)
+ *                              Re_complex_1D_wavelet_rec src/FWTa/wavelet_v7.c:124-150
+ *                              -> re_cdotx_upsampling_cc / re_cdotx_cc
+ *                              src/FWTa/cdotx.c:305-340, :176-211; cast :233-241         L2 / issue
+ * regroup, group_total, coef_matrix, select_sum kernels
+ *                              tspws_subsmpl_float / TwoStage_subsmpl_float / jackknife
+ *                              src/ts_pws1f_lib.c:501-831                                 HBM / L2
+ * prefix_weight, simil, lsconv kernels
+ *                              convergence curves src/ts_pws1f_lib.c:247-314, :433-462    L2
  *
  * Everything is written from the mathematics in SURVEY.md Appendix A.
  */
