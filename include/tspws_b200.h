@@ -208,6 +208,10 @@ int tspws_b200_profile_read(char *buf, int cap);
 int  tspws_b200_load_sac_list(const char *listfile, t_data *in, int pinned);
 int  tspws_b200_load_bin(const char *binfile, t_data *in, int pinned);
 int  tspws_b200_save_bin(const char *binfile, const t_data *in, const char *method);
+/* resampled stacks as the reference's wrbin writes them (src/ts_pws1f.c:766-823): header | time_t[M] holding the
+ * traces behind every row | data[M][npts]; rows[m] + n0 is the first sample of row m */
+int  tspws_b200_save_rows_bin(const char *binfile, float *const *rows, unsigned int M, int n0, int npts, const t_hdr *hdr,
+                              float beg, const char *method, const unsigned int *traces_per_row);
 int  tspws_b200_write_sac(const char *path, const float *y, const t_hdr *hdr, int npts, float beg,
                           const char *kinst, float user0);
 long tspws_b200_read_sac(const char *path, float *data, long maxpts, float *dt, float *beg, void *header632);

@@ -103,3 +103,29 @@ def test_sac_writer_reader_round_trip(pkg, lib, tmp_path):
     assert lib.tspws_b200_read_sac(path, buf.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(dt), C.byref(beg), None) == n
     np.testing.assert_array_equal(buf, y)
     assert lib.tspws_b200_read_sac(b"/nonexistent.sac", None, 0, None, None, None) == -1
+
+
+def test_rows_bin_writer_layout(pkg, lib, tmp_path):
+    """Resampled stacks as the reference's wrbin writes them (src/ts_pws1f.c:766-823): 116-byte header,
+    time_t[M] holding the traces behind every row, float data[M][npts] -- and no lag0 block."""
+    import ctypes as C
+    x = np.random.default_rng(5).standard_normal((4, 301)).astype(np.float32)
+    hdr = pkg.Hdr()
+    hdr.max, hdr.mtr, hdr.dt, hdr.beg = 301, 77, 0.5, -75.0
+    rows = (C.POINTER(C.c_float) * 4)(*[x[i].ctypes.data_as(C.POINTER(C.c_float)) for i in range(4)])
+    k = np.array([40, 41, 42, 43], dtype=np.uint32)
+    lib.tspws_b200_save_rows_bin.restype = C.c_int
+    lib.tspws_b200_save_rows_bin.argtypes = [C.c_char_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.POINTER(pkg.Hdr),
+                                             C.c_float, C.c_char_p, C.c_void_p]
+    path = str(tmp_path / "rows.bin").encode()
+    n0, npts = 150, 151                                   # a folded stack keeps its second half
+    assert lib.tspws_b200_save_rows_bin(path, rows, 4, n0, npts, C.byref(hdr), C.c_float(0.0), b"ts_pws", k.ctypes.data) == 0
+    raw = open(path, "rb").read()
+    assert len(raw) == 116 + 4 * 8 + 4 * npts * 4
+    assert raw[:6] == b"ts_pws"
+    nlags, nseq = np.frombuffer(raw[96:104], dtype=np.uint32)
+    tlength, lag1, lag2 = np.frombuffer(raw[104:116], dtype=np.float32)
+    assert (nlags, nseq) == (npts, 4) and lag1 == 0.0 and tlength == lag2 == 0.5 * (npts - 1)
+    np.testing.assert_array_equal(np.frombuffer(raw[116:116 + 32], dtype=np.int64), k)
+    np.testing.assert_array_equal(np.frombuffer(raw[148:], dtype=np.float32).reshape(4, npts), x[:, n0:])
+    assert lib.tspws_b200_save_rows_bin(None, rows, 4, n0, npts, C.byref(hdr), C.c_float(0.0), b"x", None) != 0

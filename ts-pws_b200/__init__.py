@@ -201,7 +201,7 @@ EXPORTS = [
     "tspws_b200_get_option", "tspws_b200_device_count", "tspws_b200_shutdown", "tspws_b200_version",
     "tspws_b200_kernel_launches", "tspws_b200_profile", "tspws_b200_profile_reset", "tspws_b200_profile_read", "tspws_b200_plan_create", "tspws_b200_plan_destroy",
     "tspws_b200_plan_reduce", "tspws_b200_plan_exchange_ptr", "tspws_b200_plan_exchange_bytes",
-    "tspws_b200_load_sac_list", "tspws_b200_load_bin", "tspws_b200_save_bin", "tspws_b200_write_sac",
+    "tspws_b200_load_sac_list", "tspws_b200_load_bin", "tspws_b200_save_bin", "tspws_b200_save_rows_bin", "tspws_b200_write_sac",
     "tspws_b200_read_sac", "tspws_b200_free_data",
     "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_peer_export", "tspws_b200_plan_peer_import", "tspws_b200_plan_peer_error", "tspws_b200_plan_peer_close", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
     "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",

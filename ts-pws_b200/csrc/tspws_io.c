@@ -236,6 +236,31 @@ int tspws_b200_save_bin(const char *binfile, const t_data *in, const char *metho
     return 0;
 }
 
+/* M stacked rows -> the container the reference's wrbin writes for resampled stacks (src/ts_pws1f.c:766-823):
+ * header | time_t[M] (= traces behind every row) | float data[M][npts] -- NO lag0 block, unlike the files
+ * sac2bin produces.  rows[m] + n0 is the first sample written of row m. */
+int tspws_b200_save_rows_bin(const char *binfile, float *const *rows, unsigned int M, int n0, int npts, const t_hdr *hd,
+                             float beg, const char *method, const unsigned int *traces_per_row)
+{
+    if (!binfile || !rows || !hd || npts <= 0) return TSPWS_ERR_NULL;
+    tspws_ccheader_t b;
+    memset(&b, 0, sizeof(b));
+    strncpy(b.method, method ? method : "", 8);
+    memcpy(b.net1, hd->net1, 8); memcpy(b.sta1, hd->sta1, 8); memcpy(b.loc1, hd->loc1, 8); memcpy(b.chn1, hd->chn1, 8);
+    memcpy(b.net2, hd->net2, 8); memcpy(b.sta2, hd->sta2, 8); memcpy(b.loc2, hd->loc2, 8); memcpy(b.chn2, hd->chn2, 8);
+    b.stlat1 = hd->evla; b.stlon1 = hd->evlo; b.stlat2 = hd->stla; b.stlon2 = hd->stlo; b.stel2 = hd->stel;
+    b.nlags = (uint32_t)npts; b.nseq = M;
+    b.tlength = hd->dt * (float)(b.nlags - 1);
+    b.lag1 = beg; b.lag2 = b.lag1 + b.tlength;
+    FILE *f = fopen(binfile, "wb");
+    if (!f) return -2;
+    fwrite(&b, sizeof(b), 1, f);
+    for (unsigned int m = 0; m < M; m++) { const time_t t = (time_t)(traces_per_row ? traces_per_row[m] : 0); fwrite(&t, sizeof(t), 1, f); }
+    for (unsigned int m = 0; m < M; m++) fwrite(rows[m] + n0, sizeof(float), (size_t)npts, f);
+    fclose(f);
+    return 0;
+}
+
 /* One evenly sampled trace -> SAC file with the fields the reference's wrsac sets (src/ts_pws1f.c:725-763). */
 int tspws_b200_write_sac(const char *path, const float *y, const t_hdr *hd, int npts, float beg, const char *kinst, float user0)
 {
