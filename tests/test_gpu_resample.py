@@ -122,3 +122,12 @@ def test_single_stage_jackknife_extension(pkg, gpu_lib):
     o = O.tspws_main(O.Params(**{k: v for k, v in kw.items() if k in ("lrm", "fold", "wu", "unbiased", "type")}), x)
     ls, ts = O.subsample_single_stage(o["frame"], o["sigall"], sel, o["params"].wu, bool(o["params"].unbiased))
     assert O.nerr(r["tsPWS_subsmpl"], ts) <= TOL and O.nerr(r["ls_subsmpl"], ls) <= TOL
+
+
+def test_cli_resampling_and_convergence_outputs(gpu_lib):
+    """tspws_b200_cli with convergence / AllSteps, jackknife + obin and sub-sampling flags: the files it writes
+    (names and layouts of the reference CLI, src/ts_pws1f.c:354-418) equal tspws_main called directly."""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "cli_probe.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "CLI_PROBE_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
