@@ -282,7 +282,9 @@ def run_ours(args, wl, name):
         if not peer:
             if rank == 0:
                 print("[bench] peer exchange set-up failed on some rank: using the NCCL all-reduce path", file=sys.stderr)
-            lib.tspws_b200_plan_destroy(plan)           # a fresh plan without half-mapped peer state
+            lib.tspws_b200_plan_peer_close(plan)        # unmap on every rank, then free (CUDA IPC rule)
+            dist.barrier()
+            lib.tspws_b200_plan_destroy(plan)           # a fresh plan without peer state
             plan = lib.tspws_b200_plan_create(C.byref(p), n, mtr, mtr * world, rank * mtr)
             if not plan:
                 raise SystemExit("tspws_b200_plan_create failed")

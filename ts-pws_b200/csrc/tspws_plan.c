@@ -771,6 +771,10 @@ int tspws_b200_plan_peer_import(tspws_plan_t *pl, int rank, int world, const voi
     if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
     rc = 0;
 out:
+    if (rc && ptr)                                   /* failed half way: unmap what was mapped */
+        for (int r = 0; r < world; r++)
+            if (r != rank && ptr[r]) cudaIpcCloseMemHandle(ptr[r]);
+    if (rc) cudaGetLastError();
     free(ptr); free(blocks); free(flags);
     return rc;
 }
