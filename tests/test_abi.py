@@ -62,3 +62,24 @@ def test_version_and_options(pkg, lib):
     assert lib.tspws_b200_set_option(99, 0) != 0
     assert lib.tspws_b200_set_option(pkg.OPT_SS_JACKKNIFE, 1) == 0 and lib.tspws_b200_get_option(pkg.OPT_SS_JACKKNIFE) == 1
     assert lib.tspws_b200_set_option(pkg.OPT_SS_JACKKNIFE, 0) == 0
+
+
+def test_empty_input_is_a_no_op_before_any_cuda_call(pkg, lib):
+    """No traces (or no samples): the reference falls through its loops and returns 0
+    (src/ts_pws1f_lib.c:194); here that happens before CUDA is touched, so it also holds without a GPU.
+    The parameter block is still derived (mutated) like in the reference."""
+    import numpy as np
+    p = pkg.default_params(lrm=1)
+    out, dat = pkg.TsPWSOut(), pkg.Data()
+    x = np.zeros((1, 64), np.float32)
+    ls = np.full(64, 7.0, np.float32)
+    ts = np.full(64, 7.0, np.float32)
+    dat.sigall = x.ctypes.data_as(C.POINTER(C.c_float))
+    dat.hdr.max, dat.hdr.mtr, dat.hdr.dt, dat.hdr.beg = 64, 0, 1.0, -31.5
+    out.ls = ls.ctypes.data_as(C.POINTER(C.c_float))
+    out.tsPWS = ts.ctypes.data_as(C.POINTER(C.c_float))
+    assert lib.tspws_main(C.byref(p), C.byref(out), C.byref(dat)) == 0
+    assert (ls == 7.0).all() and (ts == 7.0).all()
+    assert p.J > 0 and p.V == 4                      # derived from nsamp = 64 although nothing was stacked
+    dat.hdr.max, dat.hdr.mtr = 0, 5
+    assert lib.tspws_main(C.byref(p), C.byref(out), C.byref(dat)) == 0
