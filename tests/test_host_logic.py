@@ -121,3 +121,37 @@ def test_jackknife_plans_match_oracle(lib):
     assert lib.tspws_b200_jackknife_plans(None, None, 3, 1, 2, 2) == 1
     z = np.zeros(3, dtype=np.int64)
     assert lib.tspws_b200_jackknife_plans(C.create_string_buffer(6), z.ctypes.data_as(C.POINTER(C.c_long)), 3, 1, 2, 2) == -2
+
+
+@pytest.mark.parametrize("kw", [dict(lrm=1), dict(type=-3, Kmax=2, unbiased=1, fold=1, wu=1.5),
+                                dict(w0set=1, Q=4.0, subsmpl_N=3, subsmpl_p=0.5), dict(fmin=0.02, J=3, jackknife_n=4, jackknife_d=1, Kmax=2)])
+def test_verbose_parameter_report_matches_reference_text(pkg, lib, capfd, kw):
+    """`verbose` prints the derived parameters (src/ts_pws1f_lib.c:126-151); scripts grep that text.  Ours is
+    printed before any CUDA call, so an empty stack (mtr = 0) shows it without a GPU; the reference prints the
+    same block ahead of its stacking loops."""
+    import ctypes as C
+    import numpy as np
+    from oracle import ref_lib as R
+    if not R.available():
+        pytest.skip("compiled reference missing")
+    ref = pkg.declare_reference(R.load())
+    libc = C.CDLL(None)
+    n = 96
+    x = np.random.default_rng(2).standard_normal((4, n)).astype(np.float32)
+
+    def report(which, mtr):
+        p = pkg.default_params(verbose=1, **kw)
+        if mtr:
+            pkg.call_tspws_main(which, x, p, times=np.arange(4, dtype=np.int64) * 86400 * 40 + 10**9)
+        else:
+            out, dat = pkg.TsPWSOut(), pkg.Data()
+            dat.sigall = x.ctypes.data_as(C.POINTER(C.c_float))
+            dat.hdr.max, dat.hdr.mtr, dat.hdr.dt, dat.hdr.beg = n, 0, 1.0, -(n - 1) / 2.0
+            assert which.tspws_main(C.byref(p), C.byref(out), C.byref(dat)) == 0
+        libc.fflush(None)
+        text = capfd.readouterr().out
+        a = text.index("Sequence length")
+        return text[a:text.index("\n\n", a)]
+
+    capfd.readouterr()
+    assert report(lib, 0) == report(ref, 4)
