@@ -155,3 +155,37 @@ def test_verbose_parameter_report_matches_reference_text(pkg, lib, capfd, kw):
 
     capfd.readouterr()
     assert report(lib, 0) == report(ref, 4)
+
+
+@pytest.mark.parametrize("beg,expect_fold", [(-47.5, 1), (-47.0, 0), (0.0, 0), (-47.74, 1), (-47.76, 1), (-60.0, 1)])
+def test_fold_rule_and_warning_match_reference(pkg, lib, capfd, beg, expect_fold):
+    """fold is honoured only when 2*beg + (max-1)*dt <= dt/2 in float arithmetic, else a warning is printed and the
+    flag cleared in the caller's block (src/ts_pws1f_lib.c:71-75) -- same decision, same text, same mutation."""
+    import ctypes as C
+    import numpy as np
+    from oracle import ref_lib as R
+    if not R.available():
+        pytest.skip("compiled reference missing")
+    ref = pkg.declare_reference(R.load())
+    libc = C.CDLL(None)
+    n = 96
+    x = np.random.default_rng(3).standard_normal((3, n)).astype(np.float32)
+
+    def run(which, mtr):
+        p = pkg.default_params(fold=1)
+        out, dat = pkg.TsPWSOut(), pkg.Data()
+        xx = x.copy()
+        ls, ts = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        dat.sigall = xx.ctypes.data_as(C.POINTER(C.c_float))
+        dat.hdr.max, dat.hdr.mtr, dat.hdr.dt, dat.hdr.beg = n, mtr, 1.0, beg
+        out.ls, out.tsPWS = ls.ctypes.data_as(C.POINTER(C.c_float)), ts.ctypes.data_as(C.POINTER(C.c_float))
+        out.N, out.mtr = n, mtr
+        assert which.tspws_main(C.byref(p), C.byref(out), C.byref(dat)) == 0
+        libc.fflush(None)
+        text = capfd.readouterr().out
+        return p.fold, [l for l in text.splitlines() if l.startswith("Warning")]
+
+    capfd.readouterr()
+    ours, theirs = run(lib, 0), run(ref, 3)
+    assert ours == theirs
+    assert ours[0] == expect_fold and (len(ours[1]) == 0) == bool(expect_fold)
