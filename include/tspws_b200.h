@@ -108,8 +108,9 @@ typedef struct {
 
 /* Replaces reference tspws_main (src/ts_pws1f_lib.h:104, body src/ts_pws1f_lib.c:48-352).
  * Same arguments, same mutation of *tspws (derived w0,V,b0,s0,J,fmin,fold), same outputs
- * and return convention (0 ok, -1 NULL argument, 4 allocation failure); additionally
- * TSPWS_ERR_CUDA (77) when the GPU path is unusable. Host buffers in, host buffers out. */
+ * and return convention (0 ok, -1 NULL argument, 4 allocation failure or unusable wavelet family);
+ * additionally TSPWS_ERR_CUDA (77) when the GPU path is unusable. Host buffers in, host buffers out.
+ * Wavelet types: the complex families -1, -2, -3 (all the reference's front-ends reach); others return 4. */
 int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in);
 
 /* Additive (BASELINE configs[4]): npairs independent stacks (station pairs) with one

@@ -189,3 +189,33 @@ def test_fold_rule_and_warning_match_reference(pkg, lib, capfd, beg, expect_fold
     ours, theirs = run(lib, 0), run(ref, 3)
     assert ours == theirs
     assert ours[0] == expect_fold and (len(ours[1]) == 0) == bool(expect_fold)
+
+
+@pytest.mark.parametrize("typ", [0, -4, -7])
+def test_unusable_wavelet_family_returns_4_like_the_reference(pkg, lib, capfd, typ):
+    """CreateWaveletFamily fails -> tspws_main returns 4 (src/ts_pws1f_lib.c:199-204), whatever the input."""
+    import ctypes as C
+    import numpy as np
+    from oracle import ref_lib as R
+    n = 96
+    x = np.random.default_rng(4).standard_normal((3, n)).astype(np.float32)
+
+    def run(which, mtr):
+        p = pkg.default_params(type=typ)
+        out, dat = pkg.TsPWSOut(), pkg.Data()
+        xx = x.copy()
+        ls, ts = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        dat.sigall = xx.ctypes.data_as(C.POINTER(C.c_float))
+        dat.hdr.max, dat.hdr.mtr, dat.hdr.dt, dat.hdr.beg = n, mtr, 1.0, -47.5
+        out.ls, out.tsPWS = ls.ctypes.data_as(C.POINTER(C.c_float)), ts.ctypes.data_as(C.POINTER(C.c_float))
+        out.N, out.mtr = n, mtr
+        rc = which.tspws_main(C.byref(p), C.byref(out), C.byref(dat))
+        C.CDLL(None).fflush(None)
+        return rc, capfd.readouterr().out.splitlines()[0]
+
+    capfd.readouterr()
+    ours = [run(lib, 0), run(lib, 3)]                 # decided before CUDA is needed
+    assert all(rc == 4 for rc, _ in ours)
+    if R.available():
+        theirs = run(pkg.declare_reference(R.load()), 3)
+        assert theirs[0] == 4 and theirs[1] == ours[0][1]      # same first error line

@@ -185,6 +185,15 @@ long tspws_b200_get_coherence(double *coh, size_t ncap)
     return rc;
 }
 
+static int tspws_check_family(const t_tsPWS *p)
+{
+    if (p->type <= -1 && p->type >= -3 && p->V) return 0;
+    if (p->type == 0)     printf("Error: CreateWaveletFamily: Wavelet type is 0.\n");
+    else if (p->type > 0) printf("Error: wavelet type %d: only the complex families (-1 Morlet, -2 exact Morlet, -3 Mexican hat) are supported.\n", p->type);
+    else                  printf("Error: CreateWaveletFamily: Complex wavelet not defined.\n");
+    return TSPWS_ERR_ALLOC;
+}
+
 /* ------------------------------------------------------------------------------------ */
 int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
 {
@@ -204,12 +213,12 @@ int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
     }
     tspws_b200_derive_params(tspws, nsamp, hdr->dt);
     if (tspws->verbose) tspws_print_params(tspws, nsamp, hdr->dt);
-    if (max <= 0 || !mtr) return 0;                               /* nothing to stack (src/ts_pws1f_lib.c:194) */
+    if (max <= 0) return 0;
+    /* the frame is built whatever the number of traces; an unusable family makes the reference return 4
+     * (pWF == NULL, src/ts_pws1f_lib.c:199-204).  Only the complex families of the ts-PWS are supported here. */
+    if ((nerr = tspws_check_family(tspws))) return nerr;
+    if (!mtr) return 0;                                           /* nothing to stack (src/ts_pws1f_lib.c:194) */
     if (!in->sigall || !out->ls || !out->tsPWS) { printf("tspws_main: NULL input\n"); return -1; }
-    if (tspws->type > -1 || tspws->type < -3 || !tspws->V) {
-        printf("Error: CreateWaveletFamily: Complex wavelet not defined.\n");
-        return TSPWS_ERR_ARG;
-    }
 
     if ((nerr = ensure_cuda())) return nerr;
     cudaStream_t st = G.stream;
@@ -315,12 +324,10 @@ int tspws_b200_main_batch(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsign
     }
     tspws_b200_derive_params(tspws, (unsigned int)max, hdr->dt);
     if (tspws->verbose) tspws_print_params(tspws, (unsigned int)max, hdr->dt);
+    int nerr = tspws_check_family(tspws);
+    if (nerr) return nerr;
     if (!mtr) return 0;
-    if (tspws->type > -1 || tspws->type < -3 || !tspws->V) {
-        printf("Error: CreateWaveletFamily: Complex wavelet not defined.\n");
-        return TSPWS_ERR_ARG;
-    }
-    int nerr = ensure_cuda();
+    nerr = ensure_cuda();
     if (nerr) return nerr;
     cudaGetLastError();                          /* a stale error of an earlier call must not fail this one */
 
