@@ -219,3 +219,91 @@ def test_unusable_wavelet_family_returns_4_like_the_reference(pkg, lib, capfd, t
     if R.available():
         theirs = run(pkg.declare_reference(R.load()), 3)
         assert theirs[0] == 4 and theirs[1] == ours[0][1]      # same first error line
+
+
+def test_parameter_derivation_equals_the_compiled_reference_on_a_random_grid(pkg, lib):
+    """src/ts_pws1f_lib.c:91-124 against our tspws_b200_derive_params, bit for bit, over 120 random parameter
+    blocks (wavelet type, w0 / Q / cycles, fmin with and without J, fixed V / s0 / b0, uniform sampling): the
+    reference mutates *tspws inside tspws_main, here run on a tiny two-trace input."""
+    from oracle import ref_lib as R
+    if not R.available():
+        pytest.skip("compiled reference missing")
+    ref = pkg.declare_reference(R.load())
+    rng = np.random.default_rng(2024)
+    checked = 0
+    for _ in range(120):
+        n = int(rng.choice([200, 256, 333, 500, 1000]))
+        dt = float(rng.choice([1.0, 0.5, 4.0, 0.025]))
+        kw = dict(type=int(rng.choice([-1, -1, -3, -2])))
+        mode = int(rng.integers(0, 5))
+        if kw["type"] != -3:
+            if mode == 1:
+                kw.update(w0set=1, Q=float(rng.uniform(2.5, 9.0)))
+            elif mode == 2:
+                kw.update(w0set=2, cycle=float(rng.uniform(1.5, 6.0)))
+            elif mode == 3:
+                kw.update(w0set=4, w0=float(rng.uniform(4.0, 12.0)))
+        if rng.random() < 0.4:
+            kw["fmin"] = float(rng.uniform(1.5, 12.0) / (dt * n))
+            if rng.random() < 0.5:
+                kw["J"] = int(rng.integers(1, 4))
+        elif rng.random() < 0.3:
+            kw["J"] = int(rng.integers(1, 4))
+        if rng.random() < 0.2:
+            kw.update(V=int(rng.integers(1, 7)), lVfix=1)
+        if rng.random() < 0.2:
+            kw.update(s0=float(rng.uniform(1.0, 4.0)), ls0fix=1)
+        if rng.random() < 0.15:
+            kw.update(b0=float(rng.choice([0.5, 1.0, 2.0])), lb0fix=1)
+        if rng.random() < 0.15:
+            kw["uni"] = 1
+        ours = pkg.default_params(**kw)
+        assert lib.tspws_b200_derive_params(C.byref(ours), n, dt) == 0
+        if ours.J == 0 or ours.J > 7 or ours.V == 0:      # keep the reference's CPU run tiny and well defined
+            continue
+        x = rng.standard_normal((2, n)).astype(np.float32)
+        r = pkg.call_tspws_main(ref, x, pkg.default_params(**kw), dt=dt)
+        if r["rc"] != 0:
+            continue
+        theirs = r["params"]
+        for f in ("J", "V", "s0", "b0", "w0", "fmin", "fold", "w0set"):
+            assert getattr(ours, f) == getattr(theirs, f), (kw, n, dt, f, getattr(ours, f), getattr(theirs, f))
+        checked += 1
+    assert checked >= 60
+
+
+def test_frame_equals_the_compiled_reference_on_a_random_grid(pkg, lib):
+    """tspws_b200_frame_create against the reference's CreateWaveletFamily (src/FWTa/wavelet_def_v7.c:204-339)
+    over 40 random frames: scales, lengths, centres, decimations bit-equal, filters and Cpsi to 1e-13."""
+    from oracle import ref_lib as R
+    if not R.available():
+        pytest.skip("compiled reference missing")
+    rng = np.random.default_rng(77)
+    for _ in range(40):
+        typ = int(rng.choice([-1, -2, -3]))
+        N = int(rng.choice([257, 400, 512, 1000, 1501]))
+        V = int(rng.integers(1, 6))
+        J = int(rng.integers(1, 6))
+        s0 = float(rng.choice([1.0, 2.0, 2.5, 4.0]))
+        b0 = float(rng.choice([0.0, 0.5, 1.0, 2.0]))
+        w0 = math.sqrt(2.0) if typ == -3 else float(rng.uniform(4.0, 9.0))
+        uni = int(rng.random() < 0.2)
+        rf = R.RefFrame(typ, J, V, N, s0, b0, w0, uni)
+        fr = lib.tspws_b200_frame_create(typ, J, V, N, s0, b0, w0, uni)
+        assert fr
+        try:
+            d = pkg.frame_to_dict(fr)
+        finally:
+            lib.tspws_b200_frame_destroy(fr)
+        try:
+            assert d["S"] == rf.S
+            np.testing.assert_array_equal(d["L"], rf.L)
+            np.testing.assert_array_equal(d["center"], rf.center)
+            np.testing.assert_array_equal(d["D"], rf.D)
+            np.testing.assert_array_equal(d["Ns"], rf.Ns)
+            np.testing.assert_array_equal(d["scale"], rf.scale)
+            assert abs(d["Cpsi"] - rf.Cpsi) <= 1e-13 * abs(rf.Cpsi)
+            wr = np.concatenate(rf.w)
+            assert np.max(np.abs(d["w"] - wr)) <= 1e-13 * np.max(np.abs(wr)), (typ, J, V, N, s0, b0, w0, uni)
+        finally:
+            rf.close()
