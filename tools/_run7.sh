@@ -1,0 +1,8 @@
+cd /root/repo
+export TSPWS_FUSED_COMBINE=0
+for i in 1 2; do
+echo "== r1 lib"; TSPWS_LIB=tools/_r1/libtspws_b200.so timeout 300 python tools/quick_bench.py ts 2>&1 | tail -1
+echo "== new lib"; timeout 300 python tools/quick_bench.py ts 2>&1 | tail -1
+done
+echo "== timeline (graph replay, new lib, TL build)"
+TSPWS_LIB=tools/_tl/libtspws_b200.so TSPWS_TIMELINE=gpurun_out/tl_all.txt timeout 300 python tools/quick_bench.py ts 2>&1 | tail -1

@@ -6,7 +6,7 @@ import importlib.util
 _root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _spec = importlib.util.spec_from_file_location("ts_pws_b200", os.path.join(_root, "ts-pws_b200", "__init__.py"))
 B = importlib.util.module_from_spec(_spec); sys.modules["ts_pws_b200"] = B; _spec.loader.exec_module(B)
-lib = B.load_library()
+lib = B.load_library(os.environ.get('TSPWS_LIB') or None)
 
 def run(name, mtr, n, reps=5, **kw):
     p = B.default_params(**kw)

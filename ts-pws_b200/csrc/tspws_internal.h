@@ -41,6 +41,8 @@ typedef struct {
     int   inv2;      /* 1: eligible                                   */
     int   Qi;        /* taps per phase = ceil(Li4 / D)                 */
     int   gi_off;    /* offset of gi in the reversed filter array      */
+    int   tile0;     /* first 64-coefficient tile of this scale in the tile list (tickets of the fused combine) */
+    int   pad0;
     double gain;     /* synthesis gain ln2/(2 Cpsi V scale) * D       */
 } tspws_scale_t;
 
@@ -63,7 +65,8 @@ typedef struct {
     int m0;          /* first coefficient                                  */
     int pb0, pb1;    /* blocks of 32 phases [pb0,pb1) (D >= 32), else 0,1  */
     int split;       /* partial-Y slot written in per-trace mode           */
-    int pad[3];
+    int base;        /* ((m0 - A) D) mod N: sample of (tile 0, tap 0, phase 0), so the kernel needs no 64-bit modulo */
+    int pad[2];
 } tspws_fwd2_item_t;
 
 /* ---- inverse-transform work split: scales [s0,s1) ---- */
@@ -97,11 +100,13 @@ typedef struct {
     int                nitems2;
     int                fw_lg_begin[7]; /* items2 are sorted by lg: items of lg are [begin[lg], begin[lg+1]) */
     int                fw_smem_per_warp; /* floats of warp-private staging smem of the polyphase kernel */
+    int                fw_gmax;   /* float2: most filter taps one pass of the polyphase kernel reads (CTA-shared copy) */
     int                per_trace; /* item list built for per-trace (partial-Y) mode */
     int                ypart_len; /* partial-Y scratch length per trace (complex)   */
     int                max_Ns;
     int               *d_tile16;  /* [ntile16][2]: (scale, first coefficient) of every 16-coefficient tile */
     int                ntile16;
+    int               *d_tile_expect; /* [ntile16][2]: writers of a tile in fwd_tail_kernel: fp32 items (x traces), fp64 items */
     tspws_inv_group_t *d_invgrp;  /* [ninv]  scale groups of the fp64 inverse                       */
     int                ninv;
     tspws_inv_group_t *d_invgrp4; /* [ninv4] one group per scale the polyphase inverse does not cover */
@@ -174,8 +179,11 @@ int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *
                               int ntile, int do_rm, int do_fold, int split, double *d_gsum,
                               float *d_out32, double *d_gmean, void *d_regions, double *d_own, const unsigned int *d_flags,
                               unsigned int *d_step, unsigned int *d_err, int rank, int world, tspws_stream_t st);
+/* d_tickets != NULL ([f->ntile16] zeroed counters): the phasor combine is fused in (PS, ST, Zout written by
+ * the warp that completes a coefficient tile); NULL: per-trace coefficients only, tspws_cu_phasor_combine follows */
 int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
-                          const double *d_x64, void *d_y64, tspws_stream_t st);
+                          const double *d_x64, void *d_y64, unsigned int *d_tickets, const tspws_weight_t *d_rule,
+                          void *d_ps, void *d_st, void *d_zout, tspws_stream_t st);
 /* long_row0 > 0: scales with L >= f->f64_maxl read their traces from row long_row0 on (mean split) */
 int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
                               tspws_stream_t st);

@@ -127,6 +127,72 @@ extern "C" int tspws_cu_profile_read(char *buf, int cap)
         if (e__ != cudaSuccess) return (int)e__;      \
     } while (0)
 
+/* ---- per-CTA timeline of the tail kernels (diagnostics, TSPWS_TIMELINE=file): every CTA of an instrumented
+ * kernel records (start ns, end ns, SM) of %globaltimer; dumped after the inverse launch.  Off: one
+ * uniform load and a predicated-off branch per CTA. ---- */
+#ifdef TSPWS_TIMELINE_BUILD        /* make EXTRA=-DTSPWS_TIMELINE_BUILD: never in the product build */
+#define TL_MAXK 8
+#define TL_MAXCTA 4096
+__device__ unsigned long long *g_tl_dev = nullptr;
+static unsigned long long *g_tl_host = nullptr;       /* device buffer [TL_MAXK][TL_MAXCTA][4] */
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct tl_scope {
+    unsigned long long *p;
+    __device__ __forceinline__ tl_scope(const int kid)
+    {
+        unsigned long long *base = g_tl_dev;
+        p = nullptr;
+        if (base) {
+            const unsigned int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+            if (cta < TL_MAXCTA) {
+                p = base + ((size_t)kid * TL_MAXCTA + cta) * 4;
+                if (threadIdx.x == 0) {
+                    unsigned int smid;
+                    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                    p[0] = gtimer(); p[2] = smid; p[3] = 1;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ ~tl_scope() { if (p && (threadIdx.x & 31) == 0) atomicMax(p + 1, gtimer()); }
+};
+static void tl_host_init(cudaStream_t s)
+{
+    static int tried = 0;
+    if (!tried) {
+        tried = 1;
+        if (getenv("TSPWS_TIMELINE") && cudaMalloc((void **)&g_tl_host, (size_t)TL_MAXK * TL_MAXCTA * 4 * sizeof(unsigned long long)) == cudaSuccess)
+            cudaMemcpyToSymbol(g_tl_dev, &g_tl_host, sizeof g_tl_host);
+    }
+    if (g_tl_host) cudaMemsetAsync(g_tl_host, 0, (size_t)TL_MAXK * TL_MAXCTA * 4 * sizeof(unsigned long long), s);
+}
+static void tl_host_dump(cudaStream_t s)
+{
+    if (!g_tl_host) return;
+    const size_t n = (size_t)TL_MAXK * TL_MAXCTA * 4;
+    unsigned long long *h = (unsigned long long *)malloc(n * sizeof *h);
+    if (h && cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(h, g_tl_host, n * sizeof *h, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        FILE *fp = fopen(getenv("TSPWS_TIMELINE"), "w");
+        if (fp) {
+            for (size_t i = 0; i < n; i += 4)
+                if (h[i + 3]) fprintf(fp, "%d %d %llu %llu %llu\n", (int)(i / 4 / TL_MAXCTA), (int)(i / 4 % TL_MAXCTA), h[i], h[i + 1], h[i + 2]);
+            fclose(fp);
+        }
+    }
+    free(h);
+    (void)s;
+}
+#else
+struct tl_scope { __device__ __forceinline__ tl_scope(const int) {} };
+static void tl_host_init(cudaStream_t) {}
+static void tl_host_dump(cudaStream_t) {}
+#endif
+
 template <typename T> struct cplx;
 template <> struct cplx<float>  { typedef float2  type; };
 template <> struct cplx<double> { typedef double2 type; };
@@ -334,6 +400,7 @@ __global__ void __launch_bounds__(CS_THREADS, 4)
 colsum2_kernel(const float *__restrict__ x, int N, const int4 *__restrict__ parts, const int *__restrict__ grp_t0,
                double *__restrict__ slots, double *__restrict__ slot_tot, int ntile)
 {
+    tl_scope tls(0);
     __shared__ double sh[33];
     const int4 pi = parts[blockIdx.y];
     const int  col = blockIdx.x * CS_TILE + threadIdx.x * 4;
@@ -375,6 +442,7 @@ extern "C" int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts, in
 {
     if (nparts <= 0) return 0;
     if ((N & 3) || ((uintptr_t)d_x & 15)) return (int)cudaErrorInvalidValue;
+    tl_host_init((cudaStream_t)st);
     dim3 grid(ntile, nparts);
     colsum2_kernel<<<grid, CS_THREADS, 0, (cudaStream_t)st>>>(d_x, N, (const int4 *)d_parts, d_grp_t0, d_slots, d_slot_tot, ntile);
     TSPWS_LAUNCHED_N("colsum2_kernel", (cudaStream_t)st);
@@ -432,6 +500,7 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
                    double *__restrict__ gsum, double *__restrict__ gtile, float *__restrict__ out32, double *__restrict__ gmean,
                    const tspws_peer_args pa, const double inv_n, const double inv_k)
 {
+    tl_scope tls(1);
     extern __shared__ double s_c[];                      /* [K] group-mean corrections, then [K][world] presence bytes */
     __shared__ double s_m[GP2_LANES][32];
     unsigned char *s_pres = reinterpret_cast<unsigned char *>(s_c + K);
@@ -809,8 +878,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
  *   loadx(j): window sample j of the current 32-tap block (j is a compile-time constant after
  *   unrolling, so addresses are immediates), loadg(q): filter tap q of the block, advance(): step
  *   both to the next 32-tap block.  Qs is a multiple of 4 (the host pads the filters with zero
- *   taps), the window source holds Qs + 32 samples and the filter array Qs + 8 taps, so only one
- *   uniform guard per 4 taps remains.
+ *   taps), the window source holds Qs + 16 samples (exactly what the taps reach) and the filter array
+ *   Qs + 8 taps; window loads and refills are guarded per group of 4 with uniform predicates.
  * The window lives in a 32-slot register ring (slot = j mod 32): every index is static after
  * unrolling 32 taps; a slot is refilled right after its last use, 16 taps before it is needed again,
  * filter taps 4 taps ahead -- loads never stall the FMAs.
@@ -821,26 +890,33 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #define FW_GQ5 4          /* filter taps in flight per lane when D >= 32; 8 measured no faster (450 vs 462 us, 64 traces) */
 #endif
 template <int GQ, typename LoadX, typename LoadG, typename Advance>
-__device__ __forceinline__ void fw_taps(float2 (&acc)[FW_R], const int Qs, LoadX loadx, LoadG loadg, Advance advance)
+__device__ __forceinline__ void fw_taps(float2 (&acc)[FW_R], const int Qs, const int Qw, LoadX loadx, LoadG loadg, Advance advance)
 {
     float2 win[FW_WS];
     float2 gq[GQ];
+    /* only the Qs + FW_R - 1 window samples the taps reach are loaded (groups of 4; Qs % 4 == 0); Qw = Qs,
+     * or Qs + 16 when the full ring is staged */
 #pragma unroll
-    for (int j = 0; j < FW_WS; j++) { const float t = loadx(j); win[j] = make_float2(t, t); }
+    for (int j = 0; j < FW_WS; j += 4) {
+        if (j < Qw + FW_R) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const float t = loadx(j + u); win[j + u] = make_float2(t, t); }
+        }
+    }
 #pragma unroll
     for (int q = 0; q < GQ; q++) gq[q] = loadg(q);
     for (int t0 = 0; t0 < Qs; t0 += FW_WS) {
 #pragma unroll
         for (int tq = 0; tq < FW_WS; tq += 4) {
             if (t0 + tq < Qs) {
+                const bool refill = t0 + tq + FW_R < Qw;        /* sample t0 + tq + u + 32 is still needed */
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int tt = tq + u;
                     const float2 gv = gq[tt & (GQ - 1)];
 #pragma unroll
                     for (int r = 0; r < FW_R; r++) acc[r] = __ffma2_rn(win[(tt + r) % FW_WS], gv, acc[r]);
-                    const float t = loadx(tt + FW_WS);
-                    win[tt]    = make_float2(t, t);
+                    if (refill) { const float t = loadx(tt + FW_WS); win[tt] = make_float2(t, t); }
                     gq[tt & (GQ - 1)] = loadg(tt + GQ);
                 }
             }
@@ -890,33 +966,27 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
 #pragma unroll
     for (int i = 0; i < NVAL; i++) { ps[i] = 0.f; st[i] = 0.f; }
 
-    long long b0 = ((long long)(it.m0 - sc.A) * D) % N;
-    if (b0 < 0) b0 += N;
-    const int base = (int)b0;                      /* sample of (tile 0, tap 0, phase 0)     */
+    const int base = it.base;                      /* sample of (tile 0, tap 0, phase 0), computed on the host */
+    const int Qw = Qs;
 
-    /* LG < 5: D = 2^LG phases x (32 >> LG) tiles; window staged by cp.async, double buffered.
-     * 32 samples more than needed are staged so that the register ring refills need no guard. */
-    const int  W      = (TILES * FW_R + Qs + FW_WS) * LP;
+    /* LG < 5: D = 2^LG phases x (32 >> LG) tiles; window staged by cp.async, double buffered:
+     * exactly the (TILES - 1) 16 + Qs + 16 samples per phase the taps reach. */
+    const int  W      = (TILES * FW_R + Qw) * LP;
     const bool vec_ok = (N % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    if (LG < 5) {
-        __syncwarp();
-        fw_stage<LGS>(xs, x + (size_t)k_begin * N, base, W, N, lane, vec_ok);
-        cp_async_commit();
-    }
-
-    /* LG == 5: per (trace, block of 32 phases) the Qs+15 window rows of 32 consecutive samples are
+    /* LG == 5: per (trace, block of 32 phases) the Qs + 16 window rows of 32 consecutive samples are
      * staged by cp.async into a warp-private double buffer one pass ahead (16-byte copies when the
-     * geometry allows), so the FMA loop only ever waits on shared memory. */
+     * geometry allows), so the FMA loop only ever waits on shared memory.  (One 128-byte bulk copy per
+     * row -- cp.async.bulk on an mbarrier -- was measured slower: the copy engine is rate-bound on small copies.) */
     const int npb = it.pb1 - it.pb0;
-    const int nrows = Qs + FW_WS;                 /* the register ring reads 32 rows ahead, unguarded */
+    const int nrows = Qw + FW_R;
     const bool vec5 = vec_ok && (D % 4 == 0);
+    const int GS = (D + 31) & ~31;
     auto stage5 = [&](float *buf, const int k, const int pb) {
         const float *__restrict__ xk = x + (size_t)k * N;
         if (vec5) {
             int row = lane >> 3;
             const int q4 = (lane & 7) * 4;
-            long long p0 = ((long long)base + pb * 32 + q4 + (long long)row * D) % N;
-            int pos = (int)p0;
+            int pos = (int)(((long long)base + pb * 32 + q4 + (long long)row * D) % N);
             const int step = (int)((4LL * D) % N);
             for (; row < nrows; row += 4) {
                 cp_async<16>(buf + row * 32 + q4, xk + pos);
@@ -933,6 +1003,11 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
             }
         }
     };
+    if (LG < 5) {
+        __syncwarp();
+        fw_stage<LGS>(xs, x + (size_t)k_begin * N, base, W, N, lane, vec_ok);
+        cp_async_commit();
+    }
     if (LG == 5) {
         __syncwarp();
         stage5(xs, k_begin, it.pb0);
@@ -959,7 +1034,7 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
             const int a = lane >> LGS, rho = lane & (LP - 1);
             const float  *xb = cur + a * ((FW_R + 1) * LP) + rho;      /* sample j of the block at (j + (j >> 4)) LP */
             const float2 *gb = g + rho;
-            fw_taps<4>(acc, Qs,
+            fw_taps<4>(acc, Qs, Qw,
                     [&](const int j) { return xb[(j + (j >> 4)) * LP]; },
                     [&](const int q) { return __ldg(gb + q * LP); },
                     [&]() { xb += 34 * LP; gb += 32 * LP; });
@@ -967,7 +1042,6 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
         } else {
             /* D >= 32: 32 consecutive phases per block; the filter rows are zero-padded to a multiple
              * of 32 phases, so idle lanes add zeros */
-            const int GS = (D + 31) & ~31;
             for (int pb = it.pb0; pb < it.pb1; pb++, pass++) {
                 const float *cur = xs + (pass & 1) * xs_half;
                 int kn = k, pbn = pb + 1;
@@ -982,7 +1056,7 @@ fwd2_body(const tspws_scale_t &sc, const tspws_fwd2_item_t &it, const float2 *__
                 __syncwarp();
                 const float  *xb = cur + lane;
                 const float2 *gp = g + pb * 32 + lane;                  /* taps are consumed strictly in order */
-                fw_taps<FW_GQ5>(acc, Qs,
+                fw_taps<FW_GQ5>(acc, Qs, Qw,
                         [&](const int j) { return xb[j * 32]; },
                         [&](const int) { const float2 v = __ldg(gp); gp += GS; return v; },
                         [&]() { xb += 32 * 32; });
@@ -1063,7 +1137,7 @@ fwd2_acc_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restri
                 const float *__restrict__ x, int N, int ntr, int chunk, int ncoef,
                 float2 *__restrict__ part_ps, float2 *__restrict__ part_st, int smem_per_warp, int cb)
 {
-    extern __shared__ float fw_smem[];
+    extern __shared__ __align__(128) float fw_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     /* 1-D grid, two-level order: the chunks are taken in super-blocks of `cb` chunks whose traces fit
      * in L2 together; inside a super-block the chunk index runs fastest (CTAs running together share
@@ -1095,7 +1169,7 @@ fwd2_pertrace_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__r
                      const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len,
                      int smem_per_warp, int ntr, int tchunk, int long_L, int long_row0)
 {
-    extern __shared__ float fw_smem[];
+    extern __shared__ __align__(128) float fw_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     /* blockIdx.x = run of tchunk traces (fastest): the traces of one item run together -> one code
      * variant and one set of filter rows live at a time.  Inside a run the item set-up (scale record,
@@ -1300,27 +1374,150 @@ fwd_f64_kernel(const tspws_scale_t *__restrict__ scales, const double2 *__restri
                       out + (size_t)blockIdx.y * out_ld, (size_t)gridDim.y * out_ld, (int)blockIdx.x, sh);
 }
 
-/* Mean-split tail in ONE launch: the fp64 transform of the group mean (CTAs [0, nf64), one trace) and
- * the fp32 per-trace transforms of the residuals (the rest: run of traces fastest, then item group).
- * Launched separately the two kernels exclude each other -- either one fills the register files -- and
+/* ---- fused phasor combine of the tail (src/ts_pws1f_lib.c:897-904 + :909-984 in the same launch) ----
+ * Every writer of per-trace coefficients (fp32 item x trace, fp64 mean item) takes a ticket on each
+ * 64-coefficient tile it wrote into; the writer that completes a tile combines it right away: sum of the
+ * phase / tap splits + mean -> unit phasors -> PS, ST, weights, (Zout, ST) for the inverse.  The partial
+ * coefficients make an L2 round trip only (never HBM), and no separate combine launch follows. */
+struct tspws_tailfuse_t {
+    const int4 *tiles;            /* (ypart offset, coefficient offset, nvalid | nsplit << 8 | nsp64 << 16, Ns) */
+    const int2 *expect;           /* writers of a tile: (fp32 items, fp64 items) */
+    unsigned int *tickets;        /* [ntile], zero between launches (the last writer re-arms) */
+    const tspws_weight_t *rule;
+    float2 *ps, *st, *zout;
+    int ncoef;
+};
+
+/* all lanes have written; returns true in the warp that completes the tile (uniform) */
+__device__ __forceinline__ bool ticket_arrive(unsigned int *tk, const unsigned int expect, const int lane)
+{
+    __threadfence();                                   /* every lane publishes its own stores */
+    __syncwarp();
+    unsigned int old = 0;
+    if (lane == 0) old = atomicAdd(tk, 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    const bool last = (old + 1u == expect);
+    if (last) {
+        if (lane == 0) *tk = 0;                        /* re-arm for the next launch */
+        __threadfence();
+    }
+    return last;
+}
+
+__device__ __forceinline__ void tail_combine_tile(const int4 tile, const float2 *__restrict__ ypart, const int ypart_len,
+                                                  const int ntr, const double2 *__restrict__ ymean, const tspws_tailfuse_t &fz,
+                                                  const int lane)
+{
+    const int nvalid = tile.z & 255, nsplit = (tile.z >> 8) & 255, nsp64 = tile.z >> 16, Ns = tile.w;
+    const tspws_weight_t rule = *fz.rule;
+    /* lane owns coefficients lane and lane + 32 of the tile; the loads of both and of several traces are in flight together */
+    const int  c0 = lane, c1 = lane + 32;
+    const bool v0 = c0 < nvalid, v1 = c1 < nvalid;
+    const int  i0 = v0 ? c0 : 0, i1 = v1 ? c1 : 0;
+    double m0r = 0.0, m0i = 0.0, m1r = 0.0, m1i = 0.0;
+    for (int sp = 0; sp < nsp64; sp++) {                /* tap splits of the fp64 mean transform, in slot order */
+        const double2 a = __ldcg(ymean + (size_t)sp * fz.ncoef + tile.y + i0);
+        const double2 b = __ldcg(ymean + (size_t)sp * fz.ncoef + tile.y + i1);
+        m0r += a.x; m0i += a.y; m1r += b.x; m1i += b.y;
+    }
+    float  p0r = 0.f, p0i = 0.f, p1r = 0.f, p1i = 0.f;
+    double s0r = 0.0, s0i = 0.0, s1r = 0.0, s1i = 0.0;
+    const float2 *yp = ypart + tile.x;
+    if (nsplit == 1) {
+#pragma unroll 5
+        for (int k = 0; k < ntr; k++) {
+            const float2 a = __ldcg(yp + (size_t)k * ypart_len + i0);
+            const float2 b = __ldcg(yp + (size_t)k * ypart_len + i1);
+            const double ar = (double)a.x + m0r, ai = (double)a.y + m0i, br = (double)b.x + m1r, bi = (double)b.y + m1i;
+            float u, v;
+            phasor_fast((float)ar, (float)ai, u, v); p0r += u; p0i += v; s0r += ar; s0i += ai;
+            phasor_fast((float)br, (float)bi, u, v); p1r += u; p1i += v; s1r += br; s1i += bi;
+        }
+    } else {
+        for (int k = 0; k < ntr; k++) {
+            const float2 *y = yp + (size_t)k * ypart_len;
+            float are = 0.f, aim = 0.f, bre = 0.f, bim = 0.f;
+#pragma unroll 8
+            for (int sp = 0; sp < nsplit; sp++) {
+                const float2 a = __ldcg(y + (size_t)sp * Ns + i0);
+                const float2 b = __ldcg(y + (size_t)sp * Ns + i1);
+                are += a.x; aim += a.y; bre += b.x; bim += b.y;
+            }
+            const double ar = (double)are + m0r, ai = (double)aim + m0i, br = (double)bre + m1r, bi = (double)bim + m1i;
+            float u, v;
+            phasor_fast((float)ar, (float)ai, u, v); p0r += u; p0i += v; s0r += ar; s0i += ai;
+            phasor_fast((float)br, (float)bi, u, v); p1r += u; p1i += v; s1r += br; s1i += bi;
+        }
+    }
+    if (v0) {
+        const double f = weight_factor(rule, (double)p0r, (double)p0i);
+        const size_t o = (size_t)tile.y + c0;
+        fz.ps[o] = make_float2(p0r, p0i);
+        fz.st[o] = make_float2((float)s0r, (float)s0i);
+        reinterpret_cast<float4 *>(fz.zout)[o] = make_float4((float)(s0r * f), (float)(s0i * f), (float)s0r, (float)s0i);
+    }
+    if (v1) {
+        const double f = weight_factor(rule, (double)p1r, (double)p1i);
+        const size_t o = (size_t)tile.y + c1;
+        fz.ps[o] = make_float2(p1r, p1i);
+        fz.st[o] = make_float2((float)s1r, (float)s1i);
+        reinterpret_cast<float4 *>(fz.zout)[o] = make_float4((float)(s1r * f), (float)(s1i * f), (float)s1r, (float)s1i);
+    }
+}
+
+/* Mean-split tail in ONE launch: the fp64 transform of the group mean (CTAs [0, nf64), one trace), the fp32
+ * per-trace transforms of the residuals (the rest: trace fastest, then item group) and -- when fz.tickets
+ * is set -- the phasor combine of every coefficient tile by the warp that completes it.
+ * Launched separately the two transforms exclude each other -- either one fills the register files -- and
  * their times add; in one grid their CTAs share the SMs and the issue slots. */
-__global__ void __launch_bounds__(FW_WARPS * 32, FW_PT_MINB)
-fwd_tail_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
+/* Mean-split tail in ONE launch: the fp64 transform of the group mean (one trace), the fp32 per-trace
+ * transforms of the residuals (trace fastest, then item group) and -- when fz.tickets is set -- the phasor
+ * combine of every coefficient tile by the warp that completes it.
+ * Launched separately the two transforms exclude each other -- either one fills the register files -- and
+ * their times add; in one grid their CTAs share the SMs and the issue slots.
+ * CTA order = longest first: the item groups with D >= 32 (coarsest scale first: up to 8 blocks of 32 phases
+ * per item), then the fp64 CTAs, then the single-pass D < 32 groups.  Measured with the per-CTA timeline
+ * (profiles/): the heavy CTAs (12..20 us each) otherwise start at 40 % of the grid and finish alone. */
+__device__ __forceinline__ void
+fwd_tail_cta(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
                 const tspws_fwd2_item_t *__restrict__ items, int nitems,
                 const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len,
                 int smem_per_warp, int ntr, int long_L, int long_row0,
                 const double2 *__restrict__ w64, const tspws_fwd_item_t *__restrict__ items64, int nitems64, int nshort_cta,
-                const int2 *__restrict__ coefs64, int nf64, const double *__restrict__ x64, double2 *__restrict__ y64, int y64_ld)
+                const int2 *__restrict__ coefs64, int nf64, const double *__restrict__ x64, double2 *__restrict__ y64, int y64_ld,
+                const tspws_tailfuse_t &fz, const int g5, float *fw_smem, double (*sh64)[2 * F64_R])
 {
-    extern __shared__ float fw_smem[];
-    __shared__ double sh64[FW_WARPS][2 * F64_R];
-    if ((int)blockIdx.x < nf64) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngrp = (nitems + FW_WARPS - 1) / FW_WARPS;
+    const int nheavy = (ngrp - g5) * ntr;                  /* CTAs of the groups [g5, ngrp) */
+    int bid = blockIdx.x, b;
+    if (bid < nheavy) b = g5 * ntr + bid;
+    else if (bid < nheavy + nf64) b = -1 - (bid - nheavy);
+    else b = bid - nheavy - nf64;
+    if (b < 0) {
+        const int fb = -1 - b;
         f64_cta_body<FW_WARPS * 32>(scales, w64, items64, nitems64, nshort_cta, coefs64, x64, N, y64, (size_t)y64_ld,
-                                    (int)blockIdx.x, sh64);
+                                    fb, sh64);
+        if (!fz.tickets) return;
+        if (fb < nshort_cta) {
+            const int witem = fb * FW_WARPS + w;
+            if (witem >= nitems64) return;
+            const tspws_fwd_item_t it = items64[witem];
+            const int tile0 = scales[it.s].tile0;
+            for (int t = tile0 + it.m0 / 64; t <= tile0 + (it.m0 + it.nout - 1) / 64; t++) {
+                const int2 e = fz.expect[t];
+                if (ticket_arrive(fz.tickets + t, (unsigned int)(e.x * ntr + e.y), lane))
+                    tail_combine_tile(fz.tiles[t], ypart, ypart_len, ntr, y64, fz, lane);
+            }
+        } else if (w == 0) {                               /* the coefficients were stored by threads of warp 0 */
+            const int2 cm = coefs64[fb - nshort_cta];
+            const int t = scales[cm.x & 0xffff].tile0 + cm.y / 64;
+            const int2 e = fz.expect[t];
+            if (ticket_arrive(fz.tickets + t, (unsigned int)(e.x * ntr + e.y), lane))
+                tail_combine_tile(fz.tiles[t], ypart, ypart_len, ntr, y64, fz, lane);
+        }
         return;
     }
-    const int b = blockIdx.x - nf64;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int idx = (b / ntr) * FW_WARPS + w;
     if (idx >= nitems) return;
     const tspws_fwd2_item_t it = items[idx];
@@ -1336,6 +1533,32 @@ fwd_tail_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restri
     case 4: fwd2_body<4, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
     default: fwd2_body<5, true>(sc, it, g_all, x, N, k, k + 1, 0, 0, nullptr, nullptr, ypart, ypart_len, xs, smem_per_warp / 2, lane); break;
     }
+    if (!fz.tickets) return;
+    {
+        const int per_item = sc.lg < 5 ? (512 >> sc.lg) : FW_R;
+        const int mend = min(it.m0 + per_item, sc.Ns) - 1;
+        for (int t = sc.tile0 + it.m0 / 64; t <= sc.tile0 + mend / 64; t++) {
+            const int2 e = fz.expect[t];
+            if (ticket_arrive(fz.tickets + t, (unsigned int)(e.x * ntr + e.y), lane))
+                tail_combine_tile(fz.tiles[t], ypart, ypart_len, ntr, y64, fz, lane);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FW_WARPS * 32, FW_PT_MINB)
+fwd_tail_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ g_all,
+                const tspws_fwd2_item_t *__restrict__ items, int nitems,
+                const float *__restrict__ x, int N, float2 *__restrict__ ypart, int ypart_len,
+                int smem_per_warp, int ntr, int long_L, int long_row0,
+                const double2 *__restrict__ w64, const tspws_fwd_item_t *__restrict__ items64, int nitems64, int nshort_cta,
+                const int2 *__restrict__ coefs64, int nf64, const double *__restrict__ x64, double2 *__restrict__ y64, int y64_ld,
+                const tspws_tailfuse_t fz, const int g5)
+{
+    tl_scope tls(2);
+    extern __shared__ __align__(128) float fw_smem[];
+    __shared__ double sh64[FW_WARPS][2 * F64_R];
+    fwd_tail_cta(scales, g_all, items, nitems, x, N, ypart, ypart_len, smem_per_warp, ntr, long_L, long_row0, w64, items64,
+                 nitems64, nshort_cta, coefs64, nf64, x64, y64, y64_ld, fz, g5, fw_smem, sh64);
 }
 
 /* d_x: [ntr][3N] period-padded traces (see above) */
@@ -1374,7 +1597,7 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
         const int nig = (nb + FW_WARPS - 1) / FW_WARPS;                                                 \
         /* full super-blocks have nig*cb CTAs; a short last one is padded to the same count (extra CTAs exit) */ \
         dim3 grid((unsigned)(((nchunk + cb - 1) / cb) * nig * cb));                                      \
-        if (smem > 48 * 1024)                                                                           \
+        if (smem > 40 * 1024)                                                                           \
             cudaFuncSetAttribute(fwd2_acc_kernel<LGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         fwd2_acc_kernel<LGV><<<grid, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, \
             f->d_items2, f->fw_lg_begin[LGV], f->fw_lg_begin[LGV + 1], d_x, f->N, ntr, chunk, f->ncoef,  \
@@ -1399,7 +1622,8 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
 /* fp64 transform of one period-padded trace d_x64 -> d_y64 [split][ncoef] together with the per-trace fp32
  * transforms of ntr traces (see fwd_tail_kernel); only for frames fully covered by the polyphase kernel */
 extern "C" int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
-                                     const double *d_x64, void *d_y64, tspws_stream_t st)
+                                     const double *d_x64, void *d_y64, unsigned int *d_tickets, const tspws_weight_t *d_rule,
+                                     void *d_ps, void *d_st, void *d_zout, tspws_stream_t st)
 {
     if (ntr <= 0 || !f->per_trace || !f->d_w64 || f->nitems2 <= 0 || f->nitems_gen > 0) return (int)cudaErrorInvalidValue;
     cudaStream_t s = (cudaStream_t)st;
@@ -1409,10 +1633,16 @@ extern "C" int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x
     const int cpt = (f->nitems2 + FW_WARPS - 1) / FW_WARPS;
     const int nshort_cta = (f->nitems_short + FW_WARPS - 1) / FW_WARPS;
     const int nf64 = nshort_cta + f->nlong;
+    /* d_tickets != NULL: the phasor combine runs inside this launch (PS, ST, Zout are complete when it ends) */
+    tspws_tailfuse_t fz;
+    fz.tiles = (const int4 *)f->d_tile16; fz.expect = (const int2 *)f->d_tile_expect; fz.tickets = d_tickets; fz.rule = d_rule;
+    fz.ps = (float2 *)d_ps; fz.st = (float2 *)d_st; fz.zout = (float2 *)d_zout; fz.ncoef = f->ncoef;
+    int g5 = f->fw_lg_begin[5] / FW_WARPS;               /* first item group with D >= 32 items */
+    { const char *e = getenv("TSPWS_TAIL_ORDER"); if (e && atoi(e) == 0) g5 = cpt; }   /* 0: fp64 CTAs first, then all groups */
     fwd_tail_kernel<<<nf64 + ntr * cpt, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, f->d_items2, f->nitems2,
         d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp, ntr, long_row0 > 0 ? f->f64_maxl : 0x7fffffff, long_row0,
         (const double2 *)f->d_w64, f->d_items_short, f->nitems_short, nshort_cta, (const int2 *)f->d_long, nf64, d_x64,
-        (double2 *)d_y64, f->ncoef);
+        (double2 *)d_y64, f->ncoef, fz, g5);
     TSPWS_LAUNCHED_N("fwd_tail_kernel", s);
     return 0;
 }
@@ -1425,7 +1655,7 @@ extern "C" int tspws_cu_forward_pertrace(const tspws_devframe_t *f, const float 
     cudaStream_t s = (cudaStream_t)st;
     if (f->nitems2 > 0) {
         const size_t smem = (size_t)f->fw_smem_per_warp * FW_WARPS * sizeof(float);
-        if (smem > 48 * 1024)
+        if (smem > 40 * 1024)
             cudaFuncSetAttribute(fwd2_pertrace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         /* traces per CTA.  Measured at K = 10 traces x 16384 (profiles/): 1 trace per CTA 27 us, 2 -> 43 us,
          * 10 -> 90 us: the kernel is issue bound and wants the widest grid, so the default stays 1. */
@@ -1462,6 +1692,7 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
                       int ncoef, int seg, const tspws_weight_t *__restrict__ rules, const double2 *__restrict__ ymean,
                       float2 *__restrict__ ps, float2 *__restrict__ st, float2 *__restrict__ zout)
 {
+    tl_scope tls(3);
     __shared__ float  s_p[4][PC_TILE][2];
     __shared__ double s_s[4][PC_TILE][2];
     /* tile = (offset in a trace's partial-Y block, offset in the coefficient arrays, valid
@@ -2003,6 +2234,7 @@ inv4_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
             const float4 *__restrict__ zs, float *scratch, int nseg, unsigned int *tickets,
             const tspws_weight_t *__restrict__ rules, float *__restrict__ out_ts, float *__restrict__ out_ls)
 {
+    tl_scope tls(5);
     __shared__ int is_last;
     const int n0 = (blockIdx.x * INV4_THREADS + threadIdx.x) * 4;
     const tspws_inv_group_t grp = groups[blockIdx.y];
@@ -2141,6 +2373,7 @@ __global__ void __launch_bounds__(128)
 inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ gi_all, const int4 *__restrict__ items,
             int nitems, int N, int ncoef, int nslots, const float4 *__restrict__ zs, float *__restrict__ scratch, int nseg)
 {
+    tl_scope tls(4);
     const int widx = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (widx >= nitems) return;
     const int lane = threadIdx.x & 31;
@@ -2214,6 +2447,7 @@ __global__ void __launch_bounds__(256)
 inv_finish_kernel(const float *__restrict__ scratch, int nslots, int nseg, int N, const tspws_weight_t *__restrict__ rules,
                   float *__restrict__ out_ts, float *__restrict__ out_ls)
 {
+    tl_scope tls(6);
     /* 32 float4 columns x 8 slot lanes: thread (col, sl) adds slots sl, sl+8, ... of its 4 samples in
      * fp64, then the 8 lanes of a column are added in lane order -- 12 loads per thread at 44 scales */
     __shared__ double sh[8][8][33];
@@ -2333,5 +2567,6 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
         else      inv_finish_kernel<false><<<grid, 256, 0, s>>>((const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
         TSPWS_LAUNCHED_N("inv_finish_kernel", s);
     }
+    tl_host_dump(s);
     return 0;
 }

@@ -65,6 +65,7 @@ struct tspws_plan {
     cudaEvent_t  ev_fork, ev_join;
     int          mean_split;        /* fp64 transform of the group mean + fp32 transforms of the residuals */
     int          hybrid;            /* TSPWS_F64_MAXL set: long filters transform the unsplit sums instead */
+    unsigned int *d_tile_tickets;   /* [ntile16]: fused phasor combine of fwd_tail_kernel (NULL: separate combine launch) */
     double      *d_gmean;           /* [3N]: the group mean, three periods */
     void        *d_ymean;           /* double2 [TSPWS_F64_MAXSPLIT][ncoef] */
     int         *h_slot_off;        /* [K+1] first work item of every group */
@@ -105,7 +106,8 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
     tspws_fwd2_item_t *items2 = NULL;
     tspws_inv_group_t *grp  = NULL;
     float *g32 = NULL;
-    int nitems = 0, nitems_gen = 0, nitems2 = 0, ok = 0;
+    int nitems = 0, nitems_gen = 0, nitems2 = 0, ok = 0, ntile64 = 0;
+    int *texp = NULL;           /* [ntile64][2]: fp32 items (per trace) and fp64 items that write into a tile */
     size_t ng = 0;
     if (!sc || !w32) goto done;
 
@@ -140,6 +142,10 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
         }
     }
     for (size_t i = 0; i < 2 * f->ntaps; i++) w32[i] = (float)f->w[i];
+    /* 64-coefficient tiles of all scales, numbered scale by scale: the units of the fused phasor combine */
+    for (int s = 0; s < S; s++) { sc[s].tile0 = ntile64; ntile64 += (sc[s].Ns + 63) / 64; }
+    texp = (int *)calloc((size_t)(ntile64 ? ntile64 : 1) * 2, sizeof(int));
+    if (!texp) goto done;
 
     /* ---- polyphase (register-tiled) kernel: which scales it covers, padded filters, items ---- */
     {
@@ -161,13 +167,13 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
             if (!nofast && D <= N) {
                 if (D >= 32) {
                     sc[s].lg = 5;
-                    const int need5 = 2 * (sc[s].Qs + 32) * 32;      /* double-buffered window rows */
+                    const int need5 = 2 * (sc[s].Qs + 16) * 32;      /* double-buffered window rows: the Qs + 16 the taps reach */
                     if (need5 > d->fw_smem_per_warp) d->fw_smem_per_warp = need5;
                 }
                 else if ((D & (D - 1)) == 0) {
                     int lg = 0; while ((1 << lg) < D) lg++;
                     const int tiles = 32 >> lg;
-                    const long W = ((long)tiles * 16 + sc[s].Qs + 32) * D;   /* + ring over-read */
+                    const long W = ((long)tiles * 16 + sc[s].Qs) * D;        /* what the taps reach */
                     long need = W + (W / (16 * D) + 1) * D + 8;          /* skewed window + copy overrun */
                     need = 2 * ((need + 3) & ~3L);                       /* double buffered, 16 B aligned */
                     if (W <= N && need * 4 * 4 * 3 <= 200 * 1024) {
@@ -177,6 +183,8 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
                 }
             }
             if (sc[s].lg >= 0) {
+                const int gpass = (sc[s].Qs + 8) * (sc[s].lg == 5 ? 32 : D);    /* taps of one pass */
+                if (gpass > d->fw_gmax) d->fw_gmax = gpass;
                 const int gs = (sc[s].lg == 5) ? ((D + 31) & ~31) : D;     /* phases padded to 32 lanes */
                 sc[s].g_off = (int)ng;
                 ng += (size_t)(sc[s].Qs + 8) * gs;                       /* + 8 zero taps: unguarded prefetch */
@@ -222,6 +230,10 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
                                 it->s = s; it->m0 = m0; it->split = sp;
                                 it->pb0 = (lg < 5) ? 0 : (int)((long)nblk * sp / nsp);
                                 it->pb1 = (lg < 5) ? 1 : (int)((long)nblk * (sp + 1) / nsp);
+                                long long b0 = ((long long)(m0 - sc[s].A) * sc[s].D) % N;
+                                it->base = (int)(b0 < 0 ? b0 + N : b0);
+                                const int mend = (m0 + per_item < sc[s].Ns ? m0 + per_item : sc[s].Ns) - 1;
+                                for (int t = m0 / 64; t <= mend / 64; t++) texp[2 * (sc[s].tile0 + t)]++;
                             }
                             nitems2++;
                         }
@@ -299,13 +311,18 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
             if (sc[s].L >= MAXL) continue;
             if (sc[s].L >= LONG_T) {
                 for (int m = 0; m < sc[s].Ns; m += R64)
-                    for (int q = 0; q < TSPWS_F64_NSPLIT(sc[s].L); q++) { lg[2 * kl] = s | (q << 16); lg[2 * kl + 1] = m; kl++; }
+                    for (int q = 0; q < TSPWS_F64_NSPLIT(sc[s].L); q++) {
+                        lg[2 * kl] = s | (q << 16); lg[2 * kl + 1] = m; kl++;
+                        texp[2 * (sc[s].tile0 + m / 64) + 1]++;
+                    }
                 continue;
             }
             const int pass = (32 / sc[s].G) * R64;
             long run = TAPS / sc[s].L; run -= run % pass; if (run < pass) run = pass;
             for (int m0 = 0; m0 < sc[s].Ns; m0 += (int)run) {
-                its[ks].s = s; its[ks].m0 = m0; its[ks].nout = (sc[s].Ns - m0 < run) ? sc[s].Ns - m0 : (int)run; ks++;
+                its[ks].s = s; its[ks].m0 = m0; its[ks].nout = (sc[s].Ns - m0 < run) ? sc[s].Ns - m0 : (int)run;
+                for (int t = m0 / 64; t <= (m0 + its[ks].nout - 1) / 64; t++) texp[2 * (sc[s].tile0 + t) + 1]++;
+                ks++;
             }
         }
         int bad = cudaMalloc((void **)&d->d_items_short, (size_t)(ns ? ns : 1) * sizeof(*its)) != cudaSuccess ||
@@ -403,7 +420,10 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
                 k++;
             }
         int bad = cudaMalloc((void **)&d->d_tile16, (size_t)(nt ? nt : 1) * 4 * sizeof(int)) != cudaSuccess ||
-                  cudaMemcpy(d->d_tile16, tl, (size_t)nt * 4 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess;
+                  cudaMemcpy(d->d_tile16, tl, (size_t)nt * 4 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                  nt != ntile64 ||
+                  cudaMalloc((void **)&d->d_tile_expect, (size_t)(nt ? nt : 1) * 2 * sizeof(int)) != cudaSuccess ||
+                  cudaMemcpy(d->d_tile_expect, texp, (size_t)nt * 2 * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess;
         free(tl);
         if (bad) goto done;
         d->ntile16 = nt;
@@ -426,7 +446,7 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
     if (cudaDeviceSynchronize() != cudaSuccess) goto done;
     ok = 1;
 done:
-    free(sc); free(w32); free(items); free(grp); free(items2); free(items_gen); free(g32);
+    free(sc); free(w32); free(items); free(grp); free(items2); free(items_gen); free(g32); free(texp);
     return ok ? 0 : -1;
 }
 
@@ -434,7 +454,7 @@ void tspws_devframe_free(tspws_devframe_t *d)
 {
     cudaFree(d->d_scale); cudaFree(d->d_w32); cudaFree(d->d_w64);
     cudaFree(d->d_items); cudaFree(d->d_invgrp);
-    cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen); cudaFree(d->d_tile16); cudaFree(d->d_wi32); cudaFree(d->d_gi32); cudaFree(d->d_items_inv2); cudaFree(d->d_invgrp4); cudaFree(d->d_items_short); cudaFree(d->d_long);
+    cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen); cudaFree(d->d_tile16); cudaFree(d->d_tile_expect); cudaFree(d->d_wi32); cudaFree(d->d_gi32); cudaFree(d->d_items_inv2); cudaFree(d->d_invgrp4); cudaFree(d->d_items_short); cudaFree(d->d_long);
     memset(d, 0, sizeof(*d));
 }
 
@@ -552,7 +572,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     if (pl->exch_bound) { pl->d_gsum = (double *)pl->own_gsum; pl->d_exch = pl->own_exch; }
     if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
     if (pl->side) { cudaStreamDestroy(pl->side); cudaEventDestroy(pl->ev_join); cudaEventDestroy(pl->ev_fork); }
-    cudaFree(pl->d_gmean); cudaFree(pl->d_ymean);
+    cudaFree(pl->d_gmean); cudaFree(pl->d_ymean); cudaFree(pl->d_tile_tickets);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
     tspws_b200_plan_peer_close(pl);
@@ -617,6 +637,11 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
         CK(cudaMalloc((void **)&pl->d_gmean, (size_t)max * 3 * sizeof(double)));      /* period-padded, see fwd_f64_kernel */
         CK(cudaMalloc(&pl->d_ymean, (size_t)TSPWS_F64_MAXSPLIT * ncoef * 2 * sizeof(double)));   /* [split][ncoef] */
         CK(cudaMemset(pl->d_ymean, 0, (size_t)TSPWS_F64_MAXSPLIT * ncoef * 2 * sizeof(double)));
+        if (env_long("TSPWS_FUSED_COMBINE", 1)) {     /* tickets of the combine fused into fwd_tail_kernel */
+            const size_t nt = pl->dev.ntile16 ? pl->dev.ntile16 : 1;
+            CK(cudaMalloc((void **)&pl->d_tile_tickets, nt * sizeof(unsigned int)));
+            CK(cudaMemset(pl->d_tile_tickets, 0, nt * sizeof(unsigned int)));
+        }
     }
     CK(cudaMalloc(&pl->d_zout, ncoef * (pl->acc64 ? 2 * sizeof(double) : 4 * sizeof(float))));
     CK(cudaMalloc(&pl->d_invscratch, (size_t)2 * (pl->dev.inv_slots ? pl->dev.inv_slots : 1) * max * (pl->csz / 2)));
@@ -840,9 +865,12 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
         if (stop == 2) return 0;
         if (pl->dev.per_trace) {
             const int long_row0 = pl->mean_split && pl->hybrid ? pl->ntr_fwd : 0;
+            int fused_combine = 0;
             if (pl->mean_split && pl->dev.nitems_gen == 0 && pl->dev.nitems2 > 0 && env_long("TSPWS_FUSED_TAIL", 1)) {
                 /* one launch: fp64 transform of the group mean + fp32 transforms of the residuals */
-                if ((e = tspws_cu_forward_tail(&pl->dev, pl->d_gsum32, pl->ntr_fwd, long_row0, pl->d_ypart, pl->d_gmean, pl->d_ymean, stream))) return TSPWS_ERR_CUDA;
+                fused_combine = pl->d_tile_tickets != NULL;
+                if ((e = tspws_cu_forward_tail(&pl->dev, pl->d_gsum32, pl->ntr_fwd, long_row0, pl->d_ypart, pl->d_gmean, pl->d_ymean,
+                                               pl->d_tile_tickets, pl->d_rule, plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
             } else {
             /* fork: fp64 transform of the group mean on the side stream, fp32 transforms of the residuals here */
             cudaStream_t A = (cudaStream_t)stream;
@@ -856,7 +884,8 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
                 (cudaEventRecord(pl->ev_join, B) != cudaSuccess || cudaStreamWaitEvent(A, pl->ev_join, 0) != cudaSuccess)) return TSPWS_ERR_CUDA;
             }
             if (stop == 3) return 0;
-            if ((e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, pl->mean_split ? pl->d_ymean : NULL,
+            if (!fused_combine &&
+                (e = tspws_cu_phasor_combine(&pl->dev, pl->d_ypart, 1, pl->ntr_fwd, pl->d_rule, pl->mean_split ? pl->d_ymean : NULL,
                                              plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
         } else {
             if ((e = tspws_cu_forward(&pl->dev, gfin, 1, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
