@@ -114,6 +114,7 @@ typedef struct {
     void              *d_gi32;    /* float2[]: reversed, phase-padded filters of the polyphase inverse */
     int               *d_items_inv2; /* [nitems_inv2][4]: (scale, first a, phase block, -)         */
     int                nitems_inv2;
+    int                inv2_qmax; /* largest Qi among the scales of the polyphase inverse (shared-memory sizing) */
     int                inv_slots; /* scratch slots of the inverse: max(S, ninv)                         */
 } tspws_devframe_t;
 

@@ -2259,7 +2259,7 @@ inv4_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
                     const int lo = lnum <= 0 ? 0 : (int)(((unsigned int)lnum + sc.D - 1) / (unsigned int)sc.D);
                     const float2 *wp = w + (base - lo * sc.D);
                     const float4 *zp = Zs + lo;
-#pragma unroll 2
+#pragma unroll 8
                     for (int cnt = hi - lo + 1; cnt > 0; cnt--, wp -= sc.D, zp++) {
                         const float4 w01 = __ldg(reinterpret_cast<const float4 *>(wp));
                         const float4 w23 = __ldg(reinterpret_cast<const float4 *>(wp + 2));
@@ -2368,12 +2368,18 @@ inv4_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
  * One warp per item (scale, a-tile, block of 32 phases). */
 #define IV_R 8
 #define IV_WS 16
+/* The item's Qi tap rows (32 phases each) and its Qi + 7 coefficients are staged into warp-private shared memory
+ * with ONE round of cp.async before the tap loop: with loads from global inside the loop, an 8-tap prefetch
+ * distance (8 x 16 FFMA2) covers only a third of the L2 latency and every tap stalled (per-CTA timeline: 6 us per
+ * item of ~1500 instructions). */
 template <bool WITH_ST>
 __global__ void __launch_bounds__(128)
 inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ gi_all, const int4 *__restrict__ items,
-            int nitems, int N, int ncoef, int nslots, const float4 *__restrict__ zs, float *__restrict__ scratch, int nseg)
+            int nitems, int N, int ncoef, int nslots, const float4 *__restrict__ zs, float *__restrict__ scratch, int nseg,
+            int smem_per_warp /* bytes */, int qmax)
 {
     tl_scope tls(4);
+    extern __shared__ __align__(16) unsigned char iv_smem[];
     const int widx = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (widx >= nitems) return;
     const int lane = threadIdx.x & 31;
@@ -2384,22 +2390,42 @@ inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
     const int rho = it.z * 32 + lane;
     const bool act = rho < D;
     const float4 *__restrict__ Z = zs + (size_t)sg * ncoef + sc.coef_off;
-    const float2 *__restrict__ g = gi_all + sc.gi_off + (act ? rho : 0);
+    float2 *gsm = reinterpret_cast<float2 *>(iv_smem + (size_t)(threadIdx.x >> 5) * smem_per_warp);   /* [Qi + 8][32] */
+    float4 *zsm = reinterpret_cast<float4 *>(gsm + (size_t)(qmax + 8) * 32);                            /* [Qi + 7]     */
+    {
+        const float2 *__restrict__ g0 = gi_all + sc.gi_off + it.z * 32;
+        const int nrow = Qi + 8;                          /* the tap prefetch runs 8 rows ahead (zero rows in the array) */
+        if (((D | sc.gi_off) & 1) == 0 && it.z * 32 + 32 <= D) {
+            for (int c = lane; c < nrow * 16; c += 32) {  /* 16-byte chunks: row c / 16, float2 pair c % 16 */
+                const int row = c >> 4, col = (c & 15) * 2;
+                cp_async<16>(gsm + row * 32 + col, g0 + (size_t)row * D + col);
+            }
+        } else {
+            for (int row = 0; row < nrow; row++) cp_async<8>(gsm + row * 32 + lane, g0 + (size_t)row * D + (act ? lane : 0));
+        }
+        int zi0 = (a0 - Qi + 1) % Ns;                     /* window slot 0 */
+        if (zi0 < 0) zi0 += Ns;
+        for (int j = lane; j < Qi + IV_R - 1; j += 32) cp_async<16>(zsm + j, Z + (zi0 + j) % Ns);
+        cp_async_commit();
+    }
     float2 accr[IV_R];                                    /* (tsPWS, ls) partial of sample r */
 #pragma unroll
     for (int r = 0; r < IV_R; r++) accr[r] = make_float2(0.f, 0.f);
-    int zi = (a0 - Qi + 1) % Ns;                          /* window slot 0 */
-    if (zi < 0) zi += Ns;
+    cp_async_wait<0>();
+    __syncwarp();
+    const float2 *g = gsm + lane;
+    int zi = 0;
     float2 wre[IV_WS], wim[IV_WS];                        /* (Zr, Sr) and (Zi, Si) of every ring slot */
     float2 gq[8];
 #pragma unroll
     for (int j = 0; j < IV_WS; j++) {
-        const float4 z = __ldcg(Z + zi);
-        wre[j] = make_float2(z.x, z.z); wim[j] = make_float2(z.y, z.w);
-        if (++zi >= Ns) zi = 0;
+        if (j < Qi + IV_R - 1) {
+            const float4 z = zsm[zi++];
+            wre[j] = make_float2(z.x, z.z); wim[j] = make_float2(z.y, z.w);
+        }
     }
 #pragma unroll
-    for (int q = 0; q < 8; q++) gq[q] = __ldg(g + (size_t)q * D);
+    for (int q = 0; q < 8; q++) gq[q] = g[q * 32];
     for (int t0 = 0; t0 < Qi; t0 += IV_WS) {
 #pragma unroll
         for (int tt = 0; tt < IV_WS; tt++) {
@@ -2412,11 +2438,10 @@ inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
                     accr[r] = __ffma2_rn(wim[(tt + r) % IV_WS], gy, accr[r]);
                 }
                 if (t0 + tt + IV_WS - IV_R + 1 < Qi) {
-                    const float4 z = __ldcg(Z + zi);
+                    const float4 z = zsm[zi++];
                     wre[tt] = make_float2(z.x, z.z); wim[tt] = make_float2(z.y, z.w);
-                    if (++zi >= Ns) zi = 0;
                 }
-                gq[tt & 7] = __ldg(g + (size_t)(t0 + tt + 8) * D);
+                gq[tt & 7] = g[(t0 + tt + 8) * 32];
             }
         }
     }
@@ -2542,10 +2567,16 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
     }
     if (f->nitems_inv2 > 0) {
         dim3 grid((f->nitems_inv2 + 3) / 4, nseg);
-        if (d_st) inv2_kernel<true><<<grid, 128, 0, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
-                      f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg);
-        else      inv2_kernel<false><<<grid, 128, 0, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
-                      f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg);
+        /* per warp: (Qi + 8) tap rows of 32 phases + Qi + 7 coefficients (float4) */
+        const int spw = ((f->inv2_qmax + 8) * 256 + (f->inv2_qmax + 8) * 16 + 15) & ~15;
+        if (4 * spw > 40 * 1024) {
+            cudaFuncSetAttribute(inv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * spw);
+            cudaFuncSetAttribute(inv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * spw);
+        }
+        if (d_st) inv2_kernel<true><<<grid, 128, 4 * spw, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
+                      f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg, spw, f->inv2_qmax);
+        else      inv2_kernel<false><<<grid, 128, 4 * spw, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
+                      f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg, spw, f->inv2_qmax);
         TSPWS_LAUNCHED_N("inv2_kernel", s);
     }
     if (f->ninv4 > 0) {

@@ -369,6 +369,7 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
             sc[s].inv2 = !noinv2 && D >= 32 && (f->N % D == 0);
             sc[s].gi_off = (int)ngi;
             if (sc[s].inv2) {
+                if (sc[s].Qi > d->inv2_qmax) d->inv2_qmax = sc[s].Qi;
                 ngi += (size_t)(sc[s].Qi + 8) * D;
                 ni2 += ((sc[s].Ns + 7) / 8) * ((D + 31) / 32);
             } else n4++;
@@ -637,7 +638,7 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
         CK(cudaMalloc((void **)&pl->d_gmean, (size_t)max * 3 * sizeof(double)));      /* period-padded, see fwd_f64_kernel */
         CK(cudaMalloc(&pl->d_ymean, (size_t)TSPWS_F64_MAXSPLIT * ncoef * 2 * sizeof(double)));   /* [split][ncoef] */
         CK(cudaMemset(pl->d_ymean, 0, (size_t)TSPWS_F64_MAXSPLIT * ncoef * 2 * sizeof(double)));
-        if (env_long("TSPWS_FUSED_COMBINE", 1)) {     /* tickets of the combine fused into fwd_tail_kernel */
+        if (env_long("TSPWS_FUSED_COMBINE", 0)) {     /* experiment (slower): combine fused into fwd_tail_kernel by tile tickets */
             const size_t nt = pl->dev.ntile16 ? pl->dev.ntile16 : 1;
             CK(cudaMalloc((void **)&pl->d_tile_tickets, nt * sizeof(unsigned int)));
             CK(cudaMemset(pl->d_tile_tickets, 0, nt * sizeof(unsigned int)));
