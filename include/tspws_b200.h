@@ -253,9 +253,17 @@ int    tspws_b200_plan_mark_exchanged(tspws_plan_t *plan);
  * block into every rank's region (stores over NVLink / NVSwitch) and plan_finish sums the blocks of all
  * ranks inside its first kernel -- no all-reduce call, no plan_mark_exchanged, and tspws_b200_plan_stack
  * replays the whole multi-GPU step as one CUDA graph.  Ranks must call the same sequence of steps.
- * plan_peer_error: 1 if a wait for a peer ever timed out (~4 s; the step's result is then invalid). */
+ * plan_peer_error: 1 if a wait for a peer ever timed out (~4 s); the stacks of that step are then NaN (never
+ * a silent partial sum). */
 int tspws_b200_plan_peer_export(tspws_plan_t *plan, int world, void *handle64);
 int tspws_b200_plan_peer_import(tspws_plan_t *plan, int rank, int world, const void *handles /* world x 64 bytes */);
+/* Same-process variant (several plans in one process -- e.g. a test that runs all the shards of a node on one
+ * GPU, or one host thread per GPU with peer access enabled): device pointers instead of IPC handles.
+ * plan_peer_region returns the plan's exchange region (NULL when the plan cannot take part: not two-stage,
+ * max % 4 != 0 or no local traces -- decide collectively and fall back to the all-reduce path together);
+ * plan_peer_import_ptrs takes the `world` regions in rank order. */
+void *tspws_b200_plan_peer_region(tspws_plan_t *plan, int world);
+int   tspws_b200_plan_peer_import_ptrs(tspws_plan_t *plan, int rank, int world, void *const *regions);
 int tspws_b200_plan_peer_error(tspws_plan_t *plan);
 /* Teardown order (CUDA IPC rule: never free an exported allocation that another process still maps):
  * every rank calls plan_peer_close, the ranks synchronise (barrier), then every rank calls plan_destroy. */

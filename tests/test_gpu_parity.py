@@ -310,3 +310,72 @@ def test_peer_exchange_api_argument_checks(pkg, gpu_lib):
         assert gpu_lib.tspws_b200_plan_peer_error(plan) == 0
         assert O.nerr(ts.cpu().numpy(), ref[1]) <= 1e-6 and O.nerr(ls.cpu().numpy(), ref[0]) <= 1e-6
     gpu_lib.tspws_b200_plan_destroy(plan)
+
+
+def _peer_world_on_one_gpu(pkg, lib, x, world, shards, **params):
+    """All the ranks of a peer exchange inside ONE process on ONE GPU: every shard gets its own plan, the
+    exchange regions are wired with plan_peer_import_ptrs (device pointers instead of IPC handles), then every
+    plan publishes (plan_reduce) and every plan sums the blocks of all ranks (plan_finish) -- the protocol the
+    8-GPU bench runs, including the 'push only the groups a shard touches' presence marks."""
+    import torch
+    p = pkg.default_params(**params)
+    mtr, n = x.shape
+    lib.tspws_b200_derive_params(C.byref(p), n, 1.0)
+    dx = torch.from_numpy(x).cuda()
+    plans, outs = [], []
+    stream = torch.cuda.current_stream().cuda_stream
+    try:
+        for r, (a, b) in enumerate(shards):
+            plan = lib.tspws_b200_plan_create(C.byref(p), n, b - a, mtr, a)
+            assert plan
+            plans.append(plan)
+        regions = (C.c_void_p * world)(*[lib.tspws_b200_plan_peer_region(pl, world) for pl in plans])
+        assert all(regions[r] for r in range(world))
+        for r, pl in enumerate(plans):
+            assert lib.tspws_b200_plan_peer_import_ptrs(pl, r, world, regions) == 0
+        for step in range(3):                      # several steps: parity double-buffering, re-armed tickets
+            outs = []
+            for r, (pl, (a, b)) in enumerate(zip(plans, shards)):
+                assert lib.tspws_b200_plan_reduce(pl, dx[a:b].data_ptr(), stream) == 0
+            for r, pl in enumerate(plans):
+                ls = torch.empty(n, device="cuda")
+                ts = torch.empty(n, device="cuda")
+                assert lib.tspws_b200_plan_finish(pl, ls.data_ptr(), ts.data_ptr(), stream) == 0
+                outs.append((ls, ts))
+            torch.cuda.synchronize()
+        res = []
+        for pl, (ls, ts) in zip(plans, outs):
+            assert lib.tspws_b200_plan_peer_error(pl) == 0
+            nc = lib.tspws_b200_plan_ncoef(pl)
+            ps = np.empty(2 * nc)
+            assert lib.tspws_b200_plan_get_stacks(pl, None, ps.ctypes.data_as(C.POINTER(C.c_double)), nc) == nc
+            res.append((ls.cpu().numpy(), ts.cpu().numpy(), np.hypot(ps[0::2], ps[1::2]) / lib.tspws_b200_plan_K(pl)))
+        return res
+    finally:
+        for pl in plans:
+            lib.tspws_b200_plan_peer_close(pl)
+        for pl in plans:
+            lib.tspws_b200_plan_destroy(pl)
+
+
+@pytest.mark.parametrize("world,ragged", [(8, False), (3, True), (2, False)])
+def test_peer_exchange_all_ranks_on_one_gpu_vs_oracle(pkg, gpu_lib, world, ragged):
+    """Traces sharded over `world` ranks, fused peer exchange (sparse push: at 8 ranks every shard touches 2-3
+    of the 10 groups): every rank's stack against the numpy oracle of the unsharded problem, and all ranks
+    bit-identical to each other."""
+    mtr, n = 1000, 4096
+    kw = dict(Kmax=10, unbiased=1, lrm=1, fold=1)
+    x = O.synthetic_traces(mtr, n, seed=8100 + world) + np.float32(0.125)
+    if ragged:
+        cuts = [0, 137, 610, mtr]
+    else:
+        cuts = [mtr * r // world for r in range(world + 1)]
+    shards = list(zip(cuts[:-1], cuts[1:]))
+    res = _peer_world_on_one_gpu(pkg, gpu_lib, x, world, shards, **kw)
+    o = O.tspws_main(O.Params(**kw), x)
+    for r, (ls, ts, coh) in enumerate(res):
+        assert O.nerr(coh, o["coherence"]) <= TOL_COH, r
+        assert O.nerr(ls, o["ls"]) <= TOL_STACK, r
+        assert O.nerr(ts, o["tsPWS"]) <= TOL_STACK, r
+        np.testing.assert_array_equal(ts, res[0][1])
+        np.testing.assert_array_equal(ls, res[0][0])

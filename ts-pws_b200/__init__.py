@@ -173,6 +173,10 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_plan_peer_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.tspws_b200_plan_peer_import.restype = C.c_int
     lib.tspws_b200_plan_peer_import.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.tspws_b200_plan_peer_region.restype = C.c_void_p
+    lib.tspws_b200_plan_peer_region.argtypes = [C.c_void_p, C.c_int]
+    lib.tspws_b200_plan_peer_import_ptrs.restype = C.c_int
+    lib.tspws_b200_plan_peer_import_ptrs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.tspws_b200_plan_peer_error.restype = C.c_int
     lib.tspws_b200_plan_peer_error.argtypes = [C.c_void_p]
     lib.tspws_b200_plan_peer_close.restype = C.c_int
@@ -203,7 +207,7 @@ EXPORTS = [
     "tspws_b200_plan_reduce", "tspws_b200_plan_exchange_ptr", "tspws_b200_plan_exchange_bytes",
     "tspws_b200_load_sac_list", "tspws_b200_load_bin", "tspws_b200_save_bin", "tspws_b200_save_rows_bin", "tspws_b200_write_sac",
     "tspws_b200_read_sac", "tspws_b200_free_data",
-    "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_peer_export", "tspws_b200_plan_peer_import", "tspws_b200_plan_peer_error", "tspws_b200_plan_peer_close", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
+    "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_peer_export", "tspws_b200_plan_peer_import", "tspws_b200_plan_peer_region", "tspws_b200_plan_peer_import_ptrs", "tspws_b200_plan_peer_error", "tspws_b200_plan_peer_close", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
     "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",
 ]
 

@@ -175,11 +175,11 @@ int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, 
 /* Per-trace mode (f->per_trace == 1): raw coefficients of each of the ntr traces (split over
  * phase ranges for coarse scales) go to d_ypart [f->ypart_len * ntr] complex fp32 ... */
 /* peer exchange (CUDA IPC mappings of the other ranks' exchange blocks), see group_post2_kernel<true> */
-int tspws_cu_peer_signal(unsigned int *d_step, void *d_peer_flags, int rank, int world, tspws_stream_t st);
 int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
                               int ntile, int do_rm, int do_fold, int split, double *d_gsum,
                               float *d_out32, double *d_gmean, void *d_regions, double *d_own, const unsigned int *d_flags,
-                              unsigned int *d_step, unsigned int *d_err, int rank, int world, tspws_stream_t st);
+                              unsigned int *d_step /* [2]: step, CTA ticket */, unsigned int *d_err, void *d_peer_flags,
+                              int rank, int world, tspws_stream_t st);
 /* d_tickets != NULL ([f->ntile16] zeroed counters): the phasor combine is fused in (PS, ST, Zout written by
  * the warp that completes a coefficient tile); NULL: per-trace coefficients only, tspws_cu_phasor_combine follows */
 int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
@@ -207,16 +207,18 @@ int tspws_cu_weight(const void *d_ps, const void *d_st, int acc64, int ncoef, in
  *   d_out_ts/d_out_ls: float [nseg][N];  ls is divided by rules[seg].T like src/ts_pws1f_lib.c:234.
  *   d_st may be NULL (no linear stack wanted).  d_scratch: [2][ninv][nseg][N] of T;
  *   d_tickets: [nseg][ceil(N/256)] zero-initialised counters (self re-arming). */
+/* side / ev_fork / ev_join (cudaStream_t, cudaEvent_t x 2; all NULL: one stream): the two independent halves
+ * of the fp32 inverse run concurrently on `side` (fork / join, also inside a graph capture). */
 int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, const void *d_st, int acc64,
                      int nseg, const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
-                     float *d_out_ts, float *d_out_ls, tspws_stream_t st);
+                     float *d_out_ts, float *d_out_ls, tspws_stream_t st, tspws_stream_t side, void *ev_fork, void *ev_join);
 
 /* device frame construction (tspws_plan.c) */
 int  tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64, int per_trace);
 void tspws_devframe_free(tspws_devframe_t *d);
 
 /* ---- resampling / convergence support ---- */
-int tspws_cu_regroup(const float *d_x, int N, int ntr, const signed char *d_gid /*[M][ntr]*/, int M, int G,
+int tspws_cu_regroup(const float *d_x, int N, int ntr, const short *d_gid /*[M][ntr]*/, int M, int G,
                      float *d_out /*[M][G][N]*/, tspws_stream_t st);
 int tspws_cu_group_total(const float *d_gs, int M, int G, int N, const double *d_scale /*[M]*/, float *d_out /*[M][N]*/,
                          tspws_stream_t st);
@@ -231,7 +233,6 @@ int tspws_cu_simil(const float *d_cand, int B, int N, const float *d_ref, double
 int tspws_cu_lsconv(const float *d_x, int ntr, int N, const float *d_ref, float *d_steps, double *d_part,
                     double *d_sim, double *d_mis, tspws_stream_t st);
 
-void tspws_cu_inverse_side_stream(tspws_stream_t side);
 unsigned long tspws_cu_launch_count(void);
 void tspws_cu_profile_mark(tspws_stream_t st);
 int  tspws_cu_profile_enabled(void);

@@ -9,7 +9,6 @@
  * group_post2_kernel<PEER>     slot sums + mean removal / fold (:76-86, :160-168 applied
  *                              to the group sums) + fp64 mean split; PEER: the sum over
  *                              the ranks of a node, read from blocks pushed over NVLink  latency
- * peer_signal_kernel           step flag of the peer exchange                            latency
  * fwd2_acc_kernel<LG>          complex_1D_wavelet_dec src/FWTa/wavelet_v7.c:43-64 ->
  *   fwd2_pertrace_kernel         cdotx_dc src/FWTa/cdotx.c:35-72 (polyphase register
  *   fwd_tail_kernel              tile, FFMA2), fused with the phasor accumulate of
@@ -463,7 +462,7 @@ extern "C" int tspws_cu_colsum2(const float *d_x, int N, const void *d_parts, in
  *       stores pipeline; remote loads measured 10x slower at 8 GPUs: 124 us for 9 MB).  A shard is a
  *       contiguous trace range, so it touches only a few of the K groups: only those are pushed, and a
  *       presence mark per group tells the readers which ranks to add (at 8 GPUs 2-3 of 10 groups);
- *   peer_signal_kernel: system fence, then the step number into every rank's flag word;
+ *   the last CTA of the publishing launch: system fence, then the step number into every rank's flag word;
  *   PEER = true launch: waits until the flags of all ranks have reached this step, then treats the world
  *       blocks of its OWN region as the slots of every group (rank order: deterministic).
  * Blocks are double-buffered by step parity, so a rank that runs ahead never overwrites a block that a
@@ -472,8 +471,10 @@ struct tspws_peer_args {
     double *const *regions;          /* [world] base of every rank's region: [2][world][block_len] doubles */
     double              *own;        /* base of the own region */
     const unsigned int  *flags;      /* [world] own flag words, written by the peers */
-    unsigned int        *step;       /* own step counter (advanced by peer_signal_kernel) */
+    unsigned int        *step;       /* own step counter (advanced by the last CTA of the publishing launch) */
     unsigned int        *err;        /* set when a wait timed out */
+    unsigned int        *ticket;     /* publishing launch: CTAs done (the last one signals the peers) */
+    unsigned int *const *peer_flags; /* [world] every rank's flag words */
     int world, rank;
     long long block_len;             /* doubles per block = K*N group sums + K*ntile tile totals + K presence marks */
 };
@@ -506,6 +507,7 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     unsigned char *s_pres = reinterpret_cast<unsigned char *>(s_c + K);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     size_t par_off = 0;                                  /* first block of this step's parity */
+    bool dead = false;                                   /* a peer never arrived: poison the sums (NaN) instead of stacking a partial exchange */
     if (PEER) {
         const unsigned int step = *pa.step;              /* already advanced for this step */
         par_off = (size_t)((step - 1) & 1) * (size_t)pa.world * (size_t)pa.block_len;
@@ -517,6 +519,7 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
             }
         }
         __syncthreads();
+        dead = *reinterpret_cast<volatile unsigned int *>(pa.err) != 0;
         /* which rank contributes to which group (marks pushed with the blocks) */
         for (int i = threadIdx.x; i < K * pa.world; i += blockDim.x) {
             const int k = i / pa.world, j = i % pa.world;
@@ -585,6 +588,7 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
             v = 0.5 * (v + vr);                            /* the constant correction is fold-invariant */
         }
         if (mode == 1 && do_rm) v -= s_c[k];
+        if (PEER && dead) v = __longlong_as_double(0x7ff8000000000000LL);
         if (push) { if (c_k) for (int q = 0; q < pa.world; q++) pa.regions[q][par_off + (size_t)k * N + n] = v; }
         else gsum[(size_t)k * N + n] = v;
         return v;
@@ -597,7 +601,30 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
         }
         for (int k = w + GP2_KR * GP2_LANES; k < K; k += GP2_LANES) acc += group_value(k);
     }
-    if (mode == 0) return;
+    if (mode == 0) {
+        if (push) {
+            /* every CTA has pushed its columns; the LAST one to get here makes the whole block visible and stores
+             * the step number into every rank's flag word (what a separate signalling launch used to do) */
+            __shared__ unsigned int s_last;
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int t = atomicAdd(pa.ticket, 1u);
+                s_last = (t == gridDim.x - 1);
+                if (s_last) *pa.ticket = 0;
+            }
+            __syncthreads();
+            if (s_last) {
+                const unsigned int st = *pa.step + 1;
+                __threadfence_system();
+                if ((int)threadIdx.x < pa.world)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pa.peer_flags[threadIdx.x] + pa.rank), "r"(st) : "memory");
+                __syncthreads();
+                if (threadIdx.x == 0) *pa.step = st;
+            }
+        }
+        return;
+    }
     double m = 0.0;
     if (split) {
         s_m[w][lane] = acc;
@@ -623,36 +650,17 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     }
 }
 
-/* after the publishing launch: advance the own step counter and store it into every peer's flag word */
-__global__ void peer_signal_kernel(unsigned int *step, unsigned int *const *peer_flags, int rank, int world)
-{
-    __shared__ unsigned int s;
-    if (threadIdx.x == 0) s = *step + 1;
-    __syncthreads();
-    __threadfence_system();                              /* the block published by the previous kernel first */
-    if ((int)threadIdx.x < world)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[threadIdx.x] + rank), "r"(s) : "memory");
-    __syncthreads();
-    if (threadIdx.x == 0) *step = s;
-}
-
-extern "C" int tspws_cu_peer_signal(unsigned int *d_step, void *d_peer_flags, int rank, int world, tspws_stream_t st)
-{
-    peer_signal_kernel<<<1, 32, 0, (cudaStream_t)st>>>(d_step, (unsigned int *const *)d_peer_flags, rank, world);
-    TSPWS_LAUNCHED_N("peer_signal_kernel", (cudaStream_t)st);
-    return 0;
-}
-
 /* peer variants of the two group_post2 launches: publish (push into every region) and the sum over ranks */
 extern "C" int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
                                          int ntile, int do_rm, int do_fold, int split, double *d_gsum,
                                          float *d_out32, double *d_gmean, void *d_regions, double *d_own, const unsigned int *d_flags,
-                                         unsigned int *d_step, unsigned int *d_err, int rank, int world, tspws_stream_t st)
+                                         unsigned int *d_step, unsigned int *d_err, void *d_peer_flags, int rank, int world, tspws_stream_t st)
 {
     const size_t smem = (size_t)K * sizeof(double) + (size_t)K * world;
     if (smem > 40 * 1024 || world > 32 * GP2_LANES) return (int)cudaErrorInvalidValue;
     tspws_peer_args pa;
     pa.regions = (double *const *)d_regions; pa.own = d_own; pa.flags = d_flags; pa.step = d_step; pa.err = d_err;
+    pa.ticket = d_step + 1; pa.peer_flags = (unsigned int *const *)d_peer_flags;
     pa.world = world; pa.rank = rank; pa.block_len = (long long)K * N + (long long)K * ntile + K;
     if (publish)
         group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
@@ -1846,7 +1854,7 @@ extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_
 #define RG_MB 8
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-regroup_kernel(const float *__restrict__ x, int N, int ntr, const signed char *__restrict__ gid,
+regroup_kernel(const float *__restrict__ x, int N, int ntr, const short *__restrict__ gid,
                int M, int G, float *__restrict__ out)
 {
     const int m0 = blockIdx.y * RG_MB;
@@ -1894,7 +1902,7 @@ regroup_kernel(const float *__restrict__ x, int N, int ntr, const signed char *_
     }
 }
 
-extern "C" int tspws_cu_regroup(const float *d_x, int N, int ntr, const signed char *d_gid, int M, int G,
+extern "C" int tspws_cu_regroup(const float *d_x, int N, int ntr, const short *d_gid, int M, int G,
                                 float *d_out, tspws_stream_t st)
 {
     if (M <= 0 || ntr <= 0) return 0;
@@ -2535,32 +2543,21 @@ static int inv_launch(const tspws_devframe_t *f, const void *d_zout, const void 
     return 0;
 }
 
-/* optional side stream + two events: when set, the two independent halves of the fp32 inverse
- * (polyphase kernel, 4-sample kernel) run concurrently (fork / join, also inside a graph capture) */
-static cudaStream_t g_inv_side = nullptr;
-static cudaEvent_t  g_inv_fork = nullptr, g_inv_join = nullptr;
-extern "C" void tspws_cu_inverse_side_stream(tspws_stream_t side)
-{
-    g_inv_side = (cudaStream_t)side;
-    if (side && !g_inv_fork) {
-        cudaEventCreateWithFlags(&g_inv_fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&g_inv_join, cudaEventDisableTiming);
-    }
-}
-
 extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, const void *d_st, int acc64,
                                 int nseg, const tspws_weight_t *d_rules, void *d_scratch, unsigned int *d_tickets,
-                                float *d_out_ts, float *d_out_ls, tspws_stream_t st)
+                                float *d_out_ts, float *d_out_ls, tspws_stream_t st, tspws_stream_t side, void *ev_fork, void *ev_join)
 {
     if (nseg <= 0) return 0;
     if (acc64 && !f->d_w64) return (int)cudaErrorInvalidValue;
+    cudaStream_t g_inv_side = (cudaStream_t)side;
+    cudaEvent_t  g_inv_fork = (cudaEvent_t)ev_fork, g_inv_join = (cudaEvent_t)ev_join;
     if (acc64) return inv_launch<double>(f, d_zout, d_st, nseg, d_rules, d_scratch, d_tickets, d_out_ts, d_out_ls, (cudaStream_t)st);
     /* fp32: d_zout is the interleaved (Zout, ST) float4 array; d_st only says whether ls is wanted.
      * Every scale writes its contribution to its own scratch slot (polyphase kernel for D >= 32,
      * 4-sample kernel for the rest); the finish kernel adds the slots in scale order. */
     cudaStream_t s = (cudaStream_t)st;
     const int S = f->S;
-    const bool fork = g_inv_side && !g_prof.on && f->nitems_inv2 > 0 && f->ninv4 > 0 && g_inv_side != s;
+    const bool fork = g_inv_side && g_inv_fork && g_inv_join && !g_prof.on && f->nitems_inv2 > 0 && f->ninv4 > 0 && g_inv_side != s;
     cudaStream_t s4 = fork ? g_inv_side : s;
     if (fork) {
         if (cudaEventRecord(g_inv_fork, s) != cudaSuccess || cudaStreamWaitEvent(s4, g_inv_fork, 0) != cudaSuccess) return (int)cudaGetLastError();

@@ -7,6 +7,7 @@
  * No CPU fallback: when CUDA is unusable the call fails with TSPWS_ERR_CUDA.
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -42,6 +43,13 @@ static struct {
     char         *sel;   unsigned int selM, selmtr;
 } G;
 
+/* The library state above (device buffers, cached plan, stream) is one per process: every entry point that
+ * touches it runs under this lock, so concurrent callers are serialised instead of corrupting it (the
+ * reference is callable concurrently on distinct data; here the GPU is the shared resource anyway). */
+static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
+#define LOCK()   pthread_mutex_lock(&g_lock)
+#define UNLOCK() pthread_mutex_unlock(&g_lock)
+
 /* double-buffered slots of tspws_b200_main_batch(): each owns a stream, device buffers and a plan */
 #define TSPWS_NSLOT 2
 static struct batch_slot {
@@ -62,15 +70,29 @@ int tspws_b200_profile_read(char *buf, int cap) { return tspws_cu_profile_read(b
 const char *tspws_b200_version(void) { return "tspws_b200 0.1 (sm_100a)"; }
 unsigned long tspws_b200_kernel_launches(void) { return tspws_cu_launch_count(); }
 
+static void release_device_state(void);
+
 int tspws_b200_set_option(int option, long value)
 {
+    int rc = 0;
+    LOCK();
     switch (option) {
-    case TSPWS_OPT_WRITEBACK: G.opt_writeback = value; return 0;
-    case TSPWS_OPT_FP64_TAIL: G.opt_fp64_tail = value; return 0;
-    case TSPWS_OPT_DEVICE:    G.opt_device = value; G.cuda_state = 0; return 0;
-    case TSPWS_OPT_SS_JACKKNIFE: G.opt_ss_jackknife = value; return 0;
-    default: return TSPWS_ERR_ARG;
+    case TSPWS_OPT_WRITEBACK: G.opt_writeback = value; break;
+    case TSPWS_OPT_FP64_TAIL: G.opt_fp64_tail = value; break;
+    case TSPWS_OPT_DEVICE:
+        /* the stream, the cached plan, the device buffers and the batch slots belong to the previous device:
+         * give them back (on that device) before the next call binds to the new one */
+        if (value != G.opt_device) {
+            if (G.cuda_state == 1) { cudaSetDevice((int)G.opt_device); release_device_state(); }
+            G.opt_device = value;
+        }
+        G.cuda_state = 0;
+        break;
+    case TSPWS_OPT_SS_JACKKNIFE: G.opt_ss_jackknife = value; break;
+    default: rc = TSPWS_ERR_ARG;
     }
+    UNLOCK();
+    return rc;
 }
 long tspws_b200_get_option(int option)
 {
@@ -117,13 +139,13 @@ static void drop_plan(void)
     if (G.plan) { tspws_b200_plan_destroy(G.plan); G.plan = NULL; }
 }
 
-void tspws_b200_shutdown(void)
+/* everything that lives on the current device */
+static void release_device_state(void)
 {
     drop_plan();
     if (G.d_x)   { cudaFree(G.d_x);   G.d_x = NULL;   G.d_x_cap = 0; }
     if (G.d_out) { cudaFree(G.d_out); G.d_out = NULL; G.d_out_cap = 0; }
     if (G.stream) { cudaStreamDestroy(G.stream); G.stream = NULL; }
-    free(G.sel); G.sel = NULL; G.selM = G.selmtr = 0;
     for (int i = 0; i < TSPWS_NSLOT; i++) {
         if (S[i].plan)  tspws_b200_plan_destroy(S[i].plan);
         if (S[i].d_x)   cudaFree(S[i].d_x);
@@ -134,16 +156,26 @@ void tspws_b200_shutdown(void)
     G.cuda_state = 0;
 }
 
+void tspws_b200_shutdown(void)
+{
+    LOCK();
+    release_device_state();
+    free(G.sel); G.sel = NULL; G.selM = G.selmtr = 0;
+    UNLOCK();
+}
+
 int tspws_b200_set_selection(const char *sel, unsigned int M, unsigned int mtr)
 {
+    int rc = 0;
+    LOCK();
     free(G.sel); G.sel = NULL; G.selM = G.selmtr = 0;
-    if (!sel) return 0;
-    if (!M || !mtr) return TSPWS_ERR_ARG;
-    G.sel = (char *)malloc((size_t)M * mtr);
-    if (!G.sel) return TSPWS_ERR_ALLOC;
-    memcpy(G.sel, sel, (size_t)M * mtr);
-    G.selM = M; G.selmtr = mtr;
-    return 0;
+    if (sel) {
+        if (!M || !mtr) rc = TSPWS_ERR_ARG;
+        else if (!(G.sel = (char *)malloc((size_t)M * mtr))) rc = TSPWS_ERR_ALLOC;
+        else { memcpy(G.sel, sel, (size_t)M * mtr); G.selM = M; G.selmtr = mtr; }
+    }
+    UNLOCK();
+    return rc;
 }
 
 static int grow(float **buf, size_t *cap, size_t need)
@@ -165,7 +197,10 @@ static int same_plan_key(const t_tsPWS *a, const t_tsPWS *b)
 
 long tspws_b200_get_stacks(double *st, double *ps, size_t ncoef)
 {
-    return tspws_b200_plan_get_stacks(G.plan, st, ps, ncoef);
+    LOCK();
+    const long rc = tspws_b200_plan_get_stacks(G.plan, st, ps, ncoef);
+    UNLOCK();
+    return rc;
 }
 
 long tspws_b200_get_coherence(double *coh, size_t ncap)
@@ -176,9 +211,11 @@ long tspws_b200_get_coherence(double *coh, size_t ncap)
     if (ncap < n) return TSPWS_ERR_ARG;
     double *ps = (double *)malloc(2 * n * sizeof(double));
     if (!ps) return TSPWS_ERR_ALLOC;
-    long rc = tspws_b200_get_stacks(NULL, ps, n);
+    LOCK();
+    long rc = tspws_b200_plan_get_stacks(G.plan, NULL, ps, n);
+    const unsigned int K = tspws_b200_plan_K(G.plan);
+    UNLOCK();
     if (rc >= 0) {
-        const unsigned int K = tspws_b200_plan_K(G.plan);
         for (size_t i = 0; i < n; i++) coh[i] = hypot(ps[2 * i], ps[2 * i + 1]) / (double)K;
     }
     free(ps);
@@ -195,9 +232,19 @@ static int tspws_check_family(const t_tsPWS *p)
 }
 
 /* ------------------------------------------------------------------------------------ */
+static int tspws_main_locked(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in);
+
 int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
 {
     if (tspws == NULL || out == NULL || in == NULL) { printf("tspws_main: NULL input\n"); return -1; }
+    LOCK();
+    const int rc = tspws_main_locked(tspws, out, in);
+    UNLOCK();
+    return rc;
+}
+
+static int tspws_main_locked(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
+{
 
     t_hdr *hdr = &in->hdr;
     const int max = hdr->max;
@@ -238,7 +285,11 @@ int tspws_main(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
      * in-place fold / mean removal: it costs one extra pass over HBM, which is hidden behind the
      * PCIe copy, and later passes (resampling, convergence, write-back) need the cleaned traces.
      * (The device-resident plan API instead folds / de-means the Kmax group sums, see tspws_plan.c.) */
-    const int exact_prep  = two_stage && (tspws->fold || tspws->lrm);
+    /* ... unless nothing downstream reads the cleaned traces (no write-back, resampling or convergence): then
+     * fold / mean removal are applied to the Kmax group sums inside the plan (linear, within 1e-6 of the
+     * per-trace fp32 form) and the traces are read from HBM exactly once. */
+    const int exact_prep  = two_stage && (tspws->fold || tspws->lrm) &&
+                            (G.opt_writeback || resampling || tspws->convergence);
     t_tsPWS pp = *tspws;
     if (exact_prep) {
         if (tspws_cu_prep(G.d_x, (int)mtr, max, tspws->fold, tspws->lrm, st)) goto cuda_fail;
@@ -288,10 +339,20 @@ cuda_fail:
  * two slots (stream + device buffers + plan each): the H2D copy of pair i+1 runs under the kernels
  * of pair i, and the host never waits between pairs.  Anything else runs pair by pair.
  * ------------------------------------------------------------------------------------ */
+static int main_batch_locked(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsigned int npairs);
+
 int tspws_b200_main_batch(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsigned int npairs)
 {
     if (tspws == NULL || outs == NULL || ins == NULL) { printf("tspws_main: NULL input\n"); return -1; }
     if (!npairs) return 0;
+    LOCK();
+    const int rc = main_batch_locked(tspws, outs, ins, npairs);
+    UNLOCK();
+    return rc;
+}
+
+static int main_batch_locked(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsigned int npairs)
+{
 
     const int resampling = (tspws->subsmpl_N > 0 && tspws->subsmpl_p > 0) || (tspws->jackknife_n > 0 && tspws->jackknife_d > 0);
     int uniform = !resampling && !tspws->convergence && !G.opt_writeback && !G.opt_fp64_tail && ins[0].hdr.max > 0;
@@ -306,7 +367,7 @@ int tspws_b200_main_batch(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsign
         int first = 0;
         for (unsigned int i = 0; i < npairs; i++) {
             t_tsPWS p = p0;
-            int e = tspws_main(&p, &outs[i], &ins[i]);
+            int e = tspws_main_locked(&p, &outs[i], &ins[i]);
             if (i == 0) *tspws = p;
             if (e && !first) first = e;
         }
@@ -333,9 +394,11 @@ int tspws_b200_main_batch(t_tsPWS *tspws, t_tsPWS_out *outs, t_data *ins, unsign
 
     const size_t nelem = (size_t)mtr * (size_t)max;
     const int two_stage  = tspws->Kmax && tspws->Kmax <= mtr;
-    const int exact_prep = two_stage && (tspws->fold || tspws->lrm);
+    /* main stacks only (no write-back, resampling, convergence): fold / mean removal are applied to the group
+     * sums inside the plan, exactly like tspws_main does for such calls -> bit-identical to call-by-call */
+    const int exact_prep = 0;
+    (void)two_stage;
     t_tsPWS pp = *tspws;
-    if (exact_prep) { pp.fold = 0; pp.lrm = 0; }
 
     const int nslot = npairs < TSPWS_NSLOT ? (int)npairs : TSPWS_NSLOT;
     for (int k = 0; k < nslot; k++) {

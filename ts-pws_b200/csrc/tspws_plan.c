@@ -71,7 +71,7 @@ struct tspws_plan {
     int         *h_slot_off;        /* [K+1] first work item of every group */
     void  *own_gsum, *own_exch;
     /* peer exchange over CUDA IPC (two-stage, sharded): see tspws_b200_plan_peer_export / _import */
-    int           peer_on, peer_rank, peer_world, peer_pending;
+    int           peer_on, peer_rank, peer_world, peer_pending, peer_ipc;
     void         *d_peer_region;    /* own: 2 exchange blocks (step parity) + flag words + error word */
     size_t        peer_flag_off, peer_bytes;
     void        **h_peer_ptr;       /* [world] mapped regions (own entry = d_peer_region) */
@@ -685,8 +685,7 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
             unsigned int *flags = (unsigned int *)((char *)pl->d_peer_region + pl->peer_flag_off);
             if ((e = tspws_cu_group_post2_peer(1, pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
                                                0, 0, 0, NULL, NULL, NULL, pl->d_peer_blocks, (double *)pl->d_peer_region, flags,
-                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
-            if ((e = tspws_cu_peer_signal(pl->d_peer_step, pl->d_peer_flags, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->d_peer_flags, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
             pl->peer_pending = 1;
         } else if (pl->mtr_local != pl->mtr_total || pl->exch_bound) {
             /* sharded: the exchange block (group sums + tile totals) has to be complete before the all-reduce */
@@ -751,10 +750,9 @@ int tspws_b200_plan_exchange_is_f64(tspws_plan_t *pl) { return pl && pl->two_sta
 
 /* ---- peer exchange: the ranks of one node map each other's exchange blocks (CUDA IPC) and the sum over
  * ranks is read straight from peer memory inside group_post2_kernel<true>; no collective call ---- */
-int tspws_b200_plan_peer_export(tspws_plan_t *pl, int world, void *handle64)
+static int peer_region_alloc(tspws_plan_t *pl, int world)
 {
-    if (!pl || !handle64) return TSPWS_ERR_NULL;
-    if (!pl->two_stage || !pl->cs2 || sizeof(cudaIpcMemHandle_t) != 64 || world < 1 || world > TSPWS_PEER_MAXW) return TSPWS_ERR_ARG;
+    if (!pl->two_stage || !pl->cs2 || world < 1 || world > TSPWS_PEER_MAXW) return TSPWS_ERR_ARG;
     if (pl->d_peer_region && pl->peer_world != world) return TSPWS_ERR_ARG;
     if (!pl->d_peer_region) {
         const size_t blk = tspws_b200_plan_exchange_bytes(pl) + pl->K * sizeof(double);   /* + presence marks */
@@ -763,28 +761,40 @@ int tspws_b200_plan_peer_export(tspws_plan_t *pl, int world, void *handle64)
         pl->peer_bytes = pl->peer_flag_off + (TSPWS_PEER_MAXW + 1) * sizeof(unsigned int);
         if (cudaMalloc(&pl->d_peer_region, pl->peer_bytes) != cudaSuccess ||
             cudaMemset(pl->d_peer_region, 0, pl->peer_bytes) != cudaSuccess ||
-            cudaMalloc((void **)&pl->d_peer_step, sizeof(unsigned int)) != cudaSuccess ||
-            cudaMemset(pl->d_peer_step, 0, sizeof(unsigned int)) != cudaSuccess ||
+            cudaMalloc((void **)&pl->d_peer_step, 2 * sizeof(unsigned int)) != cudaSuccess ||      /* step, CTA ticket */
+            cudaMemset(pl->d_peer_step, 0, 2 * sizeof(unsigned int)) != cudaSuccess ||
             cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); return TSPWS_ERR_ALLOC; }
     }
+    return 0;
+}
+
+int tspws_b200_plan_peer_export(tspws_plan_t *pl, int world, void *handle64)
+{
+    if (!pl || !handle64) return TSPWS_ERR_NULL;
+    if (sizeof(cudaIpcMemHandle_t) != 64) return TSPWS_ERR_ARG;
+    const int e = peer_region_alloc(pl, world);
+    if (e) return e;
     if (cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, pl->d_peer_region) != cudaSuccess) { cudaGetLastError(); return TSPWS_ERR_CUDA; }
     return 0;
 }
 
-int tspws_b200_plan_peer_import(tspws_plan_t *pl, int rank, int world, const void *handles)
+/* Same-process variant (several plans of one process, on one GPU or on GPUs with peer access enabled): the
+ * region's device pointer instead of an IPC handle.  NULL when the plan cannot take part (not two-stage,
+ * N % 4 != 0, no local traces). */
+void *tspws_b200_plan_peer_region(tspws_plan_t *pl, int world)
 {
-    if (!pl || !handles) return TSPWS_ERR_NULL;
-    if (!pl->d_peer_region || world != pl->peer_world || rank < 0 || rank >= world || pl->h_peer_ptr) return TSPWS_ERR_ARG;
-    void **ptr = (void **)calloc(world, sizeof(void *));
+    if (!pl || peer_region_alloc(pl, world)) return NULL;
+    return pl->d_peer_region;
+}
+
+/* ptr[r]: mapped region of rank r (own entry ignored); takes ownership of ptr on success */
+static int peer_attach(tspws_plan_t *pl, int rank, int world, void **ptr, int ipc)
+{
     void **blocks = (void **)calloc(world, sizeof(void *)), **flags = (void **)calloc(world, sizeof(void *));
     int rc = TSPWS_ERR_CUDA;
-    if (!ptr || !blocks || !flags) { rc = TSPWS_ERR_ALLOC; goto out; }
+    if (!blocks || !flags) { rc = TSPWS_ERR_ALLOC; goto out; }
+    ptr[rank] = pl->d_peer_region;
     for (int r = 0; r < world; r++) {
-        if (r == rank) ptr[r] = pl->d_peer_region;
-        else if (cudaIpcOpenMemHandle(&ptr[r], ((const cudaIpcMemHandle_t *)handles)[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            fprintf(stderr, "tspws_b200: cannot map the exchange block of rank %d (%s)\n", r, cudaGetErrorString(cudaGetLastError()));
-            goto out;
-        }
         blocks[r] = ptr[r];
         flags[r]  = (char *)ptr[r] + pl->peer_flag_off;
     }
@@ -792,16 +802,54 @@ int tspws_b200_plan_peer_import(tspws_plan_t *pl, int rank, int world, const voi
         cudaMalloc(&pl->d_peer_flags, world * sizeof(void *)) != cudaSuccess ||
         cudaMemcpy(pl->d_peer_blocks, blocks, world * sizeof(void *), cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(pl->d_peer_flags, flags, world * sizeof(void *), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); goto out; }
-    pl->h_peer_ptr = ptr; ptr = NULL;
+    pl->h_peer_ptr = ptr;
+    pl->peer_ipc = ipc;
     pl->peer_rank = rank; pl->peer_world = world; pl->peer_on = 1;
     if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
     rc = 0;
 out:
-    if (rc && ptr)                                   /* failed half way: unmap what was mapped */
+    free(blocks); free(flags);
+    return rc;
+}
+
+int tspws_b200_plan_peer_import(tspws_plan_t *pl, int rank, int world, const void *handles)
+{
+    if (!pl || !handles) return TSPWS_ERR_NULL;
+    if (!pl->d_peer_region || world != pl->peer_world || rank < 0 || rank >= world || pl->h_peer_ptr) return TSPWS_ERR_ARG;
+    void **ptr = (void **)calloc(world, sizeof(void *));
+    if (!ptr) return TSPWS_ERR_ALLOC;
+    int rc = TSPWS_ERR_CUDA;
+    for (int r = 0; r < world; r++) {
+        if (r == rank) continue;
+        if (cudaIpcOpenMemHandle(&ptr[r], ((const cudaIpcMemHandle_t *)handles)[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            fprintf(stderr, "tspws_b200: cannot map the exchange block of rank %d (%s)\n", r, cudaGetErrorString(cudaGetLastError()));
+            ptr[r] = NULL;
+            goto out;
+        }
+    }
+    rc = peer_attach(pl, rank, world, ptr, 1);
+out:
+    if (rc) {                                        /* failed half way: unmap what was mapped */
         for (int r = 0; r < world; r++)
             if (r != rank && ptr[r]) cudaIpcCloseMemHandle(ptr[r]);
-    if (rc) cudaGetLastError();
-    free(ptr); free(blocks); free(flags);
+        cudaGetLastError();
+        free(ptr);
+    }
+    return rc;
+}
+
+int tspws_b200_plan_peer_import_ptrs(tspws_plan_t *pl, int rank, int world, void *const *regions)
+{
+    if (!pl || !regions) return TSPWS_ERR_NULL;
+    if (!pl->d_peer_region || world != pl->peer_world || rank < 0 || rank >= world || pl->h_peer_ptr) return TSPWS_ERR_ARG;
+    void **ptr = (void **)calloc(world, sizeof(void *));
+    if (!ptr) return TSPWS_ERR_ALLOC;
+    for (int r = 0; r < world; r++) {
+        ptr[r] = regions[r];
+        if (r != rank && !ptr[r]) { free(ptr); return TSPWS_ERR_ARG; }
+    }
+    const int rc = peer_attach(pl, rank, world, ptr, 0);
+    if (rc) free(ptr);
     return rc;
 }
 
@@ -815,7 +863,7 @@ int tspws_b200_plan_peer_close(tspws_plan_t *pl)
     if (pl->h_peer_ptr) {
         cudaDeviceSynchronize();
         for (int r = 0; r < pl->peer_world; r++)
-            if (r != pl->peer_rank && pl->h_peer_ptr[r]) cudaIpcCloseMemHandle(pl->h_peer_ptr[r]);
+            if (pl->peer_ipc && r != pl->peer_rank && pl->h_peer_ptr[r]) cudaIpcCloseMemHandle(pl->h_peer_ptr[r]);
         free(pl->h_peer_ptr);
         pl->h_peer_ptr = NULL;
         pl->peer_on = 0;
@@ -851,7 +899,7 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
             if ((e = tspws_cu_group_post2_peer(0, NULL, NULL, NULL, pl->N, (int)pl->K, pl->ntile, pl->p.lrm, pl->p.fold,
                                                pl->mean_split ? 1 + pl->hybrid : 0, pl->d_gfin, pl->d_gsum32,
                                                pl->mean_split ? pl->d_gmean : NULL, pl->d_peer_blocks, (double *)pl->d_peer_region, flags,
-                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+                                               pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->d_peer_flags, pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
             gfin = pl->d_gfin;
         } else if (pl->cs2_pending) {
             if ((e = tspws_cu_group_post2(pl->d_cs2_slots, pl->d_cs2_tot, pl->d_cs2_slot_off, pl->N, (int)pl->K, pl->ntile,
@@ -897,10 +945,8 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
         if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), 0, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     }
     if (stop == 4) return 0;
-    tspws_cu_inverse_side_stream(pl->side);
     e = tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), pl->acc64, 1, pl->d_rule, pl->d_invscratch,
-                         pl->d_inv_tickets, d_tspws, d_ls, stream);
-    tspws_cu_inverse_side_stream(NULL);
+                         pl->d_inv_tickets, d_tspws, d_ls, stream, pl->side, pl->ev_fork, pl->ev_join);
     return e ? TSPWS_ERR_CUDA : 0;
 }
 

@@ -74,7 +74,7 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     int rc = 0;
     const size_t N = (size_t)max, ncoef = F->fr->ncoef ? F->fr->ncoef : 1;
     const int B = RS_BATCH;
-    signed char *h_gid = NULL, *d_gid = NULL;
+    short *h_gid = NULL, *d_gid = NULL;          /* group of every trace per realisation (-1: not selected); any Kmax < 32768 */
     float *d_gs = NULL, *d_ls = NULL, *d_ts = NULL, *h_buf = NULL;
     void *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
     double *d_scale = NULL, *h_scale = NULL, *d_sim = NULL, *h_sim = NULL;
@@ -82,15 +82,15 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     unsigned int *d_tk = NULL, *Ks = NULL;
     const int ntk = (max + 255) / 256;
 
-    if (Kmax > 127) { fprintf(stderr, "tspws_b200: two-stage resampling supports Kmax <= 127\n"); return TSPWS_ERR_ARG; }
-    h_gid   = (signed char *)malloc((size_t)B * mtr);
+    if (Kmax > 32767) { fprintf(stderr, "tspws_b200: two-stage resampling supports Kmax <= 32767\n"); return TSPWS_ERR_ARG; }
+    h_gid   = (short *)malloc((size_t)B * mtr * sizeof(short));
     h_scale = (double *)malloc(B * sizeof(double));
     h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
     h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
     h_sim   = (double *)malloc(2 * B * sizeof(double));
     Ks      = (unsigned int *)malloc(B * sizeof(unsigned int));
     if (!h_gid || !h_scale || !h_rules || !h_buf || !h_sim || !Ks) { rc = TSPWS_ERR_ALLOC; goto done; }
-    CKR(cudaMalloc((void **)&d_gid, (size_t)B * mtr));
+    CKR(cudaMalloc((void **)&d_gid, (size_t)B * mtr * sizeof(short)));
     CKR(cudaMalloc((void **)&d_gs, (size_t)B * Kmax * N * sizeof(float)));
     CKR(cudaMalloc((void **)&d_ls, (size_t)B * N * sizeof(float)));
     CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
@@ -112,13 +112,13 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
             for (unsigned int t = 0; t < mtr; t++) K += (row[t] == 1);
             unsigned int r = 0;
             for (unsigned int t = 0; t < mtr; t++)
-                h_gid[(size_t)b * mtr + t] = (row[t] == 1) ? (signed char)rank_group(r++, Kmax, K) : (signed char)-1;
+                h_gid[(size_t)b * mtr + t] = (row[t] == 1) ? (short)rank_group(r++, Kmax, K) : (short)-1;
             Ks[b] = K;
             h_scale[b] = K ? 1.0 / (double)K : 0.0;                                   /* W/K with W = 1 (:672,:686) */
             h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, Kmax, K ? K : 1);
             if (K_out) K_out[m0 + b] = K;
         }
-        CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)nb * mtr, cudaMemcpyHostToDevice, st));
+        CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)nb * mtr * sizeof(short), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_scale, h_scale, nb * sizeof(double), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_rules, h_rules, nb * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
         CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, nb, (int)Kmax, d_gs, st));
@@ -130,7 +130,7 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
         }
         CKK(tspws_cu_forward_fast(&F->acc, d_gs, nb * (int)Kmax, (int)Kmax, d_pps, d_pst, st));
         CKK(tspws_cu_weight(d_pps, d_pst, 0, (int)F->fr->ncoef, nb, d_rules, d_zout, st));
-        CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st));
+        CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st, NULL, NULL, NULL));
         if (d_ref && sim_out) {
             CKK(tspws_cu_simil(d_ts, nb, max, d_ref, d_sim, d_sim + B, st));
             CKR(cudaMemcpyAsync(h_sim, d_sim, 2 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -161,14 +161,15 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     int rc = 0;
     const size_t N = (size_t)max, ncoef = F->fr->ncoef ? F->fr->ncoef : 1;
     const int B = RS_BATCH, ntk = (max + 255) / 256;
-    signed char *h_gid = NULL, *d_gid = NULL, *d_sel = NULL;
+    short *h_gid = NULL, *d_gid = NULL;
+    signed char *d_sel = NULL;
     float *d_S = NULL, *d_ls = NULL, *d_ts = NULL, *h_buf = NULL;
     void *d_ypart = NULL, *d_P = NULL, *d_ps64 = NULL, *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
     double *d_scale = NULL, *h_scale = NULL;
     tspws_weight_t *d_rules = NULL, *h_rules = NULL;
     unsigned int *d_tk = NULL;
 
-    h_gid   = (signed char *)malloc((size_t)M * mtr);
+    h_gid   = (short *)malloc((size_t)M * mtr * sizeof(short));
     h_scale = (double *)malloc(B * sizeof(double));
     h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
     h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
@@ -176,7 +177,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     for (size_t i = 0; i < (size_t)M * mtr; i++) h_gid[i] = (sel[i] == 1) ? 0 : -1;
     for (int b = 0; b < B; b++) { h_scale[b] = 1.0 / (double)(K ? K : 1); h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, K ? K : 1, K ? K : 1); }
 
-    CKR(cudaMalloc((void **)&d_gid, (size_t)M * mtr));
+    CKR(cudaMalloc((void **)&d_gid, (size_t)M * mtr * sizeof(short)));
     CKR(cudaMalloc((void **)&d_sel, (size_t)M * mtr));
     CKR(cudaMalloc((void **)&d_S, (size_t)B * N * sizeof(float)));
     CKR(cudaMalloc((void **)&d_ls, (size_t)B * N * sizeof(float)));
@@ -193,7 +194,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
     CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
     CKR(cudaMemsetAsync(d_ps64, 0, (size_t)M * ncoef * 2 * sizeof(double), st));
-    CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)M * mtr, cudaMemcpyHostToDevice, st));
+    CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)M * mtr * sizeof(short), cudaMemcpyHostToDevice, st));
     CKR(cudaMemcpyAsync(d_sel, sel, (size_t)M * mtr, cudaMemcpyHostToDevice, st));
     CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
     CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
@@ -225,7 +226,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
         CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, st));
         CKK(tspws_cu_weight_mixed((char *)d_ps64 + (size_t)m0 * ncoef * 2 * sizeof(double), d_pst, (int)F->fr->ncoef, nb,
                                   d_rules, d_zout, st));
-        CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st));
+        CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st, NULL, NULL, NULL));
         CKR(cudaMemcpyAsync(h_buf, d_ls, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
         CKR(cudaStreamSynchronize(st));
         for (int b = 0; b < nb; b++) memcpy(ls_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
@@ -275,7 +276,7 @@ int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, flo
          * TSPWS_OPT_SS_JACKKNIFE turns the extension of SURVEY 8(f) rank 3 on */
         if (!two_stage && !ss_jackknife) goto done;
         if (!Cn) goto done;
-        sel = (char *)malloc((size_t)Cn * mtr);
+        sel = (char *)calloc((size_t)Cn, mtr);       /* rows beyond C(n,d) (out->M too large) stay empty, not heap garbage */
         if (!sel) { rc = TSPWS_ERR_ALLOC; goto done; }
         if (sel_override && selM == Cn) memcpy(sel, sel_override, (size_t)Cn * mtr);
         else {
@@ -353,7 +354,7 @@ int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, 
         CKK(tspws_cu_forward_pertrace(&F.pt, d_x + (size_t)t0 * N, nb, 0, d_ypart, st));
         CKK(tspws_cu_coef_matrix(&F.pt, d_ypart, nb, d_Y, d_P, st));
         CKK(tspws_cu_prefix_weight(d_Y, d_P, (int)F.fr->ncoef, nb, d_sst, d_sps, d_rules, d_zout, st));
-        CKK(tspws_cu_inverse(&F.acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st));
+        CKK(tspws_cu_inverse(&F.acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st, NULL, NULL, NULL));
         CKK(tspws_cu_simil(d_ts, nb, max, d_ref, d_sim, d_sim + B, st));
         CKR(cudaMemcpyAsync(h_sim, d_sim, 2 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
         if (out->tsPWS_steps) CKR(cudaMemcpyAsync(out->tsPWS_steps + (size_t)t0 * N, d_ts, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
