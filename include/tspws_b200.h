@@ -179,7 +179,8 @@ int tspws_b200_set_selection(const char *sel, unsigned int M, unsigned int mtr);
 /* Options (all default 0):
  *  TSPWS_OPT_WRITEBACK  1: copy the folded / mean-removed traces back into in->sigall
  *                          like the reference's in-place mutation (src/ts_pws1f_lib.c:77-86,167).
- *  TSPWS_OPT_FP64_TAIL  1: run the two-stage transforms in fp64 instead of fp32.
+ *  TSPWS_OPT_FP64_TAIL  1: run the two-stage transforms in fp64 instead of fp32; 2: also the per-trace transforms of a
+ *                       single-stage stack (generic kernels, slow: a diagnostic for fp32 conditioning).
  *  TSPWS_OPT_DEVICE     n: CUDA device ordinal to use.
  *  TSPWS_OPT_SS_JACKKNIFE 1: EXTENSION: compute the single-stage delete-d jackknife,
  *                          which the reference leaves as an empty stub (src/ts_pws1f_lib.c:711-716): realisation

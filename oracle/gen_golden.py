@@ -114,7 +114,7 @@ def run_reference_real(B, ref):
         st, ps, K = rf.stacks(r["sigall"], pp.Kmax)
         rf.close()
         g[name + "_ls"], g[name + "_tsPWS"] = r["ls"], r["tsPWS"]
-        g[name + "_ps"], g[name + "_st"], g[name + "_K"] = ps.astype(np.complex64), st.astype(np.complex64), np.int64(K)
+        g[name + "_ps"], g[name + "_st"], g[name + "_K"] = ps.astype(np.complex128), st.astype(np.complex128), np.int64(K)
         g[name + "_derived"] = np.array([pp.J, pp.V, pp.s0, pp.b0, pp.w0, pp.fmin, pp.fold], dtype=np.float64)
     return g
 

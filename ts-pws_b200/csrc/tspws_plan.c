@@ -598,7 +598,9 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     pl->mtr_local = mtr_local; pl->mtr_total = mtr_total; pl->offset = trace_offset;
     pl->two_stage = (p->Kmax && p->Kmax <= mtr_total);            /* src/ts_pws1f_lib.c:209 */
     pl->K     = pl->two_stage ? p->Kmax : mtr_total;
-    pl->acc64 = pl->two_stage && tspws_b200_get_option(TSPWS_OPT_FP64_TAIL) != 0;
+    /* TSPWS_OPT_FP64_TAIL: 1 = the Kmax transforms of a two-stage stack in fp64; 2 = also the per-trace transforms
+     * of a single-stage stack (generic kernels, ~30x slower: a diagnostic that separates fp32 conditioning from bugs) */
+    pl->acc64 = tspws_b200_get_option(TSPWS_OPT_FP64_TAIL) >= (pl->two_stage ? 1 : 2);
     pl->csz   = pl->acc64 ? 2 * sizeof(double) : 2 * sizeof(float);
     pl->rule  = tspws_weight_rule(p->wu, p->unbiased, pl->K, mtr_total);
 
@@ -704,8 +706,12 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
         return 0;
     }
     if ((e = tspws_cu_prep(d_sigall, (int)pl->mtr_local, pl->N, pl->p.fold, pl->p.lrm, stream))) return TSPWS_ERR_CUDA;
-    if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
-    if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, 0, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
+    if (pl->acc64) {
+        if ((e = tspws_cu_forward(&pl->dev, d_sigall, 0, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+    } else {
+        if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+    }
+    if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, pl->acc64, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
                                     plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     return 0;
 }
@@ -942,7 +948,7 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
                                             plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
         }
     } else if (pl->summed_across_ranks) {
-        if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), 0, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), pl->acc64, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     }
     if (stop == 4) return 0;
     e = tspws_cu_inverse(&pl->dev, pl->d_zout, plan_st(pl), pl->acc64, 1, pl->d_rule, pl->d_invscratch,
