@@ -173,7 +173,10 @@ long tspws_b200_get_stacks(double *st, double *ps, size_t ncoef);
 /* Explicit selection matrix for the next resampling call(s) of tspws_main
  * (sel[M][mtr] of 0/1, copied).  Lets the CPU oracle and the GPU path use the SAME
  * realisations (the reference draws them from rand(), src/ts_pws1f_lib.c:522,640).
- * Pass NULL to return to rand()-driven plans. */
+ * Pass NULL to return to rand()-driven plans.
+ * Entries > 1 are COUNTS (bootstrap with replacement, an extension: SURVEY 8f rank 3): realisation m stacks trace t
+ * sel[m][t] times, K_m = sum_t sel[m][t]; single-stage stacks only (a two-stage call with counts returns
+ * TSPWS_ERR_ARG).  Counts up to 127 per entry. */
 int tspws_b200_set_selection(const char *sel, unsigned int M, unsigned int mtr);
 
 /* Options (all default 0):

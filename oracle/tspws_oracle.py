@@ -375,17 +375,19 @@ def subsample_single_stage(fr: Frame, x: np.ndarray, sel: np.ndarray, wu: float,
     ST_m = Sel.Y, PS_m = Sel.phasor(Y); weights with (K, K); ls_m in the TIME domain with
     float32 accumulators (:537-542, :579-583).  x: [mtr, max] float32 (already folded / rm)."""
     M, mtr = sel.shape
-    Ks = (sel == 1).sum(axis=1)            # the reference has one K for all rows; the per-row form also
+    cnt = np.where(sel > 0, sel, 0).astype(np.int64)    # 0/1 as in the reference; entries > 1 = bootstrap counts (extension)
+    Ks = cnt.sum(axis=1)                   # the reference has one K for all rows; the per-row form also
     st = np.zeros((M, fr.ncoef), dtype=np.complex128)   # serves the single-stage jackknife extension
     ps = np.zeros((M, fr.ncoef), dtype=np.complex128)
     ls = np.zeros((M, x.shape[1]), dtype=np.float32)
     for t in range(mtr):
         Y = analysis(fr, x[t])
         ph = phasor(Y)
-        use = sel[:, t] == 1
-        st[use] += Y
-        ps[use] += ph
-        ls[use] = (ls[use] + x[t].astype(np.float64)).astype(np.float32)   # float += double
+        for c in range(1, int(cnt[:, t].max()) + 1):    # a trace drawn c times is added c times
+            use = cnt[:, t] >= c
+            st[use] += Y
+            ps[use] += ph
+            ls[use] = (ls[use] + x[t].astype(np.float64)).astype(np.float32)   # float += double
     ts = np.empty_like(ls)
     for m in range(M):
         K = int(Ks[m])

@@ -124,6 +124,30 @@ def test_single_stage_jackknife_extension(pkg, gpu_lib):
     assert O.nerr(r["tsPWS_subsmpl"], ts) <= TOL and O.nerr(r["ls_subsmpl"], ls) <= TOL
 
 
+def test_bootstrap_with_replacement_count_matrix(pkg, gpu_lib):
+    """True bootstrap: the selection matrix holds COUNTS (traces drawn with replacement), the
+    tensor-core contraction takes them as they are; single-stage stack against the oracle with the same counts."""
+    mtr, n, M = 48, 1024, 12
+    x = O.synthetic_traces(mtr, n, seed=77)
+    rng = np.random.default_rng(5)
+    cnt = np.zeros((M, mtr), np.int8)
+    for m in range(M):
+        np.add.at(cnt[m], rng.integers(0, mtr, size=mtr), 1)        # mtr draws with replacement
+    assert cnt.max() > 1 and (cnt.sum(axis=1) == mtr).all()
+    kw = dict(lrm=1, subsmpl_N=M, subsmpl_p=0.5)
+    gpu_lib.tspws_b200_set_selection(cnt.ctypes.data_as(C.c_char_p), M, mtr)
+    try:
+        r = pkg.call_tspws_main(gpu_lib, x, pkg.default_params(**kw))
+        assert r["rc"] == 0
+        r2 = pkg.call_tspws_main(gpu_lib, x, pkg.default_params(Kmax=4, **kw))      # two-stage: counts are refused
+        assert r2["rc"] != 0
+    finally:
+        gpu_lib.tspws_b200_set_selection(None, 0, 0)
+    o = O.tspws_main(O.Params(lrm=1), x)
+    ls, ts = O.subsample_single_stage(o["frame"], o["sigall"], cnt, 2.0, False)
+    assert O.nerr(r["tsPWS_subsmpl"], ts) <= TOL and O.nerr(r["ls_subsmpl"], ls) <= TOL
+
+
 def test_cli_resampling_and_convergence_outputs(gpu_lib):
     """tspws_b200_cli with convergence / AllSteps, jackknife + obin and sub-sampling flags: the files it writes
     (names and layouts of the reference CLI, src/ts_pws1f.c:354-418) equal tspws_main called directly."""

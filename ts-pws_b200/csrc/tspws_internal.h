@@ -218,7 +218,8 @@ int  tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want6
 void tspws_devframe_free(tspws_devframe_t *d);
 
 /* ---- resampling / convergence support ---- */
-int tspws_cu_regroup(const float *d_x, int N, int ntr, const short *d_gid /*[M][ntr]*/, int M, int G,
+/* d_cnt (optional, [M][ntr] like d_gid): every selected trace is added d_cnt times (bootstrap with replacement) */
+int tspws_cu_regroup(const float *d_x, int N, int ntr, const short *d_gid /*[M][ntr]*/, const signed char *d_cnt, int M, int G,
                      float *d_out /*[M][G][N]*/, tspws_stream_t st);
 int tspws_cu_group_total(const float *d_gs, int M, int G, int N, const double *d_scale /*[M]*/, float *d_out /*[M][N]*/,
                          tspws_stream_t st);
@@ -227,6 +228,20 @@ int tspws_cu_select_sum(const void *d_P, int T, int ncoef, const signed char *d_
                         void *d_acc /*double2 [M][ncoef]*/, tspws_stream_t st);
 int tspws_cu_weight_mixed(const void *d_ps64, const void *d_st32, int ncoef, int nseg, const tspws_weight_t *d_rules,
                           void *d_zout, tspws_stream_t st);
+/* the same with PS in float2 (the tensor-core contraction's output) */
+int tspws_cu_weight_mixed32(const void *d_ps32, const void *d_st32, int ncoef, int nseg, const tspws_weight_t *d_rules,
+                            void *d_zout, tspws_stream_t st);
+/* ---- tensor-core resampling contraction (tspws_mma.cu): tile images + tcgen05 GEMM ---- */
+size_t tspws_cu_mma_a_image_bytes(int M, int T);
+size_t tspws_cu_mma_b_image_bytes(int N, int T, int nterm);
+/* counts [M][ld] (signed char; > 0 counts, anything else 0), traces [0, T) -> bf16 A image */
+int tspws_cu_count_image(const signed char *d_cnt, int ld, int M, int T, void *d_img, tspws_stream_t st);
+/* phasors P [nt][ncoef] float2 of traces [t0, t0 + nt), t0 % 64 == 0 -> their k blocks of the bf16 B image (nterm = 2 or 3) */
+int tspws_cu_phasor_image(const void *d_P, int ncoef, int nt, int t0, int kblocks_total, int nterm, void *d_img, tspws_stream_t st);
+/* out [M][ld_out] fp32 (columns [0, N)) = A image . B image^T over kblocks k blocks of 64 */
+int tspws_cu_resample_mma(const void *d_a_img, const void *d_b_img, int nterm, int M, int N, int kblocks,
+                          float *d_out, size_t ld_out, tspws_stream_t st);
+int tspws_cu_mma_selftest(const signed char *h_cnt, const float *h_P, int M, int T, int ncoef, int nterm, float *h_out);
 int tspws_cu_prefix_weight(const void *d_Y, const void *d_P, int ncoef, int B, void *d_st_state, void *d_ps_state,
                            const tspws_weight_t *d_rules, void *d_zout, tspws_stream_t st);
 int tspws_cu_simil(const float *d_cand, int B, int N, const float *d_ref, double *d_sim, double *d_mis, tspws_stream_t st);

@@ -1854,7 +1854,7 @@ extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_
 #define RG_MB 8
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-regroup_kernel(const float *__restrict__ x, int N, int ntr, const short *__restrict__ gid,
+regroup_kernel(const float *__restrict__ x, int N, int ntr, const short *__restrict__ gid, const signed char *__restrict__ cnt,
                int M, int G, float *__restrict__ out)
 {
     const int m0 = blockIdx.y * RG_MB;
@@ -1886,8 +1886,9 @@ regroup_kernel(const float *__restrict__ x, int N, int ntr, const short *__restr
                         }
                         cur[i] = g;
                     }
+                    const double wgt = cnt ? (double)cnt[(size_t)(m0 + i) * ntr + t] : 1.0;
 #pragma unroll
-                    for (int c = 0; c < (VEC ? 4 : 1); c++) acc[i][c] += (double)v[c];
+                    for (int c = 0; c < (VEC ? 4 : 1); c++) acc[i][c] += wgt * (double)v[c];
                 }
             }
         }
@@ -1902,7 +1903,7 @@ regroup_kernel(const float *__restrict__ x, int N, int ntr, const short *__restr
     }
 }
 
-extern "C" int tspws_cu_regroup(const float *d_x, int N, int ntr, const short *d_gid, int M, int G,
+extern "C" int tspws_cu_regroup(const float *d_x, int N, int ntr, const short *d_gid, const signed char *d_cnt, int M, int G,
                                 float *d_out, tspws_stream_t st)
 {
     if (M <= 0 || ntr <= 0) return 0;
@@ -1911,10 +1912,10 @@ extern "C" int tspws_cu_regroup(const float *d_x, int N, int ntr, const short *d
     const bool vec = (N % 4 == 0) && (((uintptr_t)d_x & 15) == 0) && (((uintptr_t)d_out & 15) == 0);
     if (vec) {
         dim3 grid((N / 4 + 255) / 256, (M + RG_MB - 1) / RG_MB);
-        regroup_kernel<true><<<grid, 256, 0, s>>>(d_x, N, ntr, d_gid, M, G, d_out);
+        regroup_kernel<true><<<grid, 256, 0, s>>>(d_x, N, ntr, d_gid, d_cnt, M, G, d_out);
     } else {
         dim3 grid((N + 255) / 256, (M + RG_MB - 1) / RG_MB);
-        regroup_kernel<false><<<grid, 256, 0, s>>>(d_x, N, ntr, d_gid, M, G, d_out);
+        regroup_kernel<false><<<grid, 256, 0, s>>>(d_x, N, ntr, d_gid, d_cnt, M, G, d_out);
     }
     TSPWS_LAUNCHED_N("regroup_kernel", s);
     return 0;
@@ -2023,6 +2024,30 @@ weight_mixed_kernel(const double2 *__restrict__ ps, const float2 *__restrict__ s
     const float2 s = st[o];
     const double f = weight_factor(rules[blockIdx.y], p.x, p.y);
     reinterpret_cast<float4 *>(zout)[o] = make_float4((float)((double)s.x * f), (float)((double)s.y * f), s.x, s.y);
+}
+
+__global__ void __launch_bounds__(256)
+weight_mixed32_kernel(const float2 *__restrict__ ps, const float2 *__restrict__ st, int ncoef,
+                      const tspws_weight_t *__restrict__ rules, float2 *__restrict__ zout)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncoef) return;
+    const size_t o = (size_t)blockIdx.y * ncoef + i;
+    const float2 p = ps[o];
+    const float2 s = st[o];
+    const double f = weight_factor(rules[blockIdx.y], (double)p.x, (double)p.y);
+    reinterpret_cast<float4 *>(zout)[o] = make_float4((float)((double)s.x * f), (float)((double)s.y * f), s.x, s.y);
+}
+
+extern "C" int tspws_cu_weight_mixed32(const void *d_ps32, const void *d_st32, int ncoef, int nseg,
+                                       const tspws_weight_t *d_rules, void *d_zout, tspws_stream_t st)
+{
+    if (nseg <= 0) return 0;
+    dim3 grid((ncoef + 255) / 256, nseg);
+    weight_mixed32_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const float2 *)d_ps32, (const float2 *)d_st32, ncoef, d_rules,
+                                                              (float2 *)d_zout);
+    TSPWS_LAUNCHED_N("weight_mixed32_kernel", (cudaStream_t)st);
+    return 0;
 }
 
 extern "C" int tspws_cu_weight_mixed(const void *d_ps64, const void *d_st32, int ncoef, int nseg,

@@ -83,6 +83,11 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     const int ntk = (max + 255) / 256;
 
     if (Kmax > 32767) { fprintf(stderr, "tspws_b200: two-stage resampling supports Kmax <= 32767\n"); return TSPWS_ERR_ARG; }
+    for (size_t i = 0; i < (size_t)nres * mtr; i++)
+        if (sel[i] > 1) {
+            fprintf(stderr, "tspws_b200: count matrices (bootstrap with replacement) are supported for single-stage stacks only\n");
+            return TSPWS_ERR_ARG;
+        }
     h_gid   = (short *)malloc((size_t)B * mtr * sizeof(short));
     h_scale = (double *)malloc(B * sizeof(double));
     h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
@@ -121,7 +126,7 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
         CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)nb * mtr * sizeof(short), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_scale, h_scale, nb * sizeof(double), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_rules, h_rules, nb * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
-        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, nb, (int)Kmax, d_gs, st));
+        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, NULL, nb, (int)Kmax, d_gs, st));
         if (ls_rows) {
             CKK(tspws_cu_group_total(d_gs, nb, (int)Kmax, max, d_scale, d_ls, st));
             CKR(cudaMemcpyAsync(h_buf, d_ls, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -156,26 +161,39 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
                                   const char *sel, unsigned int M, unsigned int K, unsigned int *k_rows /* out or NULL */,
                                   float **ls_rows, float **ts_rows, cudaStream_t st)
 {
-    /* K != 0: every realisation keeps exactly K traces (sub-sampling); K == 0: realisation m keeps the
-     * traces its selection row marks, K_m of them (jackknife), written to k_rows[m] */
+    /* sel[m][t] = how many times realisation m stacks trace t: 0 / 1 (sub-sampling, jackknife) or a count (bootstrap
+     * with replacement); K_m = sum_t sel[m][t] is written to k_rows[m].  (K: the count every row is expected to have
+     * in sub-sampling mode; only used for the weights' K when all rows agree -- the per-row sums are what is applied.)
+     * Phase stacks: PS_m = sum_t sel[m][t] phasor(Y_t), the [M x T] . [T x 2 ncoef] contraction, on the tensor cores
+     * (tspws_mma.cu) unless TSPWS_NO_MMA=1 (the SIMT kernel it replaced, kept for the before / after profile). */
     int rc = 0;
     const size_t N = (size_t)max, ncoef = F->fr->ncoef ? F->fr->ncoef : 1;
     const int B = RS_BATCH, ntk = (max + 255) / 256;
+    const int use_mma = !getenv("TSPWS_NO_MMA") || atoi(getenv("TSPWS_NO_MMA")) == 0;
+    const int nterm = (getenv("TSPWS_MMA_TERMS") && atoi(getenv("TSPWS_MMA_TERMS")) == 3) ? 3 : 2;
+    const int kblocks = ((int)mtr + 63) / 64;
     short *h_gid = NULL, *d_gid = NULL;
     signed char *d_sel = NULL;
     float *d_S = NULL, *d_ls = NULL, *d_ts = NULL, *h_buf = NULL;
-    void *d_ypart = NULL, *d_P = NULL, *d_ps64 = NULL, *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
+    void *d_ypart = NULL, *d_P = NULL, *d_ps = NULL, *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
+    void *d_aimg = NULL, *d_bimg = NULL;
     double *d_scale = NULL, *h_scale = NULL;
     tspws_weight_t *d_rules = NULL, *h_rules = NULL;
-    unsigned int *d_tk = NULL;
+    unsigned int *d_tk = NULL, *km_all = NULL;
+    (void)K;
 
     h_gid   = (short *)malloc((size_t)M * mtr * sizeof(short));
     h_scale = (double *)malloc(B * sizeof(double));
     h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
     h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
-    if (!h_gid || !h_scale || !h_rules || !h_buf) { rc = TSPWS_ERR_ALLOC; goto done; }
-    for (size_t i = 0; i < (size_t)M * mtr; i++) h_gid[i] = (sel[i] == 1) ? 0 : -1;
-    for (int b = 0; b < B; b++) { h_scale[b] = 1.0 / (double)(K ? K : 1); h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, K ? K : 1, K ? K : 1); }
+    km_all  = (unsigned int *)calloc(M ? M : 1, sizeof(unsigned int));
+    if (!h_gid || !h_scale || !h_rules || !h_buf || !km_all) { rc = TSPWS_ERR_ALLOC; goto done; }
+    for (unsigned int m = 0; m < M; m++)
+        for (unsigned int t = 0; t < mtr; t++) {
+            const int c = sel[(size_t)m * mtr + t];
+            h_gid[(size_t)m * mtr + t] = c > 0 ? 0 : -1;
+            if (c > 0) km_all[m] += (unsigned int)c;
+        }
 
     CKR(cudaMalloc((void **)&d_gid, (size_t)M * mtr * sizeof(short)));
     CKR(cudaMalloc((void **)&d_sel, (size_t)M * mtr));
@@ -184,7 +202,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
     CKR(cudaMalloc(&d_ypart, (size_t)TR_BATCH * (F->pt.ypart_len ? F->pt.ypart_len : 1) * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_P, (size_t)TR_BATCH * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_ps64, (size_t)M * ncoef * 2 * sizeof(double)));
+    CKR(cudaMalloc(&d_ps, (size_t)M * ncoef * 2 * (use_mma ? sizeof(float) : sizeof(double))));
     CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
@@ -193,39 +211,49 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
     CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
     CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
-    CKR(cudaMemsetAsync(d_ps64, 0, (size_t)M * ncoef * 2 * sizeof(double), st));
     CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)M * mtr * sizeof(short), cudaMemcpyHostToDevice, st));
     CKR(cudaMemcpyAsync(d_sel, sel, (size_t)M * mtr, cudaMemcpyHostToDevice, st));
-    CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
-    CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+    if (use_mma) {
+        /* tile images: counts (A) once, unit phasors (B) batch by batch as the traces are transformed */
+        CKR(cudaMalloc(&d_aimg, tspws_cu_mma_a_image_bytes((int)M, (int)mtr)));
+        CKR(cudaMalloc(&d_bimg, tspws_cu_mma_b_image_bytes(2 * (int)F->fr->ncoef, (int)mtr, nterm)));
+        CKK(tspws_cu_count_image(d_sel, (int)mtr, (int)M, (int)mtr, d_aimg, st));
+    } else {
+        CKR(cudaMemsetAsync(d_ps, 0, (size_t)M * ncoef * 2 * sizeof(double), st));
+    }
 
-    /* phase stacks: PS_m = sum_t sel[m][t] phasor(Y_t); every trace is transformed once */
+    /* every trace is transformed once: per-trace coefficients -> unit phasors -> image (or the SIMT contraction) */
     for (unsigned int t0 = 0; t0 < mtr; t0 += TR_BATCH) {
         const int nt = (int)((mtr - t0 < TR_BATCH) ? mtr - t0 : TR_BATCH);
         CKK(tspws_cu_forward_pertrace(&F->pt, d_x + (size_t)t0 * N, nt, 0, d_ypart, st));
         CKK(tspws_cu_coef_matrix(&F->pt, d_ypart, nt, NULL, d_P, st));
-        CKK(tspws_cu_select_sum(d_P, nt, (int)F->fr->ncoef, d_sel, (int)mtr, (int)t0, (int)M, d_ps64, st));
+        if (use_mma) CKK(tspws_cu_phasor_image(d_P, (int)F->fr->ncoef, nt, (int)t0, kblocks, nterm, d_bimg, st));
+        else         CKK(tspws_cu_select_sum(d_P, nt, (int)F->fr->ncoef, d_sel, (int)mtr, (int)t0, (int)M, d_ps, st));
     }
-    /* per batch of resamples: time-domain sums -> ls, ST by linearity, weights, inverse */
+    if (use_mma)
+        CKK(tspws_cu_resample_mma(d_aimg, d_bimg, nterm, (int)M, 2 * (int)F->fr->ncoef, kblocks, (float *)d_ps, 2 * ncoef, st));
+
+    /* per batch of realisations: time-domain sums -> ls, ST by linearity, weights, inverse */
     for (unsigned int m0 = 0; m0 < M; m0 += B) {
         const int nb = (int)((M - m0 < (unsigned int)B) ? M - m0 : (unsigned int)B);
-        if (!K) {                                  /* per-realisation trace counts */
-            for (int b = 0; b < nb; b++) {
-                unsigned int km = 0;
-                for (unsigned int t = 0; t < mtr; t++) km += sel[(size_t)(m0 + b) * mtr + t] == 1;
-                if (k_rows) k_rows[m0 + b] = km;
-                if (!km) km = 1;
-                h_scale[b] = 1.0 / (double)km;
-                h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, km, km);
-            }
-            CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
-            CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+        for (int b = 0; b < nb; b++) {
+            unsigned int km = km_all[m0 + b];
+            if (k_rows) k_rows[m0 + b] = km;
+            if (!km) km = 1;
+            h_scale[b] = 1.0 / (double)km;
+            h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, km, km);
         }
-        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, nb, 1, d_S, st));
+        CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
+        CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, d_sel + (size_t)m0 * mtr, nb, 1, d_S, st));
         CKK(tspws_cu_group_total(d_S, nb, 1, max, d_scale, d_ls, st));
         CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, st));
-        CKK(tspws_cu_weight_mixed((char *)d_ps64 + (size_t)m0 * ncoef * 2 * sizeof(double), d_pst, (int)F->fr->ncoef, nb,
-                                  d_rules, d_zout, st));
+        if (use_mma)
+            CKK(tspws_cu_weight_mixed32((char *)d_ps + (size_t)m0 * ncoef * 2 * sizeof(float), d_pst, (int)F->fr->ncoef, nb,
+                                        d_rules, d_zout, st));
+        else
+            CKK(tspws_cu_weight_mixed((char *)d_ps + (size_t)m0 * ncoef * 2 * sizeof(double), d_pst, (int)F->fr->ncoef, nb,
+                                      d_rules, d_zout, st));
         CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st, NULL, NULL, NULL));
         CKR(cudaMemcpyAsync(h_buf, d_ls, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
         CKR(cudaStreamSynchronize(st));
@@ -235,10 +263,10 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
         for (int b = 0; b < nb; b++) memcpy(ts_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
     }
 done:
-    free(h_gid); free(h_scale); free(h_rules); free(h_buf);
+    free(h_gid); free(h_scale); free(h_rules); free(h_buf); free(km_all);
     cudaFree(d_gid); cudaFree(d_sel); cudaFree(d_S); cudaFree(d_ls); cudaFree(d_ts); cudaFree(d_ypart); cudaFree(d_P);
-    cudaFree(d_ps64); cudaFree(d_pps); cudaFree(d_pst); cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale);
-    cudaFree(d_rules); cudaFree(d_tk);
+    cudaFree(d_ps); cudaFree(d_pps); cudaFree(d_pst); cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale);
+    cudaFree(d_rules); cudaFree(d_tk); cudaFree(d_aimg); cudaFree(d_bimg);
     return rc;
 }
 
