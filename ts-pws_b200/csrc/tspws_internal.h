@@ -89,6 +89,7 @@ typedef struct {
     void              *d_wi32;    /* float2[]: origin-aligned, zero-padded filters of the 4-sample inverse */
     tspws_fwd_item_t  *d_items;   /* [nitems]  generic kernel: all scales   */
     int                nitems;
+    int               *h_item_first; /* host: [S+1] first generic item of every scale */
     tspws_fwd_item_t  *d_items_gen; /* [nitems_gen] generic kernel: only scales with lg < 0 */
     int                nitems_gen;
     int                f64_maxl;  /* mean split: filters at least this long are transformed unsplit in fp32 */
@@ -170,8 +171,20 @@ int tspws_cu_forward(const tspws_devframe_t *f, const void *d_x, int in64, int a
                      int ntr, int chunk, void *d_part_ps, void *d_part_st, tspws_stream_t st);
 /* fp32 fast path: polyphase register-tiled kernel for the scales it covers + generic kernel for the
  * rest.  Chunk-accumulate mode (f->per_trace == 0): same outputs as tspws_cu_forward. */
+/* skip5: the first skip5 items of the D >= 32 list (coarsest scales first) are left out -- the dense tensor-core
+ * transform covers them (tspws_cu_forward_dense) */
+/* generic kernel, ONE fp32 trace, only the items [item0, nitems) (= the scales from some scale on): Y -> d_st, phasor -> d_ps */
+int tspws_cu_forward_one(const tspws_devframe_t *f, const float *d_x, int item0, void *d_ps, void *d_st, tspws_stream_t st);
 int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, int chunk,
-                          void *d_part_ps, void *d_part_st, tspws_stream_t st);
+                          void *d_part_ps, void *d_part_st, int skip5, tspws_stream_t st);
+/* ---- coarse scales of the single-stage forward transform as one dense GEMM on tcgen05 (tspws_mma.cu) ---- */
+size_t tspws_cu_dense_ximg_bytes(int ntr, int N);
+size_t tspws_cu_dense_wimg_bytes(int ncol, int N);
+int tspws_cu_dense_wimage(const tspws_devframe_t *f, int s0, int ci0, int ncd, void *d_img, tspws_stream_t st);
+int tspws_cu_forward_dense(const float *d_x, int ntr, int N, const void *d_wimg, int ncd, void *d_ximg,
+                           float *d_tsum, float *d_sumtrace, float *d_part, tspws_stream_t st);
+int tspws_cu_dense_finish(const float *d_part, int ntr, int ncd, const void *d_ysum, int ci0, void *d_pps0, void *d_pst0,
+                          tspws_stream_t st);
 /* Per-trace mode (f->per_trace == 1): raw coefficients of each of the ntr traces (split over
  * phase ranges for coarse scales) go to d_ypart [f->ypart_len * ntr] complex fp32 ... */
 /* peer exchange (CUDA IPC mappings of the other ranks' exchange blocks), see group_post2_kernel<true> */

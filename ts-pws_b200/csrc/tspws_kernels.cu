@@ -798,6 +798,17 @@ static int fwd_launch(const tspws_devframe_t *f, const void *d_x, int ntr, int c
     return 0;
 }
 
+extern "C" int tspws_cu_forward_one(const tspws_devframe_t *f, const float *d_x, int item0, void *d_ps, void *d_st, tspws_stream_t st)
+{
+    const int n = f->nitems - item0;
+    if (n <= 0) return 0;
+    dim3 grid((n + FWD_WARPS - 1) / FWD_WARPS, 1);
+    fwd_kernel<float, float, 1><<<grid, FWD_WARPS * 32, 0, (cudaStream_t)st>>>(f->d_scale, (const float2 *)f->d_w32, f->d_items + item0, n,
+        d_x, f->N, 1, 1, f->ncoef, (float2 *)d_ps, (float2 *)d_st);
+    TSPWS_LAUNCHED_N("fwd_kernel", (cudaStream_t)st);
+    return 0;
+}
+
 extern "C" int tspws_cu_forward(const tspws_devframe_t *f, const void *d_x, int in64, int acc64,
                                 int ntr, int chunk, void *d_part_ps, void *d_part_st, tspws_stream_t st)
 {
@@ -1584,7 +1595,7 @@ extern "C" int tspws_cu_forward_f64(const tspws_devframe_t *f, const double *d_x
 }
 
 extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, int chunk,
-                                     void *d_part_ps, void *d_part_st, tspws_stream_t st)
+                                     void *d_part_ps, void *d_part_st, int skip5, tspws_stream_t st)
 {
     if (ntr <= 0) return 0;
     if (f->per_trace) return (int)cudaErrorInvalidValue;
@@ -1600,15 +1611,16 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
     { const char *e = getenv("TSPWS_FW_CB"); if (e && atoi(e) > 0) cb = atoi(e); }
     if (cb > nchunk) cb = nchunk;
 #define FW_ACC_LAUNCH(LGV)                                                                              \
-    if (f->fw_lg_begin[LGV + 1] > f->fw_lg_begin[LGV]) {                                                \
-        const int nb = f->fw_lg_begin[LGV + 1] - f->fw_lg_begin[LGV];                                   \
+    if (f->fw_lg_begin[LGV + 1] > f->fw_lg_begin[LGV] + (LGV == 5 ? skip5 : 0)) {                       \
+        const int ib = f->fw_lg_begin[LGV] + (LGV == 5 ? skip5 : 0);                                    \
+        const int nb = f->fw_lg_begin[LGV + 1] - ib;                                                    \
         const int nig = (nb + FW_WARPS - 1) / FW_WARPS;                                                 \
         /* full super-blocks have nig*cb CTAs; a short last one is padded to the same count (extra CTAs exit) */ \
         dim3 grid((unsigned)(((nchunk + cb - 1) / cb) * nig * cb));                                      \
         if (smem > 40 * 1024)                                                                           \
             cudaFuncSetAttribute(fwd2_acc_kernel<LGV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         fwd2_acc_kernel<LGV><<<grid, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, \
-            f->d_items2, f->fw_lg_begin[LGV], f->fw_lg_begin[LGV + 1], d_x, f->N, ntr, chunk, f->ncoef,  \
+            f->d_items2, ib, f->fw_lg_begin[LGV + 1], d_x, f->N, ntr, chunk, f->ncoef,                  \
             (float2 *)d_part_ps, (float2 *)d_part_st, f->fw_smem_per_warp, cb);                          \
         TSPWS_LAUNCHED_N("fwd2_acc_kernel<" #LGV ">", s);                                                                               \
     }

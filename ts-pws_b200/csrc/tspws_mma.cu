@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "tspws_internal.h"
 
@@ -359,4 +360,312 @@ extern "C" int tspws_cu_mma_selftest(const signed char *h_cnt, const float *h_P,
 out:
     cudaFree(d_cnt); cudaFree(d_P); cudaFree(d_out); cudaFree(d_a); cudaFree(d_b);
     return rc;
+}
+
+/* ===================================================================================== */
+/* Coarse scales of the single-stage forward transform as ONE dense GEMM on tcgen05       */
+/*                                                                                       */
+/* For the scales with few, long filters (D >= 256: L = 2560 .. N taps, Ns <= 64 coefficients)  */
+/* the transform of a batch of traces (src/FWTa/wavelet_v7.c:43-64 -> cdotx_dc, cdotx.c:35-72)  */
+/* is a plain matrix product  Y[t][(s,m,c)] = sum_n x_t[n] W[(s,m,c)][n],  W = the conjugated  */
+/* filter of scale s placed (circularly) at coefficient m -- [traces x N] . [N x 2 ncoarse].    */
+/* On the SIMT polyphase kernel these octaves were 4/7 of the D >= 32 time.  Here:              */
+/*   A = traces      [mtr x N]  as THREE bf16 terms x = x0 + x1 + x2 (24 mantissa bits: fp32-exact)  */
+/*   B = W           [2 ncoarse x N] as three bf16 terms (built once per plan on the device)     */
+/*   D = x0 W0 + x0 W1 + x1 W0 + x1 W1 + x0 W2 + x2 W0   (everything above 2^-25), fp32 in TMEM  */
+/* Two terms (2^-17) are NOT enough: a trace whose coefficient happens to be ~1e-4 of the typical     */
+/* magnitude has an ill-conditioned phase, and one such (trace, coefficient) pair in 150 000 moved   */
+/* the coherence by 1.2e-4 (tools/_dense_check2.py); fp32-faithful products keep it at the SIMT      */
+/* path's 2e-6.                                                                                    */
+/* and the epilogue is the phasor accumulate of src/ts_pws1f_lib.c:486-494: unit phasor of     */
+/* every (trace, coefficient), summed over the 128 traces of the M tile (warp transpose-reduce   */
+/* + shared memory) into one partial row per M tile; the rows are added in tile order later      */
+/* (deterministic).  The per-trace coefficients never leave the SM.                              */
+/* ===================================================================================== */
+#define FD_STAGES 2
+#define FD_NT 3                                          /* bf16 terms per operand */
+#define FD_STAGE_BYTES (2 * FD_NT * MMA_TILE_BYTES)    /* A terms 0..2, B terms 0..2 */
+
+__device__ __forceinline__ void fd_phasor(float re, float im, float &pr, float &pi)
+{
+    const float s = re * re + im * im;
+    if (s > 1e-30f && s < 1e30f) { const float inv = rsqrtf(s); pr = re * inv; pi = im * inv; }
+    else {
+        const float a = hypotf(re, im);
+        if (a > 0.f && a <= 3.0e38f) { pr = re / a; pi = im / a; } else { pr = 0.f; pi = 0.f; }   /* skipped like :492 */
+    }
+}
+
+/* one stage of the transposing butterfly: lanes l and l ^ HALF exchange halves of the 2 HALF live values */
+template <int HALF>
+__device__ __forceinline__ void fd_transpose_stage(float (&f)[32], const int lane)
+{
+    const bool up = (lane & HALF) != 0;
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+        const float send = up ? f[i] : f[i + HALF];
+        const float keep = up ? f[i + HALF] : f[i];
+        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, HALF);
+    }
+}
+
+/* The tensor core adds into its fp32 accumulator with truncation, not round-to-nearest: measured on B200
+ * (tools/_mma_acc_check.py) the result of a K = 16384 accumulation is biased by -1.7e-5 relative, linearly in K
+ * -- 8e-5 on the coherence of the coarse scales.  So the K loop is cut into chunks of FD_CHUNK k blocks (512 samples:
+ * bias < 1e-6): every chunk accumulates into one of TWO TMEM accumulators, and the epilogue warps drain the finished
+ * one into fp32 registers (round-to-nearest adds) while the next chunk's MMAs run -- the promotion trick of FP8 GEMMs. */
+#define FD_CHUNK 8
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat16 *__restrict__ w_img,
+                     int kblocks, int ncol, float *__restrict__ part /* [mtiles][ncol] */, int term_mask)
+{
+    extern __shared__ __align__(1024) unsigned char mma_smem[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(mma_smem) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full   = reinterpret_cast<uint64_t *>(tiles + (size_t)FD_STAGES * FD_STAGE_BYTES);
+    uint64_t *empty  = full + FD_STAGES;
+    uint64_t *tfull  = empty + FD_STAGES;       /* [2] accumulator complete */
+    uint64_t *tempty = tfull + 2;               /* [2] accumulator drained (4 epilogue warps) */
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    float (*colsum)[MMA_TILE_MN] = reinterpret_cast<float (*)[MMA_TILE_MN]>(tiles);   /* [4 warps][128 columns]: reuses stage 0 after the MMAs */
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x, mt = blockIdx.y;          /* column tiles fastest: the CTAs that share an A tile run together */
+    constexpr unsigned TMEM_COLS = 2 * MMA_TILE_MN;
+    const int nchunk = (kblocks + FD_CHUNK - 1) / FD_CHUNK;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < FD_STAGES; s++) { m_mbar_init(full + s, 1); m_mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; s++) { m_mbar_init(tfull + s, 1); m_mbar_init(tempty + s, 4); }
+        m_fence_barrier_init();
+    } else if (warp == 2) {
+        m_tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    m_tc_fence_before();
+    __syncthreads();
+    m_tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        for (int kb = 0; kb < kblocks; kb++) {
+            const int s = kb % FD_STAGES;
+            if (kb >= FD_STAGES) m_mbar_wait(empty + s, ((kb / FD_STAGES) & 1) ^ 1);
+            unsigned char *st = tiles + (size_t)s * FD_STAGE_BYTES;
+            m_mbar_expect_tx(full + s, FD_STAGE_BYTES);
+            /* images: [tile][kb][term] -> the terms of a tile are one contiguous 48 KiB copy */
+            m_bulk_g2s(st, x_img + ((size_t)mt * kblocks + kb) * FD_NT * (MMA_TILE_MN * MMA_TILE_K), FD_NT * MMA_TILE_BYTES, full + s);
+            m_bulk_g2s(st + FD_NT * MMA_TILE_BYTES, w_img + ((size_t)nt * kblocks + kb) * FD_NT * (MMA_TILE_MN * MMA_TILE_K), FD_NT * MMA_TILE_BYTES, full + s);
+        }
+    } else if (warp == 1 && lane == 0) {
+        for (int c = 0; c < nchunk; c++) {
+            const int buf = c & 1;
+            if (c >= 2) { m_mbar_wait(tempty + buf, ((c >> 1) & 1) ^ 1); m_tc_fence_after(); }
+            const uint32_t acc = tmem + (uint32_t)buf * MMA_TILE_MN;
+            const int kb1 = min(kblocks, (c + 1) * FD_CHUNK);
+            for (int kb = c * FD_CHUNK; kb < kb1; kb++) {
+                const int s = kb % FD_STAGES;
+                m_mbar_wait(full + s, (kb / FD_STAGES) & 1);
+                m_tc_fence_after();
+                const unsigned char *st = tiles + (size_t)s * FD_STAGE_BYTES;
+                const unsigned char *a = st, *b = st + FD_NT * MMA_TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < MMA_TILE_K / MMA_UMMA_K; k++) {
+                    const unsigned kby = k * MMA_UMMA_K * 2;
+                    /* smallest products first: they are added while the accumulator is still small */
+                    bool first = (kb == c * FD_CHUNK) && k == 0;
+#define FD_MMA(I, J) do { if (term_mask & (1 << (I + J))) { m_umma_bf16(acc, m_smem_desc(a + (I) * MMA_TILE_BYTES, kby), m_smem_desc(b + (J) * MMA_TILE_BYTES, kby), MMA_IDESC, !first); first = false; } } while (0)
+                    FD_MMA(2, 0); FD_MMA(0, 2); FD_MMA(1, 1); FD_MMA(1, 0); FD_MMA(0, 1); FD_MMA(0, 0);
+#undef FD_MMA
+                }
+                m_umma_commit(empty + s);
+            }
+            m_umma_commit(tfull + buf);
+        }
+    } else if (warp >= 2) {
+        /* ---- epilogue warps: thread = trace (TMEM lane); drain every finished chunk into registers ---- */
+        const int q = warp & 3;
+        float y[MMA_TILE_MN];
+#pragma unroll
+        for (int j = 0; j < MMA_TILE_MN; j++) y[j] = 0.f;
+        for (int c = 0; c < nchunk; c++) {
+            const int buf = c & 1;
+            m_mbar_wait(tfull + buf, (c >> 1) & 1);
+            m_tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < MMA_TILE_MN; c0 += 32) {
+                uint32_t v[32];
+                m_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MMA_TILE_MN + c0), v);
+#pragma unroll
+                for (int j = 0; j < 32; j++) y[c0 + j] += __uint_as_float(v[j]);
+            }
+            m_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(m_smem_u32(tempty + buf)) : "memory");
+        }
+        /* phasor of every (trace, coefficient), then the sum over this warp's 32 traces */
+#pragma unroll
+        for (int c0 = 0; c0 < MMA_TILE_MN; c0 += 32) {
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) fd_phasor(y[c0 + j], y[c0 + j + 1], f[j], f[j + 1]);
+            /* transposing butterfly over the 32 lanes (= traces): lane j ends with the sum of column j */
+            fd_transpose_stage<16>(f, lane); fd_transpose_stage<8>(f, lane); fd_transpose_stage<4>(f, lane);
+            fd_transpose_stage<2>(f, lane);  fd_transpose_stage<1>(f, lane);
+            colsum[q][c0 + lane] = f[0];
+        }
+    }
+    m_tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < MMA_TILE_MN) {
+        const int col = nt * MMA_TILE_MN + threadIdx.x;
+        if (col < ncol)
+            part[(size_t)mt * ncol + col] = ((colsum[2][threadIdx.x] + colsum[3][threadIdx.x]) + colsum[0][threadIdx.x]) + colsum[1][threadIdx.x];
+    }
+    if (warp == 2) m_tmem_dealloc(tmem, TMEM_COLS);
+}
+
+/* traces x [ntr][N] fp32 -> A image [mtiles][kblocks][hi | lo], rows beyond ntr zero; and per M tile the column sums
+ * of its traces (the linear stack of the coarse scales is the transform of the summed trace, by linearity) */
+__global__ void __launch_bounds__(256)
+trace_image_kernel(const float *__restrict__ x, int ntr, int N, int kblocks, __nv_bfloat16 *__restrict__ img, float *__restrict__ tsum /* [mtiles][N] */)
+{
+    extern __shared__ __align__(16) unsigned char ti_smem[];
+    __nv_bfloat16 (*s_img)[MMA_TILE_MN * MMA_TILE_K] = reinterpret_cast<__nv_bfloat16 (*)[MMA_TILE_MN * MMA_TILE_K]>(ti_smem);
+    __shared__ float s_sum[4][MMA_TILE_K];
+    const int kb = blockIdx.x, mt = blockIdx.y;
+    const int k = threadIdx.x & 63, r0 = threadIdx.x >> 6;             /* 4 rows per pass, 64 consecutive samples per row */
+    float acc = 0.f;
+    for (int r = r0; r < MMA_TILE_MN; r += 4) {
+        const int t = mt * MMA_TILE_MN + r;
+        const float v = t < ntr ? __ldg(x + (size_t)t * N + (size_t)kb * MMA_TILE_K + k) : 0.f;
+        acc += v;
+        const unsigned o = mma_img_offset(r, k);
+        float rem = v;
+#pragma unroll
+        for (int term = 0; term < FD_NT; term++) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+            s_img[term][o] = h;
+            rem -= __bfloat162float(h);
+        }
+    }
+    s_sum[r0][k] = acc;
+    __syncthreads();
+    if (threadIdx.x < MMA_TILE_K)
+        tsum[(size_t)mt * N + (size_t)kb * MMA_TILE_K + threadIdx.x] = (s_sum[0][threadIdx.x] + s_sum[1][threadIdx.x]) + (s_sum[2][threadIdx.x] + s_sum[3][threadIdx.x]);
+    uint4 *dst = reinterpret_cast<uint4 *>(img + ((size_t)mt * kblocks + kb) * FD_NT * (MMA_TILE_MN * MMA_TILE_K));
+    const uint4 *src = reinterpret_cast<const uint4 *>(&s_img[0][0]);
+    for (int e = threadIdx.x; e < FD_NT * MMA_TILE_BYTES / 16; e += blockDim.x) dst[e] = src[e];
+}
+
+/* sum trace = sum over the M tiles (fixed order), fp64 accumulate -> fp32 */
+__global__ void __launch_bounds__(256)
+tile_sum_kernel(const float *__restrict__ tsum, int mtiles, int N, float *__restrict__ out)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double a = 0.0;
+    for (int m = 0; m < mtiles; m++) a += (double)tsum[(size_t)m * N + n];
+    out[n] = (float)a;
+}
+
+/* PS of the dense coefficients = sum over the M tiles of the partial rows (fixed order); ST = the transform of the
+ * summed trace.  Both go to chunk 0 of the per-chunk partial arrays (the other chunks hold zeros for these coefficients). */
+__global__ void __launch_bounds__(256)
+dense_finish_kernel(const float *__restrict__ part, int mtiles, int ncd, const float2 *__restrict__ ysum /* [ncoef] */, int ci0,
+                    float2 *__restrict__ pps0, float2 *__restrict__ pst0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncd) return;
+    float pr = 0.f, pi = 0.f;
+    for (int m = 0; m < mtiles; m++) { pr += part[(size_t)m * 2 * ncd + 2 * i]; pi += part[(size_t)m * 2 * ncd + 2 * i + 1]; }
+    pps0[ci0 + i] = make_float2(pr, pi);
+    pst0[ci0 + i] = ysum[ci0 + i];
+}
+
+extern "C" size_t tspws_cu_dense_ximg_bytes(int ntr, int N)
+{
+    return (size_t)((ntr + MMA_TILE_MN - 1) / MMA_TILE_MN) * (N / MMA_TILE_K) * FD_NT * MMA_TILE_BYTES;
+}
+extern "C" size_t tspws_cu_dense_wimg_bytes(int ncol, int N)
+{
+    return (size_t)((ncol + MMA_TILE_MN - 1) / MMA_TILE_MN) * (N / MMA_TILE_K) * FD_NT * MMA_TILE_BYTES;
+}
+
+/* x [ntr][N] (N % 64 == 0) -> PS partial rows of the dense coefficients + the summed trace */
+extern "C" int tspws_cu_forward_dense(const float *d_x, int ntr, int N, const void *d_wimg, int ncd, void *d_ximg,
+                                      float *d_tsum /* [mtiles][N] */, float *d_sumtrace /* [N] */, float *d_part /* [mtiles][2 ncd] */,
+                                      tspws_stream_t st)
+{
+    if (ntr <= 0 || ncd <= 0) return 0;
+    if (N % MMA_TILE_K) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)st;
+    const int mtiles = (ntr + MMA_TILE_MN - 1) / MMA_TILE_MN, kblocks = N / MMA_TILE_K, ncol = 2 * ncd;
+    const int ntiles = (ncol + MMA_TILE_MN - 1) / MMA_TILE_MN;
+    cudaFuncSetAttribute(trace_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_NT * MMA_TILE_BYTES);
+    trace_image_kernel<<<dim3(kblocks, mtiles), 256, FD_NT * MMA_TILE_BYTES, s>>>(d_x, ntr, N, kblocks, (__nv_bfloat16 *)d_ximg, d_tsum);
+    tile_sum_kernel<<<(N + 255) / 256, 256, 0, s>>>(d_tsum, mtiles, N, d_sumtrace);
+    const size_t smem = (size_t)FD_STAGES * FD_STAGE_BYTES + 1024 + (2 * FD_STAGES + 4) * 8 + 16;
+    cudaError_t e = cudaFuncSetAttribute(fwd_dense_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fwd_dense_mma_kernel<<<dim3(ntiles, mtiles), MMA_THREADS, smem, s>>>((const __nv_bfloat16 *)d_ximg, (const __nv_bfloat16 *)d_wimg,
+                                                                         kblocks, ncol, d_part,
+                                                                         getenv("TSPWS_DENSE_TERMS") ? atoi(getenv("TSPWS_DENSE_TERMS")) : 7);   /* bit (i + j): products of terms i, j */
+    tspws_cu_launch_count_add(3);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tspws_cu_dense_finish(const float *d_part, int ntr, int ncd, const void *d_ysum, int ci0, void *d_pps0, void *d_pst0,
+                                     tspws_stream_t st)
+{
+    if (ncd <= 0) return 0;
+    const int mtiles = (ntr + MMA_TILE_MN - 1) / MMA_TILE_MN;
+    dense_finish_kernel<<<(ncd + 255) / 256, 256, 0, (cudaStream_t)st>>>(d_part, mtiles, ncd, (const float2 *)d_ysum, ci0,
+                                                                          (float2 *)d_pps0, (float2 *)d_pst0);
+    tspws_cu_launch_count_add(1);
+    return (int)cudaGetLastError();
+}
+
+/* B image of the dense forward GEMM: row = column of the product = 2 (i - ci0) + (re | im) for the coefficients
+ * i >= ci0 (the coarse scales, contiguous at the end of the ragged coefficient array); element n = the conjugated
+ * filter of the coefficient's scale placed circularly at its position: W[n] = conj(w_s[(n - m D_s + c_s) mod N]). */
+__global__ void __launch_bounds__(256)
+w_image_kernel(const tspws_scale_t *__restrict__ scales, int S, int s0, const float2 *__restrict__ w32, int ci0, int ncd, int N, int kblocks,
+               __nv_bfloat16 *__restrict__ img)
+{
+    const int kb = blockIdx.x, nt = blockIdx.y;
+    __nv_bfloat16 *t0 = img + ((size_t)nt * kblocks + kb) * FD_NT * (MMA_TILE_MN * MMA_TILE_K);
+    for (int e = threadIdx.x; e < MMA_TILE_MN * MMA_TILE_K; e += blockDim.x) {
+        const int r = e / MMA_TILE_K, k = e % MMA_TILE_K;
+        const int col = nt * MMA_TILE_MN + r, n = kb * MMA_TILE_K + k;
+        float v = 0.f;
+        if (col < 2 * ncd) {
+            const int i = ci0 + (col >> 1);
+            int s = s0;
+            while (s + 1 < S && scales[s + 1].coef_off <= i) s++;
+            const tspws_scale_t sc = scales[s];
+            const int m = i - sc.coef_off;
+            long long l = ((long long)n - (long long)m * sc.D + sc.c) % N;
+            if (l < 0) l += N;
+            if (l < sc.L) {
+                const float2 w = w32[sc.tap_off + (int)l];
+                v = (col & 1) ? -w.y : w.x;
+            }
+        }
+        const unsigned o = mma_img_offset(r, k);
+#pragma unroll
+        for (int term = 0; term < FD_NT; term++) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            t0[(size_t)term * (MMA_TILE_MN * MMA_TILE_K) + o] = h;
+            v -= __bfloat162float(h);
+        }
+    }
+}
+
+extern "C" int tspws_cu_dense_wimage(const tspws_devframe_t *f, int s0, int ci0, int ncd, void *d_img, tspws_stream_t st)
+{
+    if (ncd <= 0) return 0;
+    if (f->N % MMA_TILE_K) return (int)cudaErrorInvalidValue;
+    const int kblocks = f->N / MMA_TILE_K, ntiles = (2 * ncd + MMA_TILE_MN - 1) / MMA_TILE_MN;
+    w_image_kernel<<<dim3(kblocks, ntiles), 256, 0, (cudaStream_t)st>>>(f->d_scale, f->S, s0, (const float2 *)f->d_w32, ci0, ncd, f->N, kblocks,
+                                                                         (__nv_bfloat16 *)d_img);
+    return (int)cudaGetLastError();
 }

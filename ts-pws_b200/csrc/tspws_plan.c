@@ -65,6 +65,10 @@ struct tspws_plan {
     cudaEvent_t  ev_fork, ev_join;
     int          mean_split;        /* fp64 transform of the group mean + fp32 transforms of the residuals */
     int          hybrid;            /* TSPWS_F64_MAXL set: long filters transform the unsplit sums instead */
+    /* coarse scales of the single-stage forward transform on the tensor cores (tspws_cu_forward_dense) */
+    int     dense_on, dense_s0, dense_ci0, dense_ncd, dense_items;
+    void   *d_wimg, *d_ximg, *d_ysum_ps, *d_ysum_st;
+    float  *d_tsum, *d_sumtrace, *d_dpart;
     unsigned int *d_tile_tickets;   /* [ntile16]: fused phasor combine of fwd_tail_kernel (NULL: separate combine launch) */
     double      *d_gmean;           /* [3N]: the group mean, three periods */
     void        *d_ymean;           /* double2 [TSPWS_F64_MAXSPLIT][ncoef] */
@@ -128,6 +132,7 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
                 sc[s].G = G;
                 sc[s].gain = log(2.) / (2 * f->Cpsi * f->V * f->scale[s]) * (double)f->D[s];
             }
+            if (pass) d->h_item_first[s] = nitems;
             for (int m0 = 0; m0 < Ns; m0 += (int)run) {
                 if (pass) {
                     items[nitems].s = s; items[nitems].m0 = m0;
@@ -138,8 +143,9 @@ int tspws_devframe_build(tspws_devframe_t *d, const tspws_frame_t *f, int want64
         }
         if (!pass) {
             items = (tspws_fwd_item_t *)calloc(nitems ? nitems : 1, sizeof(*items));
-            if (!items) goto done;
-        }
+            d->h_item_first = (int *)calloc((size_t)S + 1, sizeof(int));
+            if (!items || !d->h_item_first) goto done;
+        } else d->h_item_first[S] = nitems;
     }
     for (size_t i = 0; i < 2 * f->ntaps; i++) w32[i] = (float)f->w[i];
     /* 64-coefficient tiles of all scales, numbered scale by scale: the units of the fused phasor combine */
@@ -453,6 +459,7 @@ done:
 
 void tspws_devframe_free(tspws_devframe_t *d)
 {
+    free(d->h_item_first);
     cudaFree(d->d_scale); cudaFree(d->d_w32); cudaFree(d->d_w64);
     cudaFree(d->d_items); cudaFree(d->d_invgrp);
     cudaFree(d->d_g32); cudaFree(d->d_items2); cudaFree(d->d_items_gen); cudaFree(d->d_tile16); cudaFree(d->d_tile_expect); cudaFree(d->d_wi32); cudaFree(d->d_gi32); cudaFree(d->d_items_inv2); cudaFree(d->d_invgrp4); cudaFree(d->d_items_short); cudaFree(d->d_long);
@@ -574,6 +581,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
     if (pl->side) { cudaStreamDestroy(pl->side); cudaEventDestroy(pl->ev_join); cudaEventDestroy(pl->ev_fork); }
     cudaFree(pl->d_gmean); cudaFree(pl->d_ymean); cudaFree(pl->d_tile_tickets);
+    cudaFree(pl->d_wimg); cudaFree(pl->d_ximg); cudaFree(pl->d_tsum); cudaFree(pl->d_sumtrace); cudaFree(pl->d_dpart); cudaFree(pl->d_ysum_ps); cudaFree(pl->d_ysum_st);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
     tspws_b200_plan_peer_close(pl);
@@ -634,6 +642,41 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
     } else {
         CK(cudaMalloc(&pl->d_pps, (size_t)pl->nchunk * ncoef * pl->csz));
         CK(cudaMalloc(&pl->d_pst, (size_t)pl->nchunk * ncoef * pl->csz));
+        /* Dense tensor-core transform of the coarse scales (D >= TSPWS_DENSE_D, default 256; 0 = off): single-stage fp32
+         * stacks of at least TSPWS_DENSE_MIN traces (default 1024: the products are fp32-faithful, but the phase of a near-zero
+         * coefficient of a single trace weighs 1/mtr in the coherence -- measured 1.1e-5 at 256 traces, 2e-6 from 1024 on) whose length is a multiple of 64.  The scales must be
+         * polyphase (D >= 32) items so that the SIMT launch can skip them by item index. */
+        const long dD = env_long("TSPWS_DENSE_D", 256);
+        if (!pl->two_stage && !pl->acc64 && dD > 0 && max % 64 == 0 && (long)mtr_local >= env_long("TSPWS_DENSE_MIN", 1024)) {
+            int s0 = -1;
+            for (unsigned int s = 0; s < pl->fr->S; s++)
+                if ((long)pl->fr->D[s] >= dD && pl->fr->D[s] >= 32 && pl->fr->D[s] <= (unsigned int)max) { s0 = (int)s; break; }
+            if (s0 >= 0) {
+                int ok = 1, items = 0;
+                for (unsigned int s = (unsigned int)s0; s < pl->fr->S; s++) {
+                    if (pl->fr->D[s] < 32 || pl->fr->D[s] > (unsigned int)max) ok = 0;
+                    items += ((int)pl->fr->Ns[s] + 15) / 16;
+                }
+                if (ok) {
+                    pl->dense_s0 = s0; pl->dense_ci0 = (int)pl->fr->coef_off[s0];
+                    pl->dense_ncd = (int)(pl->fr->ncoef - pl->fr->coef_off[s0]);
+                    pl->dense_items = items;
+                    const int mtiles = ((int)mtr_local + 127) / 128;
+                    CK(cudaMalloc(&pl->d_wimg, tspws_cu_dense_wimg_bytes(2 * pl->dense_ncd, max)));
+                    CK(cudaMalloc(&pl->d_ximg, tspws_cu_dense_ximg_bytes((int)mtr_local, max)));
+                    CK(cudaMalloc((void **)&pl->d_tsum, (size_t)mtiles * max * sizeof(float)));
+                    CK(cudaMalloc((void **)&pl->d_sumtrace, (size_t)max * sizeof(float)));
+                    CK(cudaMalloc((void **)&pl->d_dpart, (size_t)mtiles * 2 * pl->dense_ncd * sizeof(float)));
+                    CK(cudaMalloc(&pl->d_ysum_ps, ncoef * 2 * sizeof(float)));
+                    CK(cudaMalloc(&pl->d_ysum_st, ncoef * 2 * sizeof(float)));
+                    if (tspws_cu_dense_wimage(&pl->dev, s0, pl->dense_ci0, pl->dense_ncd, pl->d_wimg, NULL)) goto fail;
+                    /* the SIMT kernels never write the dense coefficients: their chunk partials stay zero */
+                    CK(cudaMemset(pl->d_pps, 0, (size_t)pl->nchunk * ncoef * pl->csz));
+                    CK(cudaMemset(pl->d_pst, 0, (size_t)pl->nchunk * ncoef * pl->csz));
+                    pl->dense_on = 1;
+                }
+            }
+        }
     }
     CK(cudaMalloc(&pl->d_exch, 2 * ncoef * pl->csz));
     if (pl->mean_split) {
@@ -709,7 +752,16 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     if (pl->acc64) {
         if ((e = tspws_cu_forward(&pl->dev, d_sigall, 0, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
     } else {
-        if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+        if (pl->dense_on &&
+            (e = tspws_cu_forward_dense(d_sigall, pl->ntr_fwd, pl->N, pl->d_wimg, pl->dense_ncd, pl->d_ximg, pl->d_tsum, pl->d_sumtrace,
+                                        pl->d_dpart, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst,
+                                       pl->dense_on ? pl->dense_items : 0, stream))) return TSPWS_ERR_CUDA;
+        if (pl->dense_on) {
+            /* linear stack of the dense coefficients = transform of the summed trace (generic kernel, one trace) */
+            if ((e = tspws_cu_forward_one(&pl->dev, pl->d_sumtrace, pl->dev.h_item_first[pl->dense_s0], pl->d_ysum_ps, pl->d_ysum_st, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_dense_finish(pl->d_dpart, pl->ntr_fwd, pl->dense_ncd, pl->d_ysum_st, pl->dense_ci0, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+        }
     }
     if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, pl->acc64, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
                                     plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
