@@ -376,7 +376,7 @@ class ShardedStack:
             raise SystemExit("tspws_b200_plan_create failed")
         self.peer, self.exch, self.graph = False, None, None
         world = ctx.world
-        if world > 1 and self.two_stage and want_peer and not os.environ.get("TSPWS_BENCH_NCCL"):
+        if world > 1 and want_peer and not os.environ.get("TSPWS_BENCH_NCCL"):
             # peer exchange: every rank maps the others' exchange regions (CUDA IPC); plan_reduce pushes the rank's
             # block into every region over NVLink, plan_finish sums the blocks inside its first kernel.  The
             # decision is collective: if any rank cannot take part, all fall back to the all-reduce path.
@@ -741,7 +741,7 @@ def run_stack(args, wl, name):
                    "ms_per_step_with_kernel_events": ms_prof,
                    "ms_per_step_sustained": ms_sustained, "sustained_steps": sus_steps,
                    "step_replayed_as_cuda_graph": bool(world == 1 or peer or st.graph is not None),
-                   "exchange": ("none" if world == 1 else "peer memory over NVLink, fused into group_post2_kernel" if peer
+                   "exchange": ("none" if world == 1 else "peer memory over NVLink, fused into the stack's own kernels" if peer
                                 else "NCCL all-reduce")},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity": parity or None, "strong": strong, "extra_workloads": extra,

@@ -353,16 +353,20 @@ def test_group_sum_slots_across_many_group_boundaries(pkg, gpu_lib, mtr, n, kmax
 
 
 def test_peer_exchange_api_argument_checks(pkg, gpu_lib):
-    """Peer exchange is a two-stage feature; a world of one is the degenerate but legal case and must
-    give the plain result."""
+    """Argument checks of the peer exchange; a world of one is the degenerate but legal case and must give the
+    plain result (two-stage and single-stage)."""
     import torch
     x = O.synthetic_traces(64, 2048, seed=8)
-    p = pkg.default_params(lrm=1)
-    gpu_lib.tspws_b200_derive_params(C.byref(p), 2048, 1.0)
-    plan = gpu_lib.tspws_b200_plan_create(C.byref(p), 2048, 64, 64, 0)
     h = (C.c_ubyte * 64)()
-    assert gpu_lib.tspws_b200_plan_peer_export(plan, 1, h) != 0          # single-stage: refused
-    gpu_lib.tspws_b200_plan_destroy(plan)
+    gpu_lib.tspws_b200_set_option(pkg.OPT_FP64_TAIL, 2)                   # fp64 transforms: no peer exchange
+    try:
+        p = pkg.default_params(lrm=1)
+        gpu_lib.tspws_b200_derive_params(C.byref(p), 2048, 1.0)
+        plan = gpu_lib.tspws_b200_plan_create(C.byref(p), 2048, 64, 64, 0)
+        assert gpu_lib.tspws_b200_plan_peer_export(plan, 1, h) != 0
+        gpu_lib.tspws_b200_plan_destroy(plan)
+    finally:
+        gpu_lib.tspws_b200_set_option(pkg.OPT_FP64_TAIL, 0)
     kw = dict(Kmax=8, unbiased=1, lrm=1)
     ref = _plan_stack(pkg, gpu_lib, x, **kw)
     p = pkg.default_params(**kw)
@@ -449,3 +453,18 @@ def test_peer_exchange_all_ranks_on_one_gpu_vs_oracle(pkg, gpu_lib, world, ragge
         assert O.nerr(ts, o["tsPWS"]) <= TOL_STACK, r
         np.testing.assert_array_equal(ts, res[0][1])
         np.testing.assert_array_equal(ls, res[0][0])
+
+
+def test_single_stage_peer_exchange_all_ranks_on_one_gpu_vs_oracle(pkg, gpu_lib):
+    """Single-stage stack, traces sharded over 4 ranks: the phasor / linear sums travel through the fused peer exchange
+    (publish into every region, sum in rank order) instead of an all-reduce call; every rank against the oracle."""
+    mtr, n, world = 120, 2048, 4
+    kw = dict(lrm=1, w0=6.0, w0set=4)
+    x = O.synthetic_traces(mtr, n, seed=4141)
+    cuts = [0, 17, 60, 61, mtr]
+    res = _peer_world_on_one_gpu(pkg, gpu_lib, x, world, list(zip(cuts[:-1], cuts[1:])), **kw)
+    o = O.tspws_main(O.Params(**kw), x)
+    for r, (ls, ts, coh) in enumerate(res):
+        assert O.nerr(coh, o["coherence"]) <= TOL_COH, r
+        assert O.nerr(ls, o["ls"]) <= TOL_STACK and O.nerr(ts, o["tsPWS"]) <= TOL_STACK, r
+        np.testing.assert_array_equal(ts, res[0][1])

@@ -195,6 +195,10 @@ int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *
                               int rank, int world, tspws_stream_t st);
 /* d_tickets != NULL ([f->ntile16] zeroed counters): the phasor combine is fused in (PS, ST, Zout written by
  * the warp that completes a coefficient tile); NULL: per-trace coefficients only, tspws_cu_phasor_combine follows */
+/* single-stage peer exchange of a flat fp32 block (PS | ST sums): publish into every region / wait + sum in rank order */
+int tspws_cu_peer_f32(int publish, float *d_buf, long long n, long long block_len_doubles, void *d_regions, double *d_own,
+                      const unsigned int *d_flags, unsigned int *d_step, unsigned int *d_err, void *d_peer_flags,
+                      int rank, int world, tspws_stream_t st);
 int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x, int ntr, int long_row0, void *d_ypart,
                           const double *d_x64, void *d_y64, unsigned int *d_tickets, const tspws_weight_t *d_rule,
                           void *d_ps, void *d_st, void *d_zout, tspws_stream_t st);

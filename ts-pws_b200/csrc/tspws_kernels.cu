@@ -650,6 +650,83 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
     }
 }
 
+/* ---- peer exchange of a flat fp32 block (single-stage stacks: the rank's phasor and linear sums, 4 ncoef floats):
+ * publish = every thread stores its elements into slot [parity][rank] of every rank's region, the last CTA signals;
+ * collect = wait for all ranks, then the sum of the world blocks of the own region in rank order (deterministic,
+ * identical on all ranks).  Same regions, flags, step counter and parity double buffering as the two-stage exchange. ---- */
+__global__ void __launch_bounds__(256)
+peer_publish_f32_kernel(const float *__restrict__ src, long long n, const tspws_peer_args pa)
+{
+    __shared__ unsigned int s_last;
+    const size_t blk = (size_t)pa.block_len * 2;                         /* floats per block (block_len counts doubles) */
+    const size_t off = ((size_t)(*pa.step & 1) * (size_t)pa.world + (size_t)pa.rank) * blk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = src[i];
+        for (int q = 0; q < pa.world; q++) reinterpret_cast<float *>(pa.regions[q])[off + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(pa.ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+        if (s_last) *pa.ticket = 0;
+    }
+    __syncthreads();
+    if (s_last) {
+        const unsigned int st = *pa.step + 1;
+        __threadfence_system();
+        if ((int)threadIdx.x < pa.world)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pa.peer_flags[threadIdx.x] + pa.rank), "r"(st) : "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) *pa.step = st;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+peer_collect_f32_kernel(float *__restrict__ dst, long long n, const tspws_peer_args pa)
+{
+    __shared__ int s_dead;
+    const unsigned int step = *pa.step;                                    /* already advanced by the publishing launch */
+    if (threadIdx.x == 0) s_dead = 0;
+    __syncthreads();
+    if (threadIdx.x < pa.world) {
+        long long spins = 0;
+        while (ld_acquire_sys(pa.flags + threadIdx.x) < step) {
+            __nanosleep(200);
+            if (++spins > 20000000LL) { *pa.err = 1; s_dead = 1; break; }
+        }
+    }
+    __syncthreads();
+    const bool dead = s_dead || *reinterpret_cast<volatile unsigned int *>(pa.err) != 0;
+    const size_t blk = (size_t)pa.block_len * 2;
+    const float *own = reinterpret_cast<const float *>(pa.own) + (size_t)((step - 1) & 1) * (size_t)pa.world * blk;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int r = 0; r < pa.world; r++) {
+            float v;
+            asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(own + (size_t)r * blk + i) : "memory");
+            a += v;
+        }
+        dst[i] = dead ? __int_as_float(0x7fc00000) : a;
+    }
+}
+
+extern "C" int tspws_cu_peer_f32(int publish, float *d_buf, long long n, long long block_len_doubles, void *d_regions, double *d_own,
+                                 const unsigned int *d_flags, unsigned int *d_step, unsigned int *d_err, void *d_peer_flags,
+                                 int rank, int world, tspws_stream_t st)
+{
+    if (world > 256) return (int)cudaErrorInvalidValue;
+    tspws_peer_args pa;
+    pa.regions = (double *const *)d_regions; pa.own = d_own; pa.flags = d_flags; pa.step = d_step; pa.err = d_err;
+    pa.ticket = d_step + 1; pa.peer_flags = (unsigned int *const *)d_peer_flags;
+    pa.world = world; pa.rank = rank; pa.block_len = block_len_doubles;
+    const int grid = (int)((n + 255) / 256 < 592 ? (n + 255) / 256 : 592);
+    if (publish) peer_publish_f32_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(d_buf, n, pa);
+    else         peer_collect_f32_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(d_buf, n, pa);
+    TSPWS_LAUNCHED_N(publish ? "peer_publish_f32_kernel" : "peer_collect_f32_kernel", (cudaStream_t)st);
+    return 0;
+}
+
 /* peer variants of the two group_post2 launches: publish (push into every region) and the sum over ranks */
 extern "C" int tspws_cu_group_post2_peer(int publish, const double *d_slots, const double *d_slot_tot, const int *d_slot_off, int N, int K,
                                          int ntile, int do_rm, int do_fold, int split, double *d_gsum,

@@ -765,6 +765,15 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     }
     if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, pl->acc64, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
                                     plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
+    if (pl->peer_on && !pl->acc64) {
+        /* push this rank's PS | ST sums into every rank's region; plan_finish adds the blocks of all ranks */
+        unsigned int *flags = (unsigned int *)((char *)pl->d_peer_region + pl->peer_flag_off);
+        const size_t blkd = ((tspws_b200_plan_exchange_bytes(pl) + 15) & ~(size_t)15) / sizeof(double);
+        if ((e = tspws_cu_peer_f32(1, (float *)pl->d_exch, (long long)(4 * pl->fr->ncoef), (long long)blkd, pl->d_peer_blocks,
+                                   (double *)pl->d_peer_region, flags, pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->d_peer_flags,
+                                   pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+        pl->peer_pending = 1;
+    }
     return 0;
 }
 
@@ -810,10 +819,12 @@ int tspws_b200_plan_exchange_is_f64(tspws_plan_t *pl) { return pl && pl->two_sta
  * ranks is read straight from peer memory inside group_post2_kernel<true>; no collective call ---- */
 static int peer_region_alloc(tspws_plan_t *pl, int world)
 {
-    if (!pl->two_stage || !pl->cs2 || world < 1 || world > TSPWS_PEER_MAXW) return TSPWS_ERR_ARG;
+    /* two-stage: fp64 group sums (needs the single-wave group-sum kernel); single-stage: the fp32 PS | ST sums */
+    if ((pl->two_stage && !pl->cs2) || pl->acc64 || world < 1 || world > TSPWS_PEER_MAXW) return TSPWS_ERR_ARG;
     if (pl->d_peer_region && pl->peer_world != world) return TSPWS_ERR_ARG;
     if (!pl->d_peer_region) {
-        const size_t blk = tspws_b200_plan_exchange_bytes(pl) + pl->K * sizeof(double);   /* + presence marks */
+        const size_t blk = pl->two_stage ? tspws_b200_plan_exchange_bytes(pl) + pl->K * sizeof(double)   /* + presence marks */
+                                         : ((tspws_b200_plan_exchange_bytes(pl) + 15) & ~(size_t)15);
         pl->peer_world = world;
         pl->peer_flag_off = (2 * (size_t)world * blk + 255) & ~(size_t)255;     /* [parity][rank][block] */
         pl->peer_bytes = pl->peer_flag_off + (TSPWS_PEER_MAXW + 1) * sizeof(unsigned int);
@@ -999,6 +1010,13 @@ int tspws_b200_plan_finish(tspws_plan_t *pl, float *d_ls, float *d_tspws, void *
             if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, 1, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
                                             plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
         }
+    } else if (pl->peer_pending) {
+        unsigned int *flags = (unsigned int *)((char *)pl->d_peer_region + pl->peer_flag_off);
+        const size_t blkd = ((tspws_b200_plan_exchange_bytes(pl) + 15) & ~(size_t)15) / sizeof(double);
+        if ((e = tspws_cu_peer_f32(0, (float *)pl->d_exch, (long long)(4 * pl->fr->ncoef), (long long)blkd, pl->d_peer_blocks,
+                                   (double *)pl->d_peer_region, flags, pl->d_peer_step, flags + TSPWS_PEER_MAXW, pl->d_peer_flags,
+                                   pl->peer_rank, pl->peer_world, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), pl->acc64, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     } else if (pl->summed_across_ranks) {
         if ((e = tspws_cu_weight(plan_ps(pl), plan_st(pl), pl->acc64, pl->dev.ncoef, 1, pl->d_rule, pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     }
