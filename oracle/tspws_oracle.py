@@ -6,8 +6,8 @@ cpu_baseline / --impl reference legs may import this; the product
 
 Parity status: PINNED -- the reference ships no golden vectors, so
 this restatement is pinned against the reference ITSELF compiled here from
-/root/reference/src into oracle/_ref (oracle/Makefile): tests/test_oracle_vs_ref.py
-when oracle/_ref is present, and tests/golden/*.npz (made by oracle/gen_golden.py from
+/root/reference/src into oracle/_ref (oracle/Makefile): tests/test_oracle_golden.py and
+tests/test_oracle_resample.py when oracle/_ref is present, and tests/golden/*.npz (made by oracle/gen_golden.py from
 the compiled reference) everywhere else.
 
 Everything is written from the mathematics; citations give the
