@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import time
 import os
 from typing import Optional
 
@@ -300,6 +301,7 @@ def call_tspws_main(lib: C.CDLL, sigall: np.ndarray, params: TsPWS, dt: float = 
         msub = np.zeros(M, np.uint32)
         lsub = np.zeros((M, nmax), np.float32)
         tsub = np.zeros((M, nmax), np.float32)
+        lsub.fill(0); tsub.fill(0)          # touch the pages now: first-touch faults are not the library's time
         rows_l = (C.POINTER(C.c_float) * M)(*[_fptr(lsub[m]) for m in range(M)])
         rows_t = (C.POINTER(C.c_float) * M)(*[_fptr(tsub[m]) for m in range(M)])
         out.mtr_subsmpl = msub.ctypes.data_as(C.POINTER(C.c_uint))
@@ -307,8 +309,9 @@ def call_tspws_main(lib: C.CDLL, sigall: np.ndarray, params: TsPWS, dt: float = 
         out.tsPWS_subsmpl = C.cast(rows_t, C.POINTER(C.POINTER(C.c_float)))
         keep += [rows_l, rows_t]
         res.update(mtr_subsmpl=msub, ls_subsmpl=lsub, tsPWS_subsmpl=tsub)
+    t0 = time.perf_counter()
     rc = lib.tspws_main(C.byref(p), C.byref(out), C.byref(dat))
-    res.update(rc=rc, ls=ls, tsPWS=ts, params=p, sigall=x, M=M)
+    res.update(rc=rc, ls=ls, tsPWS=ts, params=p, sigall=x, M=M, seconds=time.perf_counter() - t0)
     return res
 
 

@@ -25,6 +25,7 @@ int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, flo
                        int ss_jackknife, cudaStream_t stream);
 int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, float *d_x,
                           unsigned int mtr, int max, cudaStream_t stream);
+void tspws_resample_release(void);
 
 static struct {
     long          opt_writeback, opt_fp64_tail, opt_device, opt_ss_jackknife;
@@ -143,6 +144,7 @@ static void drop_plan(void)
 static void release_device_state(void)
 {
     drop_plan();
+    tspws_resample_release();
     if (G.d_x)   { cudaFree(G.d_x);   G.d_x = NULL;   G.d_x_cap = 0; }
     if (G.d_out) { cudaFree(G.d_out); G.d_out = NULL; G.d_out_cap = 0; }
     if (G.stream) { cudaStreamDestroy(G.stream); G.stream = NULL; }

@@ -64,6 +64,98 @@ static int rank_group(unsigned int r, unsigned int Kmax, unsigned int K)
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Row pipe: the stacks of a batch of realisations leave the device through double-buffered device rows and PINNED
+ * staging on a copy stream, and are scattered to the caller's (pageable) row pointers by the host while the GPU
+ * computes the next batch.  (Round 1 copied every batch synchronously into pageable memory: at configs[3] the
+ * 2 x 131 MB of results cost more than all the kernels.) */
+typedef struct {
+    int B; size_t N;
+    float  *d_ls[2], *d_ts[2];
+    double *d_sim[2];                    /* [2 B] similarity, misfit (convergence) */
+    float  *h_pin[2];                    /* pinned [2][B][N]: ls rows then tsPWS rows */
+    double *h_sim[2];
+    cudaStream_t cst;
+    cudaEvent_t ev_done[2], ev_copied[2];
+    int nb[2], with_ls[2], with_ts[2], with_sim[2], used[2];
+    unsigned int m0[2];
+} rowpipe_t;
+
+static void rp_close(rowpipe_t *rp)
+{
+    for (int i = 0; i < 2; i++) {
+        cudaFree(rp->d_ls[i]); cudaFree(rp->d_ts[i]); cudaFree(rp->d_sim[i]);
+        if (rp->h_pin[i]) cudaFreeHost(rp->h_pin[i]);
+        if (rp->h_sim[i]) cudaFreeHost(rp->h_sim[i]);
+        if (rp->ev_done[i]) cudaEventDestroy(rp->ev_done[i]);
+        if (rp->ev_copied[i]) cudaEventDestroy(rp->ev_copied[i]);
+    }
+    if (rp->cst) cudaStreamDestroy(rp->cst);
+    memset(rp, 0, sizeof *rp);
+}
+static int rp_open(rowpipe_t *rp, int B, size_t N)
+{
+    memset(rp, 0, sizeof *rp);
+    rp->B = B; rp->N = N;
+    int ok = cudaStreamCreateWithFlags(&rp->cst, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaMalloc((void **)&rp->d_ls[i], (size_t)B * N * sizeof(float)) == cudaSuccess &&
+             cudaMalloc((void **)&rp->d_ts[i], (size_t)B * N * sizeof(float)) == cudaSuccess &&
+             cudaMalloc((void **)&rp->d_sim[i], 2 * (size_t)B * sizeof(double)) == cudaSuccess &&
+             cudaHostAlloc((void **)&rp->h_pin[i], 2 * (size_t)B * N * sizeof(float), cudaHostAllocDefault) == cudaSuccess &&
+             cudaHostAlloc((void **)&rp->h_sim[i], 2 * (size_t)B * sizeof(double), cudaHostAllocDefault) == cudaSuccess &&
+             cudaEventCreateWithFlags(&rp->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&rp->ev_copied[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); rp_close(rp); return TSPWS_ERR_ALLOC; }
+    return 0;
+}
+/* One pipe is kept between calls (pinning host memory costs milliseconds); callers hold the library lock. */
+static rowpipe_t g_rp;
+static int rp_acquire(rowpipe_t **out, int B, size_t N)
+{
+    if (g_rp.cst && (g_rp.B != B || g_rp.N != N)) rp_close(&g_rp);
+    if (!g_rp.cst) { const int e = rp_open(&g_rp, B, N); if (e) return e; }
+    g_rp.used[0] = g_rp.used[1] = 0;
+    *out = &g_rp;
+    return 0;
+}
+void tspws_resample_release(void) { if (g_rp.cst) rp_close(&g_rp); }
+
+/* batch k is about to be computed into buffers k & 1: the copy of batch k - 2 out of them must have finished */
+static int rp_begin(rowpipe_t *rp, int k, cudaStream_t st)
+{
+    const int i = k & 1;
+    if (rp->used[i] && cudaStreamWaitEvent(st, rp->ev_copied[i], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
+    return 0;
+}
+/* the kernels of batch k are queued on st: queue its D2H behind them on the copy stream */
+static int rp_submit(rowpipe_t *rp, int k, cudaStream_t st, unsigned int m0, int nb, int with_ls, int with_ts, int with_sim)
+{
+    const int i = k & 1;
+    const size_t row = rp->N * sizeof(float);
+    if (cudaEventRecord(rp->ev_done[i], st) != cudaSuccess || cudaStreamWaitEvent(rp->cst, rp->ev_done[i], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (with_ls && cudaMemcpyAsync(rp->h_pin[i], rp->d_ls[i], (size_t)nb * row, cudaMemcpyDeviceToHost, rp->cst) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (with_ts && cudaMemcpyAsync(rp->h_pin[i] + (size_t)rp->B * rp->N, rp->d_ts[i], (size_t)nb * row, cudaMemcpyDeviceToHost, rp->cst) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (with_sim && cudaMemcpyAsync(rp->h_sim[i], rp->d_sim[i], 2 * (size_t)rp->B * sizeof(double), cudaMemcpyDeviceToHost, rp->cst) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (cudaEventRecord(rp->ev_copied[i], rp->cst) != cudaSuccess) return TSPWS_ERR_CUDA;
+    rp->nb[i] = nb; rp->m0[i] = m0; rp->with_ls[i] = with_ls; rp->with_ts[i] = with_ts; rp->with_sim[i] = with_sim; rp->used[i] = 1;
+    return 0;
+}
+/* host side of batch k: wait for its copy, scatter the rows */
+static int rp_collect(rowpipe_t *rp, int k, float **ls_rows, float **ts_rows, double *sim_out, double *mis_out)
+{
+    const int i = k & 1;
+    if (!rp->used[i]) return 0;
+    if (cudaEventSynchronize(rp->ev_copied[i]) != cudaSuccess) return TSPWS_ERR_CUDA;
+    const size_t row = rp->N * sizeof(float);
+    for (int b = 0; b < rp->nb[i]; b++) {
+        if (rp->with_ls[i] && ls_rows && ls_rows[rp->m0[i] + b]) memcpy(ls_rows[rp->m0[i] + b], rp->h_pin[i] + (size_t)b * rp->N, row);
+        if (rp->with_ts[i] && ts_rows && ts_rows[rp->m0[i] + b]) memcpy(ts_rows[rp->m0[i] + b], rp->h_pin[i] + ((size_t)rp->B + b) * rp->N, row);
+        if (rp->with_sim[i] && sim_out) { sim_out[rp->m0[i] + b] = rp->h_sim[i][b]; mis_out[rp->m0[i] + b] = rp->h_sim[i][rp->B + b]; }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* two-stage machinery: nres selection rows -> ls / tsPWS rows (host pointers)            */
 /* ------------------------------------------------------------------------------------ */
 static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, unsigned int mtr, int max,
@@ -75,12 +167,13 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     const size_t N = (size_t)max, ncoef = F->fr->ncoef ? F->fr->ncoef : 1;
     const int B = RS_BATCH;
     short *h_gid = NULL, *d_gid = NULL;          /* group of every trace per realisation (-1: not selected); any Kmax < 32768 */
-    float *d_gs = NULL, *d_ls = NULL, *d_ts = NULL, *h_buf = NULL;
+    float *d_gs = NULL;
     void *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
-    double *d_scale = NULL, *h_scale = NULL, *d_sim = NULL, *h_sim = NULL;
+    double *d_scale = NULL, *h_scale = NULL;
     tspws_weight_t *d_rules = NULL, *h_rules = NULL;
     unsigned int *d_tk = NULL, *Ks = NULL;
     const int ntk = (max + 255) / 256;
+    rowpipe_t *rpp = NULL;
 
     if (Kmax > 32767) { fprintf(stderr, "tspws_b200: two-stage resampling supports Kmax <= 32767\n"); return TSPWS_ERR_ARG; }
     for (size_t i = 0; i < (size_t)nres * mtr; i++)
@@ -91,14 +184,11 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     h_gid   = (short *)malloc((size_t)B * mtr * sizeof(short));
     h_scale = (double *)malloc(B * sizeof(double));
     h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
-    h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
-    h_sim   = (double *)malloc(2 * B * sizeof(double));
     Ks      = (unsigned int *)malloc(B * sizeof(unsigned int));
-    if (!h_gid || !h_scale || !h_rules || !h_buf || !h_sim || !Ks) { rc = TSPWS_ERR_ALLOC; goto done; }
+    if (!h_gid || !h_scale || !h_rules || !Ks) { rc = TSPWS_ERR_ALLOC; goto done; }
+    if ((rc = rp_acquire(&rpp, B, N))) goto done;
     CKR(cudaMalloc((void **)&d_gid, (size_t)B * mtr * sizeof(short)));
     CKR(cudaMalloc((void **)&d_gs, (size_t)B * Kmax * N * sizeof(float)));
-    CKR(cudaMalloc((void **)&d_ls, (size_t)B * N * sizeof(float)));
-    CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
     CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
@@ -106,11 +196,14 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     CKR(cudaMalloc((void **)&d_scale, B * sizeof(double)));
     CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
     CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
-    CKR(cudaMalloc((void **)&d_sim, 2 * B * sizeof(double)));
     CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
 
-    for (unsigned int m0 = 0; m0 < nres; m0 += B) {
+    int k = 0;
+    for (unsigned int m0 = 0; m0 < nres; m0 += B, k++) {
         const int nb = (int)((nres - m0 < (unsigned int)B) ? nres - m0 : (unsigned int)B);
+        float *d_ls = rpp->d_ls[k & 1], *d_ts = rpp->d_ts[k & 1];
+        double *d_sim = rpp->d_sim[k & 1];
+        /* (h_gid / h_scale / h_rules are pageable: cudaMemcpyAsync has staged them when it returns, so they can be refilled) */
         for (int b = 0; b < nb; b++) {
             const char *row = sel + (size_t)(m0 + b) * mtr;
             unsigned int K = 0;
@@ -126,31 +219,23 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
         CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)nb * mtr * sizeof(short), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_scale, h_scale, nb * sizeof(double), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_rules, h_rules, nb * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+        if ((rc = rp_begin(rpp, k, st))) goto done;
         CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, NULL, nb, (int)Kmax, d_gs, st));
-        if (ls_rows) {
-            CKK(tspws_cu_group_total(d_gs, nb, (int)Kmax, max, d_scale, d_ls, st));
-            CKR(cudaMemcpyAsync(h_buf, d_ls, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
-            CKR(cudaStreamSynchronize(st));
-            for (int b = 0; b < nb; b++) memcpy(ls_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
-        }
+        if (ls_rows) CKK(tspws_cu_group_total(d_gs, nb, (int)Kmax, max, d_scale, d_ls, st));
         CKK(tspws_cu_forward_fast(&F->acc, d_gs, nb * (int)Kmax, (int)Kmax, d_pps, d_pst, 0, st));
         CKK(tspws_cu_weight(d_pps, d_pst, 0, (int)F->fr->ncoef, nb, d_rules, d_zout, st));
         CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st, NULL, NULL, NULL));
-        if (d_ref && sim_out) {
-            CKK(tspws_cu_simil(d_ts, nb, max, d_ref, d_sim, d_sim + B, st));
-            CKR(cudaMemcpyAsync(h_sim, d_sim, 2 * B * sizeof(double), cudaMemcpyDeviceToHost, st));
-        }
-        if (ts_rows) CKR(cudaMemcpyAsync(h_buf, d_ts, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CKR(cudaStreamSynchronize(st));
-        for (int b = 0; b < nb; b++) {
-            if (ts_rows && ts_rows[m0 + b]) memcpy(ts_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
-            if (d_ref && sim_out) { sim_out[m0 + b] = h_sim[b]; mis_out[m0 + b] = h_sim[B + b]; }
-        }
+        if (d_ref && sim_out) CKK(tspws_cu_simil(d_ts, nb, max, d_ref, d_sim, d_sim + B, st));
+        if ((rc = rp_submit(rpp, k, st, m0, nb, ls_rows != NULL, ts_rows != NULL, d_ref && sim_out))) goto done;
+        if (k > 0 && (rc = rp_collect(rpp, k - 1, ls_rows, ts_rows, sim_out, mis_out))) goto done;
     }
+    if (k > 0) rc = rp_collect(rpp, k - 1, ls_rows, ts_rows, sim_out, mis_out);
 done:
-    free(h_gid); free(h_scale); free(h_rules); free(h_buf); free(h_sim); free(Ks);
-    cudaFree(d_gid); cudaFree(d_gs); cudaFree(d_ls); cudaFree(d_ts); cudaFree(d_pps); cudaFree(d_pst);
-    cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale); cudaFree(d_rules); cudaFree(d_tk); cudaFree(d_sim);
+    cudaStreamSynchronize(st);
+    free(h_gid); free(h_scale); free(h_rules); free(Ks);
+    cudaFree(d_gid); cudaFree(d_gs); cudaFree(d_pps); cudaFree(d_pst);
+    cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale); cudaFree(d_rules); cudaFree(d_tk);
+    if (rpp) cudaStreamSynchronize(rpp->cst);
     return rc;
 }
 
@@ -174,8 +259,9 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     const int kblocks = ((int)mtr + 63) / 64;
     short *h_gid = NULL, *d_gid = NULL;
     signed char *d_sel = NULL;
-    float *d_S = NULL, *d_ls = NULL, *d_ts = NULL, *h_buf = NULL;
+    float *d_S = NULL;
     void *d_ypart = NULL, *d_P = NULL, *d_ps = NULL, *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
+    rowpipe_t *rpp = NULL;
     void *d_aimg = NULL, *d_bimg = NULL;
     double *d_scale = NULL, *h_scale = NULL;
     tspws_weight_t *d_rules = NULL, *h_rules = NULL;
@@ -185,9 +271,9 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     h_gid   = (short *)malloc((size_t)M * mtr * sizeof(short));
     h_scale = (double *)malloc(B * sizeof(double));
     h_rules = (tspws_weight_t *)malloc(B * sizeof(tspws_weight_t));
-    h_buf   = (float *)malloc((size_t)B * N * sizeof(float));
     km_all  = (unsigned int *)calloc(M ? M : 1, sizeof(unsigned int));
-    if (!h_gid || !h_scale || !h_rules || !h_buf || !km_all) { rc = TSPWS_ERR_ALLOC; goto done; }
+    if (!h_gid || !h_scale || !h_rules || !km_all) { rc = TSPWS_ERR_ALLOC; goto done; }
+    if ((rc = rp_acquire(&rpp, B, N))) goto done;
     for (unsigned int m = 0; m < M; m++)
         for (unsigned int t = 0; t < mtr; t++) {
             const int c = sel[(size_t)m * mtr + t];
@@ -198,8 +284,6 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     CKR(cudaMalloc((void **)&d_gid, (size_t)M * mtr * sizeof(short)));
     CKR(cudaMalloc((void **)&d_sel, (size_t)M * mtr));
     CKR(cudaMalloc((void **)&d_S, (size_t)B * N * sizeof(float)));
-    CKR(cudaMalloc((void **)&d_ls, (size_t)B * N * sizeof(float)));
-    CKR(cudaMalloc((void **)&d_ts, (size_t)B * N * sizeof(float)));
     CKR(cudaMalloc(&d_ypart, (size_t)TR_BATCH * (F->pt.ypart_len ? F->pt.ypart_len : 1) * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_P, (size_t)TR_BATCH * ncoef * 2 * sizeof(float)));
     CKR(cudaMalloc(&d_ps, (size_t)M * ncoef * 2 * (use_mma ? sizeof(float) : sizeof(double))));
@@ -234,8 +318,10 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
         CKK(tspws_cu_resample_mma(d_aimg, d_bimg, nterm, (int)M, 2 * (int)F->fr->ncoef, kblocks, (float *)d_ps, 2 * ncoef, st));
 
     /* per batch of realisations: time-domain sums -> ls, ST by linearity, weights, inverse */
-    for (unsigned int m0 = 0; m0 < M; m0 += B) {
+    int k = 0;
+    for (unsigned int m0 = 0; m0 < M; m0 += B, k++) {
         const int nb = (int)((M - m0 < (unsigned int)B) ? M - m0 : (unsigned int)B);
+        float *d_ls = rpp->d_ls[k & 1], *d_ts = rpp->d_ts[k & 1];
         for (int b = 0; b < nb; b++) {
             unsigned int km = km_all[m0 + b];
             if (k_rows) k_rows[m0 + b] = km;
@@ -245,6 +331,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
         }
         CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
+        if ((rc = rp_begin(rpp, k, st))) goto done;
         CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, d_sel + (size_t)m0 * mtr, nb, 1, d_S, st));
         CKK(tspws_cu_group_total(d_S, nb, 1, max, d_scale, d_ls, st));
         CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, 0, st));
@@ -255,16 +342,15 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
             CKK(tspws_cu_weight_mixed((char *)d_ps + (size_t)m0 * ncoef * 2 * sizeof(double), d_pst, (int)F->fr->ncoef, nb,
                                       d_rules, d_zout, st));
         CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st, NULL, NULL, NULL));
-        CKR(cudaMemcpyAsync(h_buf, d_ls, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CKR(cudaStreamSynchronize(st));
-        for (int b = 0; b < nb; b++) memcpy(ls_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
-        CKR(cudaMemcpyAsync(h_buf, d_ts, (size_t)nb * N * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CKR(cudaStreamSynchronize(st));
-        for (int b = 0; b < nb; b++) memcpy(ts_rows[m0 + b], h_buf + (size_t)b * N, N * sizeof(float));
+        if ((rc = rp_submit(rpp, k, st, m0, nb, 1, 1, 0))) goto done;
+        if (k > 0 && (rc = rp_collect(rpp, k - 1, ls_rows, ts_rows, NULL, NULL))) goto done;
     }
+    if (k > 0) rc = rp_collect(rpp, k - 1, ls_rows, ts_rows, NULL, NULL);
 done:
-    free(h_gid); free(h_scale); free(h_rules); free(h_buf); free(km_all);
-    cudaFree(d_gid); cudaFree(d_sel); cudaFree(d_S); cudaFree(d_ls); cudaFree(d_ts); cudaFree(d_ypart); cudaFree(d_P);
+    cudaStreamSynchronize(st);
+    if (rpp) cudaStreamSynchronize(rpp->cst);
+    free(h_gid); free(h_scale); free(h_rules); free(km_all);
+    cudaFree(d_gid); cudaFree(d_sel); cudaFree(d_S); cudaFree(d_ypart); cudaFree(d_P);
     cudaFree(d_ps); cudaFree(d_pps); cudaFree(d_pst); cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale);
     cudaFree(d_rules); cudaFree(d_tk); cudaFree(d_aimg); cudaFree(d_bimg);
     return rc;
