@@ -320,6 +320,28 @@ def test_full_size_single_stage_w6_vs_oracle(pkg, gpu_lib):
     assert O.nerr(ls, o_ls) <= TOL_STACK and O.nerr(ts, o_ts) <= TOL_STACK
 
 
+@pytest.mark.parametrize("kw", [dict(w0=6.0, w0set=4), dict(), dict(type=-3)], ids=["morlet_w6", "morlet_default", "mexhat"])
+def test_tensor_core_octaves_vs_simt_and_oracle(pkg, gpu_lib, kw, monkeypatch):
+    """1024 x 16384 single stage: the octaves D >= 16 run as banded / dense tcgen05 GEMMs (tspws_cu_forward_band,
+    tspws_cu_forward_dense).  Against the numpy oracle per decimation (so that a wrong octave cannot hide behind
+    the global maximum), and against the same stack with the tensor-core paths switched off (SIMT kernels)."""
+    mtr, n = 1024, 16384
+    x = _bench_traces(mtr, n)
+    o = O.tspws_main(O.Params(**kw), x)
+    fr = o["frame"]
+    ls, ts, coh = _plan_stack(pkg, gpu_lib, x, **kw)
+    monkeypatch.setenv("TSPWS_DENSE_D", "0")
+    s_ls, s_ts, s_coh = _plan_stack(pkg, gpu_lib, x, **kw)
+    monkeypatch.delenv("TSPWS_DENSE_D")
+    cmax = o["coherence"].max()
+    for D in sorted(set(fr.D.tolist())):
+        idx = np.concatenate([np.arange(fr.coef_off[s], fr.coef_off[s + 1]) for s in range(fr.S) if fr.D[s] == D])
+        assert np.abs(coh[idx] - o["coherence"][idx]).max() <= TOL_COH * cmax, D
+        assert np.abs(coh[idx] - s_coh[idx]).max() <= TOL_COH * cmax, D
+    assert O.nerr(ts, o["tsPWS"]) <= TOL_STACK and O.nerr(ls, o["ls"]) <= TOL_STACK
+    assert O.nerr(ts, s_ts) <= TOL_STACK and O.nerr(ls, s_ls) <= TOL_STACK
+
+
 def test_large_single_stage_two_independent_kernel_paths_agree(pkg, gpu_lib):
     """2048 x 16384, Morlet w0 = 6 (the C2 frame): the single-stage stack (chunk-accumulating kernels) must
     equal the two-stage stack with one trace per group (per-trace kernels + combine) -- a size-independent

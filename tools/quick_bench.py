@@ -46,6 +46,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "ss64":
         run("single-stage morlet w0=6 (64 traces)", 64, 16384, reps=1, w0=6.0, w0set=4, lrm=1)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c2":
+        run("single-stage morlet w0=6 (8192 traces)", 8192, 16384, reps=3, w0=6.0, w0set=4, lrm=1)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "ss":
         run("single-stage morlet w0=6 (256 traces)", 256, 16384, reps=1, w0=6.0, w0set=4, lrm=1)
         sys.exit(0)

@@ -171,18 +171,42 @@ int tspws_cu_forward(const tspws_devframe_t *f, const void *d_x, int in64, int a
                      int ntr, int chunk, void *d_part_ps, void *d_part_st, tspws_stream_t st);
 /* fp32 fast path: polyphase register-tiled kernel for the scales it covers + generic kernel for the
  * rest.  Chunk-accumulate mode (f->per_trace == 0): same outputs as tspws_cu_forward. */
-/* skip5: the first skip5 items of the D >= 32 list (coarsest scales first) are left out -- the dense tensor-core
- * transform covers them (tspws_cu_forward_dense) */
+/* skip5: the first skip5 items of the D >= 32 list (coarsest scales first) are left out -- the tensor-core
+ * transforms cover them (tspws_cu_forward_dense / _band); lg_end: the lists of D = 2^lg < 32 run only for lg < lg_end (5 = all) */
 /* generic kernel, ONE fp32 trace, only the items [item0, nitems) (= the scales from some scale on): Y -> d_st, phasor -> d_ps */
 int tspws_cu_forward_one(const tspws_devframe_t *f, const float *d_x, int item0, void *d_ps, void *d_st, tspws_stream_t st);
 int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, int chunk,
-                          void *d_part_ps, void *d_part_st, int skip5, tspws_stream_t st);
+                          void *d_part_ps, void *d_part_st, int skip5, int lg_end, tspws_stream_t st);
 /* ---- coarse scales of the single-stage forward transform as one dense GEMM on tcgen05 (tspws_mma.cu) ---- */
 size_t tspws_cu_dense_ximg_bytes(int ntr, int N);
 size_t tspws_cu_dense_wimg_bytes(int ncol, int N);
 int tspws_cu_dense_wimage(const tspws_devframe_t *f, int s0, int ci0, int ncd, void *d_img, tspws_stream_t st);
 int tspws_cu_forward_dense(const float *d_x, int ntr, int N, const void *d_wimg, int ncd, void *d_ximg,
-                           float *d_tsum, float *d_sumtrace, float *d_part, tspws_stream_t st);
+                           float *d_tsum, float *d_sumtrace, float *d_part, int ld_part, int col0, tspws_stream_t st);
+/* ---- middle octaves (32 <= D < dense D) as BANDED GEMMs on tcgen05: one octave (the voices sharing a decimation D)
+ * per descriptor.  With the trace cut into rows of 64 samples, the coefficient m = U P + u (U = 64/D sub-positions per
+ * row when D <= 64; one coefficient every E = D/64 rows otherwise) is
+ *     Y[m] = sum_q  x_row[(P E') + q] . B_q[(u)]      B_q[r] = conj(w[64 q + r - u D + c])
+ * so a group of Pn consecutive row positions x U sub-positions x nv voices x (re|im) = ncols columns is the product of
+ * nj = E (Pn - 1) + qmax - qmin + 1 consecutive 64-sample row blocks of the traces with nj small B tiles that are THE
+ * SAME for every group of the octave (shift invariance) -- [128 traces x 64] . [64 x ncols], accumulated over the nj
+ * row blocks in TMEM.  The A tiles are the dense path's trace image; the epilogue is the dense path's. */
+#define TSPWS_BAND_MAXV 8
+typedef struct {
+    int tile_base;       /* first B tile (unit: one 3-term tile triple) of this octave                  */
+    int nj;              /* row blocks per group                                                        */
+    int ncols;           /* UMMA N: nv * Pn * U * 2 rounded up to a multiple of 16, <= 128              */
+    int rows_per_group;  /* E * Pn: row blocks between consecutive groups                               */
+    int qmin;            /* first row block of group 0 (negative: wraps)                                */
+    int ngroups;
+    int nv, Pn, U, E;    /* column = ((v * Pn + p') * U + u) * 2 + (re | im)                            */
+    int Ns, D;
+    int coef_rel[TSPWS_BAND_MAXV];   /* coefficient offset of voice v relative to the first band coefficient */
+    int s_of[TSPWS_BAND_MAXV];       /* scale index of voice v                                          */
+} tspws_band_t;
+int tspws_cu_band_wimage(const tspws_devframe_t *f, const tspws_band_t *d_bands, int nbands, int ntiles, void *d_img, tspws_stream_t st);
+int tspws_cu_forward_band(const void *d_ximg, int ntr, int N, const void *d_bimg, const tspws_band_t *d_bands, int nbands,
+                          int ngroups_total, float *d_part, int ld_part, tspws_stream_t st);
 int tspws_cu_dense_finish(const float *d_part, int ntr, int ncd, const void *d_ysum, int ci0, void *d_pps0, void *d_pst0,
                           tspws_stream_t st);
 /* Per-trace mode (f->per_trace == 1): raw coefficients of each of the ntr traces (split over
@@ -267,6 +291,7 @@ int tspws_cu_lsconv(const float *d_x, int ntr, int N, const float *d_ref, float 
 
 unsigned long tspws_cu_launch_count(void);
 void tspws_cu_profile_mark(tspws_stream_t st);
+void tspws_cu_profile_launched(const char *name, tspws_stream_t st);
 int  tspws_cu_profile_enabled(void);
 void tspws_cu_launch_count_add(unsigned long n);
 int  tspws_cu_profile_enable(int on);

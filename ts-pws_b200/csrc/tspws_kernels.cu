@@ -95,6 +95,8 @@ static void prof_record(const char *name, cudaStream_t s)
 
 extern "C" int tspws_cu_profile_enabled(void) { return g_prof.on; }
 extern "C" void tspws_cu_profile_mark(tspws_stream_t st) { if (g_prof.on) prof_record(nullptr, (cudaStream_t)st); }
+/* kernels launched from other translation units (tspws_mma.cu): name must be a string literal */
+extern "C" void tspws_cu_profile_launched(const char *name, tspws_stream_t st) { if (g_prof.on) prof_record(name, (cudaStream_t)st); }
 extern "C" int tspws_cu_profile_enable(int on)
 {
     if (!on) prof_flush();
@@ -1672,7 +1674,7 @@ extern "C" int tspws_cu_forward_f64(const tspws_devframe_t *f, const double *d_x
 }
 
 extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x, int ntr, int chunk,
-                                     void *d_part_ps, void *d_part_st, int skip5, tspws_stream_t st)
+                                     void *d_part_ps, void *d_part_st, int skip5, int lg_end, tspws_stream_t st)
 {
     if (ntr <= 0) return 0;
     if (f->per_trace) return (int)cudaErrorInvalidValue;
@@ -1688,7 +1690,7 @@ extern "C" int tspws_cu_forward_fast(const tspws_devframe_t *f, const float *d_x
     { const char *e = getenv("TSPWS_FW_CB"); if (e && atoi(e) > 0) cb = atoi(e); }
     if (cb > nchunk) cb = nchunk;
 #define FW_ACC_LAUNCH(LGV)                                                                              \
-    if (f->fw_lg_begin[LGV + 1] > f->fw_lg_begin[LGV] + (LGV == 5 ? skip5 : 0)) {                       \
+    if ((LGV == 5 || LGV < lg_end) && f->fw_lg_begin[LGV + 1] > f->fw_lg_begin[LGV] + (LGV == 5 ? skip5 : 0)) { \
         const int ib = f->fw_lg_begin[LGV] + (LGV == 5 ? skip5 : 0);                                    \
         const int nb = f->fw_lg_begin[LGV + 1] - ib;                                                    \
         const int nig = (nb + FW_WARPS - 1) / FW_WARPS;                                                 \

@@ -415,9 +415,14 @@ __device__ __forceinline__ void fd_transpose_stage(float (&f)[32], const int lan
  * bias < 1e-6): every chunk accumulates into one of TWO TMEM accumulators, and the epilogue warps drain the finished
  * one into fp32 registers (round-to-nearest adds) while the next chunk's MMAs run -- the promotion trick of FP8 GEMMs. */
 #define FD_CHUNK 8
+/* BAND = false: dense GEMM over all kblocks row blocks, column tile blockIdx.x of w_img, output columns col0 + ...
+ * BAND = true : banded GEMM of one (octave, group) = blockIdx.x (see tspws_band_t): nj row blocks starting at
+ *               group * rows_per_group + qmin (circular), B tiles tile_base .. tile_base + nj of w_img, UMMA N = ncols */
+template <bool BAND>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat16 *__restrict__ w_img,
-                     int kblocks, int ncol, float *__restrict__ part /* [mtiles][ncol] */, int term_mask)
+                     int kblocks_total, int ncol, float *__restrict__ part /* [mtiles][ld_part] */, int ld_part, int col0,
+                     int term_mask, const tspws_band_t *__restrict__ bands)
 {
     extern __shared__ __align__(1024) unsigned char mma_smem[];
     unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(mma_smem) + 1023) & ~(uintptr_t)1023);
@@ -429,7 +434,17 @@ fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat1
     float (*colsum)[MMA_TILE_MN] = reinterpret_cast<float (*)[MMA_TILE_MN]>(tiles);   /* [4 warps][128 columns]: reuses stage 0 after the MMAs */
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nt = blockIdx.x, mt = blockIdx.y;          /* column tiles fastest: the CTAs that share an A tile run together */
+    const int mt = blockIdx.y;                           /* column tiles fastest: the CTAs that share an A tile run together */
+    int nt = blockIdx.x, kblocks = kblocks_total, row0 = 0, btile0 = 0, ncols = MMA_TILE_MN, grp = 0, ob = 0;
+    if (BAND) {
+        grp = blockIdx.x;
+        while (grp >= bands[ob].ngroups) { grp -= bands[ob].ngroups; ob++; }
+        kblocks = bands[ob].nj; ncols = bands[ob].ncols; btile0 = bands[ob].tile_base;
+        row0 = (grp * bands[ob].rows_per_group + bands[ob].qmin) % kblocks_total;
+        if (row0 < 0) row0 += kblocks_total;
+        nt = 0;
+    }
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(MMA_TILE_MN >> 4) << 24);
     constexpr unsigned TMEM_COLS = 2 * MMA_TILE_MN;
     const int nchunk = (kblocks + FD_CHUNK - 1) / FD_CHUNK;
 
@@ -450,10 +465,17 @@ fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat1
             const int s = kb % FD_STAGES;
             if (kb >= FD_STAGES) m_mbar_wait(empty + s, ((kb / FD_STAGES) & 1) ^ 1);
             unsigned char *st = tiles + (size_t)s * FD_STAGE_BYTES;
-            m_mbar_expect_tx(full + s, FD_STAGE_BYTES);
+            m_mbar_expect_tx(full + s, BAND ? FD_NT * MMA_TILE_BYTES + FD_NT * ncols * 128 : FD_STAGE_BYTES);
             /* images: [tile][kb][term] -> the terms of a tile are one contiguous 48 KiB copy */
-            m_bulk_g2s(st, x_img + ((size_t)mt * kblocks + kb) * FD_NT * (MMA_TILE_MN * MMA_TILE_K), FD_NT * MMA_TILE_BYTES, full + s);
-            m_bulk_g2s(st + FD_NT * MMA_TILE_BYTES, w_img + ((size_t)nt * kblocks + kb) * FD_NT * (MMA_TILE_MN * MMA_TILE_K), FD_NT * MMA_TILE_BYTES, full + s);
+            int ka = row0 + kb;                          /* BAND: circular row block of the trace; nj <= kblocks_total */
+            if (ka >= kblocks_total) ka -= kblocks_total;
+            const size_t kw = BAND ? (size_t)(btile0 + kb) : (size_t)nt * kblocks + kb;
+            m_bulk_g2s(st, x_img + ((size_t)mt * kblocks_total + ka) * FD_NT * (MMA_TILE_MN * MMA_TILE_K), FD_NT * MMA_TILE_BYTES, full + s);
+            if (BAND) {                                  /* only the ncols rows (128 B each) the MMA reads, per term */
+                for (int t = 0; t < FD_NT; t++)
+                    m_bulk_g2s(st + (FD_NT + t) * MMA_TILE_BYTES, w_img + (kw * FD_NT + t) * (MMA_TILE_MN * MMA_TILE_K), ncols * 128, full + s);
+            } else
+                m_bulk_g2s(st + FD_NT * MMA_TILE_BYTES, w_img + kw * FD_NT * (MMA_TILE_MN * MMA_TILE_K), FD_NT * MMA_TILE_BYTES, full + s);
         }
     } else if (warp == 1 && lane == 0) {
         for (int c = 0; c < nchunk; c++) {
@@ -472,7 +494,7 @@ fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat1
                     const unsigned kby = k * MMA_UMMA_K * 2;
                     /* smallest products first: they are added while the accumulator is still small */
                     bool first = (kb == c * FD_CHUNK) && k == 0;
-#define FD_MMA(I, J) do { if (term_mask & (1 << (I + J))) { m_umma_bf16(acc, m_smem_desc(a + (I) * MMA_TILE_BYTES, kby), m_smem_desc(b + (J) * MMA_TILE_BYTES, kby), MMA_IDESC, !first); first = false; } } while (0)
+#define FD_MMA(I, J) do { if (term_mask & (1 << (I + J))) { m_umma_bf16(acc, m_smem_desc(a + (I) * MMA_TILE_BYTES, kby), m_smem_desc(b + (J) * MMA_TILE_BYTES, kby), idesc, !first); first = false; } } while (0)
                     FD_MMA(2, 0); FD_MMA(0, 2); FD_MMA(1, 1); FD_MMA(1, 0); FD_MMA(0, 1); FD_MMA(0, 0);
 #undef FD_MMA
                 }
@@ -492,6 +514,7 @@ fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat1
             m_tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < MMA_TILE_MN; c0 += 32) {
+                if (BAND && c0 >= ncols) break;          /* columns the MMA never wrote */
                 uint32_t v[32];
                 m_tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * MMA_TILE_MN + c0), v);
 #pragma unroll
@@ -504,6 +527,7 @@ fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat1
         /* phasor of every (trace, coefficient), then the sum over this warp's 32 traces */
 #pragma unroll
         for (int c0 = 0; c0 < MMA_TILE_MN; c0 += 32) {
+            if (BAND && c0 >= ncols) break;
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) fd_phasor(y[c0 + j], y[c0 + j + 1], f[j], f[j + 1]);
@@ -516,9 +540,19 @@ fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat1
     m_tc_fence_before();
     __syncthreads();
     if (threadIdx.x < MMA_TILE_MN) {
-        const int col = nt * MMA_TILE_MN + threadIdx.x;
-        if (col < ncol)
-            part[(size_t)mt * ncol + col] = ((colsum[2][threadIdx.x] + colsum[3][threadIdx.x]) + colsum[0][threadIdx.x]) + colsum[1][threadIdx.x];
+        const float sum = ((colsum[2][threadIdx.x] + colsum[3][threadIdx.x]) + colsum[0][threadIdx.x]) + colsum[1][threadIdx.x];
+        if (BAND) {
+            /* column = ((v Pn + p') U + u) 2 + (re | im)  ->  coefficient m = (grp Pn + p') U + u of voice v */
+            const tspws_band_t *bd = bands + ob;
+            const int col = threadIdx.x, t2 = col >> 1, U = bd->U, Pn = bd->Pn;
+            const int u = t2 % U, t3 = t2 / U, pp = t3 % Pn, v = t3 / Pn;
+            const int m = (grp * Pn + pp) * U + u;
+            if (col < ncols && v < bd->nv && m < bd->Ns)
+                part[(size_t)mt * ld_part + 2 * (bd->coef_rel[v] + m) + (col & 1)] = sum;
+        } else {
+            const int col = nt * MMA_TILE_MN + threadIdx.x;
+            if (col < ncol) part[(size_t)mt * ld_part + col0 + col] = sum;
+        }
     }
     if (warp == 2) m_tmem_dealloc(tmem, TMEM_COLS);
 }
@@ -592,8 +626,8 @@ extern "C" size_t tspws_cu_dense_wimg_bytes(int ncol, int N)
 
 /* x [ntr][N] (N % 64 == 0) -> PS partial rows of the dense coefficients + the summed trace */
 extern "C" int tspws_cu_forward_dense(const float *d_x, int ntr, int N, const void *d_wimg, int ncd, void *d_ximg,
-                                      float *d_tsum /* [mtiles][N] */, float *d_sumtrace /* [N] */, float *d_part /* [mtiles][2 ncd] */,
-                                      tspws_stream_t st)
+                                      float *d_tsum /* [mtiles][N] */, float *d_sumtrace /* [N] */, float *d_part /* [mtiles][ld_part] */,
+                                      int ld_part, int col0, tspws_stream_t st)
 {
     if (ntr <= 0 || ncd <= 0) return 0;
     if (N % MMA_TILE_K) return (int)cudaErrorInvalidValue;
@@ -602,14 +636,78 @@ extern "C" int tspws_cu_forward_dense(const float *d_x, int ntr, int N, const vo
     const int ntiles = (ncol + MMA_TILE_MN - 1) / MMA_TILE_MN;
     cudaFuncSetAttribute(trace_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_NT * MMA_TILE_BYTES);
     trace_image_kernel<<<dim3(kblocks, mtiles), 256, FD_NT * MMA_TILE_BYTES, s>>>(d_x, ntr, N, kblocks, (__nv_bfloat16 *)d_ximg, d_tsum);
+    tspws_cu_profile_launched("trace_image_kernel", st);
     tile_sum_kernel<<<(N + 255) / 256, 256, 0, s>>>(d_tsum, mtiles, N, d_sumtrace);
+    tspws_cu_profile_launched("tile_sum_kernel", st);
     const size_t smem = (size_t)FD_STAGES * FD_STAGE_BYTES + 1024 + (2 * FD_STAGES + 4) * 8 + 16;
-    cudaError_t e = cudaFuncSetAttribute(fwd_dense_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fwd_dense_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    fwd_dense_mma_kernel<<<dim3(ntiles, mtiles), MMA_THREADS, smem, s>>>((const __nv_bfloat16 *)d_ximg, (const __nv_bfloat16 *)d_wimg,
-                                                                         kblocks, ncol, d_part,
-                                                                         getenv("TSPWS_DENSE_TERMS") ? atoi(getenv("TSPWS_DENSE_TERMS")) : 7);   /* bit (i + j): products of terms i, j */
+    fwd_dense_mma_kernel<false><<<dim3(ntiles, mtiles), MMA_THREADS, smem, s>>>((const __nv_bfloat16 *)d_ximg, (const __nv_bfloat16 *)d_wimg,
+                                                                         kblocks, ncol, d_part, ld_part, col0,
+                                                                         getenv("TSPWS_DENSE_TERMS") ? atoi(getenv("TSPWS_DENSE_TERMS")) : 7,   /* bit (i + j): products of terms i, j */
+                                                                         nullptr);
+    tspws_cu_profile_launched("fwd_dense_mma_kernel<dense>", st);
     tspws_cu_launch_count_add(3);
+    return (int)cudaGetLastError();
+}
+
+/* middle octaves: banded GEMMs over the trace image tspws_cu_forward_dense built (call it first) */
+extern "C" int tspws_cu_forward_band(const void *d_ximg, int ntr, int N, const void *d_bimg, const tspws_band_t *d_bands, int nbands,
+                                     int ngroups_total, float *d_part, int ld_part, tspws_stream_t st)
+{
+    if (ntr <= 0 || nbands <= 0 || ngroups_total <= 0) return 0;
+    if (N % MMA_TILE_K) return (int)cudaErrorInvalidValue;
+    const int mtiles = (ntr + MMA_TILE_MN - 1) / MMA_TILE_MN;
+    const size_t smem = (size_t)FD_STAGES * FD_STAGE_BYTES + 1024 + (2 * FD_STAGES + 4) * 8 + 16;
+    cudaError_t e = cudaFuncSetAttribute(fwd_dense_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    fwd_dense_mma_kernel<true><<<dim3(ngroups_total, mtiles), MMA_THREADS, smem, (cudaStream_t)st>>>(
+        (const __nv_bfloat16 *)d_ximg, (const __nv_bfloat16 *)d_bimg, N / MMA_TILE_K, 0, d_part, ld_part, 0,
+        getenv("TSPWS_DENSE_TERMS") ? atoi(getenv("TSPWS_DENSE_TERMS")) : 7, d_bands);
+    tspws_cu_profile_launched("fwd_dense_mma_kernel<band>", st);
+    tspws_cu_launch_count_add(1);
+    return (int)cudaGetLastError();
+}
+
+/* B tiles of the banded GEMMs: tile (octave, jj), row = column of the product, element r of the 64-sample row block:
+ *   q = jj + qmin - E p',  l = 64 q + r - u D + c_v,  value = conj(w_v[l]) for 0 <= l < L_v, else 0 */
+__global__ void __launch_bounds__(256)
+band_w_image_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__ w32, const tspws_band_t *__restrict__ bands,
+                    int nbands, __nv_bfloat16 *__restrict__ img)
+{
+    const int tile = blockIdx.x;
+    int ob = 0;
+    while (ob + 1 < nbands && bands[ob + 1].tile_base <= tile) ob++;
+    const tspws_band_t bd = bands[ob];
+    const int jj = tile - bd.tile_base;
+    __nv_bfloat16 *t0 = img + (size_t)tile * FD_NT * (MMA_TILE_MN * MMA_TILE_K);
+    for (int e = threadIdx.x; e < MMA_TILE_MN * MMA_TILE_K; e += blockDim.x) {
+        const int col = e / MMA_TILE_K, r = e % MMA_TILE_K;
+        float v = 0.f;
+        const int t2 = col >> 1, u = t2 % bd.U, t3 = t2 / bd.U, pp = t3 % bd.Pn, vi = t3 / bd.Pn;
+        if (col < bd.ncols && vi < bd.nv) {
+            const tspws_scale_t sc = scales[bands[ob].s_of[vi]];
+            const int q = jj + bd.qmin - bd.E * pp;
+            const int l = 64 * q + r - u * bd.D + sc.c;
+            if (l >= 0 && l < sc.L) {
+                const float2 w = w32[sc.tap_off + l];
+                v = (col & 1) ? -w.y : w.x;
+            }
+        }
+        const unsigned o = mma_img_offset(col, r);
+#pragma unroll
+        for (int term = 0; term < FD_NT; term++) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            t0[(size_t)term * (MMA_TILE_MN * MMA_TILE_K) + o] = h;
+            v -= __bfloat162float(h);
+        }
+    }
+}
+
+extern "C" int tspws_cu_band_wimage(const tspws_devframe_t *f, const tspws_band_t *d_bands, int nbands, int ntiles, void *d_img, tspws_stream_t st)
+{
+    if (nbands <= 0 || ntiles <= 0) return 0;
+    band_w_image_kernel<<<ntiles, 256, 0, (cudaStream_t)st>>>(f->d_scale, (const float2 *)f->d_w32, d_bands, nbands, (__nv_bfloat16 *)d_img);
     return (int)cudaGetLastError();
 }
 
@@ -620,6 +718,7 @@ extern "C" int tspws_cu_dense_finish(const float *d_part, int ntr, int ncd, cons
     const int mtiles = (ntr + MMA_TILE_MN - 1) / MMA_TILE_MN;
     dense_finish_kernel<<<(ncd + 255) / 256, 256, 0, (cudaStream_t)st>>>(d_part, mtiles, ncd, (const float2 *)d_ysum, ci0,
                                                                           (float2 *)d_pps0, (float2 *)d_pst0);
+    tspws_cu_profile_launched("dense_finish_kernel", st);
     tspws_cu_launch_count_add(1);
     return (int)cudaGetLastError();
 }

@@ -67,6 +67,9 @@ struct tspws_plan {
     int          hybrid;            /* TSPWS_F64_MAXL set: long filters transform the unsplit sums instead */
     /* coarse scales of the single-stage forward transform on the tensor cores (tspws_cu_forward_dense) */
     int     dense_on, dense_s0, dense_ci0, dense_ncd, dense_items;
+    /* middle octaves as banded GEMMs (tspws_cu_forward_band); td_*: the whole tensor-core range = band + dense scales */
+    int     band_n, band_groups, td_s0, td_ci0, td_ncd, simt_lg_end;
+    void   *d_bimg; tspws_band_t *d_bands;
     void   *d_wimg, *d_ximg, *d_ysum_ps, *d_ysum_st;
     float  *d_tsum, *d_sumtrace, *d_dpart;
     unsigned int *d_tile_tickets;   /* [ntile16]: fused phasor combine of fwd_tail_kernel (NULL: separate combine launch) */
@@ -581,7 +584,7 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = NULL; }
     if (pl->side) { cudaStreamDestroy(pl->side); cudaEventDestroy(pl->ev_join); cudaEventDestroy(pl->ev_fork); }
     cudaFree(pl->d_gmean); cudaFree(pl->d_ymean); cudaFree(pl->d_tile_tickets);
-    cudaFree(pl->d_wimg); cudaFree(pl->d_ximg); cudaFree(pl->d_tsum); cudaFree(pl->d_sumtrace); cudaFree(pl->d_dpart); cudaFree(pl->d_ysum_ps); cudaFree(pl->d_ysum_st);
+    cudaFree(pl->d_bimg); cudaFree(pl->d_bands); cudaFree(pl->d_wimg); cudaFree(pl->d_ximg); cudaFree(pl->d_tsum); cudaFree(pl->d_sumtrace); cudaFree(pl->d_dpart); cudaFree(pl->d_ysum_ps); cudaFree(pl->d_ysum_st);
     free(pl->h_slot_off);
     tspws_devframe_free(&pl->dev);
     tspws_b200_plan_peer_close(pl);
@@ -594,6 +597,70 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
     cudaFree(pl->d_zout); cudaFree(pl->d_invscratch); cudaFree(pl->d_ypart); cudaFree(pl->d_inv_tickets);
     tspws_b200_frame_destroy(pl->fr);
     free(pl);
+}
+
+static int floor_div(int a, int b) { int q = a / b; if ((a % b) && ((a < 0) != (b < 0))) q--; return q; }
+
+/* Middle octaves of a single-stage plan as banded GEMMs: walks down from the first dense scale, one descriptor per
+ * run of scales with equal decimation D >= TSPWS_BAND_D (default 16 -- measured at 8192 x 16384, w0 = 6: 9.11 ms with 32,
+ * 8.55 with 16, 8.66 with 8; 0 = off).  Updates td_* and dense_items. */
+static int band_plan(tspws_plan_t *pl, int N)
+{
+    const tspws_frame_t *fr = pl->fr;
+    const long bD = env_long("TSPWS_BAND_D", 16);
+    if (bD <= 0) return 0;
+    tspws_band_t bands[16];
+    int nb = 0, tiles = 0, groups = 0, sb = pl->dense_s0;
+    const int kblocks = N / 64;
+    while (sb > 0 && nb < 16) {
+        const int D = (int)fr->D[sb - 1];
+        if (D < bD || D < 2 || (N % D)) break;
+        if (D < 32 && pl->dev.nitems_gen) break;         /* D = 2^lg < 32: its whole polyphase list is skipped, so every scale must be on it */
+        if (D <= 64 ? (64 % D) : (D % 64)) break;
+        int sa = sb - 1;
+        while (sa > 0 && (int)fr->D[sa - 1] == D) sa--;
+        const int nv = sb - sa, U = D <= 64 ? 64 / D : 1, E = D <= 64 ? 1 : D / 64;
+        if (nv > TSPWS_BAND_MAXV || nv * U * 2 > 128) break;
+        int Pn = 128 / (nv * U * 2);                     /* as many row positions per group as 128 columns hold */
+        if (Pn * E > kblocks) Pn = kblocks / E;
+        if (Pn < 1) break;
+        int qmin = 1 << 30, qmax = -(1 << 30);
+        for (int v = 0; v < nv; v++) {
+            const int c = fr->center[sa + v], L = (int)fr->L[sa + v];
+            const int a = floor_div(-c, 64), b = floor_div((U - 1) * D - c + L - 1, 64);
+            if (a < qmin) qmin = a;
+            if (b > qmax) qmax = b;
+        }
+        tspws_band_t *b = &bands[nb];
+        memset(b, 0, sizeof *b);
+        b->nj = E * (Pn - 1) + qmax - qmin + 1;
+        if (b->nj > kblocks) break;
+        b->tile_base = tiles; b->ncols = (nv * Pn * U * 2 + 15) & ~15; b->rows_per_group = E * Pn; b->qmin = qmin;
+        b->nv = nv; b->Pn = Pn; b->U = U; b->E = E; b->Ns = (int)fr->Ns[sa]; b->D = D;
+        b->ngroups = (b->Ns + Pn * U - 1) / (Pn * U);
+        for (int v = 0; v < nv; v++) { b->s_of[v] = sa + v; b->coef_rel[v] = (int)fr->coef_off[sa + v]; }
+        tiles += b->nj; groups += b->ngroups; nb++;
+        sb = sa;
+    }
+    if (!nb) return 0;
+    const int ci0 = (int)fr->coef_off[sb];
+    int items = 0;
+    int lg_end = 5;
+    for (unsigned int s = (unsigned int)sb; s < fr->S; s++) {
+        if (fr->D[s] >= 32) items += ((int)fr->Ns[s] + 15) / 16;
+        else { int lg = 0; while ((1u << lg) < fr->D[s]) lg++; if (lg < lg_end) lg_end = lg; }   /* whole list of D = 2^lg skipped */
+    }
+    pl->simt_lg_end = lg_end;
+    for (int i = 0; i < nb; i++)
+        for (int v = 0; v < bands[i].nv; v++) bands[i].coef_rel[v] -= ci0;
+    if (cudaMalloc((void **)&pl->d_bands, nb * sizeof(tspws_band_t)) != cudaSuccess) return 1;
+    if (cudaMemcpy(pl->d_bands, bands, nb * sizeof(tspws_band_t), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+    if (cudaMalloc(&pl->d_bimg, (size_t)tiles * 3 * 16384) != cudaSuccess) return 1;
+    if (tspws_cu_band_wimage(&pl->dev, pl->d_bands, nb, tiles, pl->d_bimg, NULL)) return 1;
+    pl->band_n = nb; pl->band_groups = groups;
+    pl->td_s0 = sb; pl->td_ci0 = ci0; pl->td_ncd = (int)(fr->ncoef - (size_t)ci0);
+    pl->dense_items = items;
+    return 0;
 }
 
 tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr_local,
@@ -666,7 +733,10 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
                     CK(cudaMalloc(&pl->d_ximg, tspws_cu_dense_ximg_bytes((int)mtr_local, max)));
                     CK(cudaMalloc((void **)&pl->d_tsum, (size_t)mtiles * max * sizeof(float)));
                     CK(cudaMalloc((void **)&pl->d_sumtrace, (size_t)max * sizeof(float)));
-                    CK(cudaMalloc((void **)&pl->d_dpart, (size_t)mtiles * 2 * pl->dense_ncd * sizeof(float)));
+                    pl->td_s0 = s0; pl->td_ci0 = pl->dense_ci0; pl->td_ncd = pl->dense_ncd; pl->simt_lg_end = 5;
+                    if (band_plan(pl, (int)max)) goto fail;
+                    CK(cudaMalloc((void **)&pl->d_dpart, (size_t)mtiles * 2 * pl->td_ncd * sizeof(float)));
+                    CK(cudaMemset(pl->d_dpart, 0, (size_t)mtiles * 2 * pl->td_ncd * sizeof(float)));
                     CK(cudaMalloc(&pl->d_ysum_ps, ncoef * 2 * sizeof(float)));
                     CK(cudaMalloc(&pl->d_ysum_st, ncoef * 2 * sizeof(float)));
                     if (tspws_cu_dense_wimage(&pl->dev, s0, pl->dense_ci0, pl->dense_ncd, pl->d_wimg, NULL)) goto fail;
@@ -754,13 +824,16 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     } else {
         if (pl->dense_on &&
             (e = tspws_cu_forward_dense(d_sigall, pl->ntr_fwd, pl->N, pl->d_wimg, pl->dense_ncd, pl->d_ximg, pl->d_tsum, pl->d_sumtrace,
-                                        pl->d_dpart, stream))) return TSPWS_ERR_CUDA;
+                                        pl->d_dpart, 2 * pl->td_ncd, 2 * (pl->dense_ci0 - pl->td_ci0), stream))) return TSPWS_ERR_CUDA;
+        if (pl->band_n &&
+            (e = tspws_cu_forward_band(pl->d_ximg, pl->ntr_fwd, pl->N, pl->d_bimg, pl->d_bands, pl->band_n, pl->band_groups,
+                                       pl->d_dpart, 2 * pl->td_ncd, stream))) return TSPWS_ERR_CUDA;
         if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst,
-                                       pl->dense_on ? pl->dense_items : 0, stream))) return TSPWS_ERR_CUDA;
+                                       pl->dense_on ? pl->dense_items : 0, pl->dense_on ? pl->simt_lg_end : 5, stream))) return TSPWS_ERR_CUDA;
         if (pl->dense_on) {
             /* linear stack of the dense coefficients = transform of the summed trace (generic kernel, one trace) */
-            if ((e = tspws_cu_forward_one(&pl->dev, pl->d_sumtrace, pl->dev.h_item_first[pl->dense_s0], pl->d_ysum_ps, pl->d_ysum_st, stream))) return TSPWS_ERR_CUDA;
-            if ((e = tspws_cu_dense_finish(pl->d_dpart, pl->ntr_fwd, pl->dense_ncd, pl->d_ysum_st, pl->dense_ci0, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_forward_one(&pl->dev, pl->d_sumtrace, pl->dev.h_item_first[pl->td_s0], pl->d_ysum_ps, pl->d_ysum_st, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_dense_finish(pl->d_dpart, pl->ntr_fwd, pl->td_ncd, pl->d_ysum_st, pl->td_ci0, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
         }
     }
     if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, pl->acc64, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,

@@ -222,7 +222,7 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
         if ((rc = rp_begin(rpp, k, st))) goto done;
         CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, NULL, nb, (int)Kmax, d_gs, st));
         if (ls_rows) CKK(tspws_cu_group_total(d_gs, nb, (int)Kmax, max, d_scale, d_ls, st));
-        CKK(tspws_cu_forward_fast(&F->acc, d_gs, nb * (int)Kmax, (int)Kmax, d_pps, d_pst, 0, st));
+        CKK(tspws_cu_forward_fast(&F->acc, d_gs, nb * (int)Kmax, (int)Kmax, d_pps, d_pst, 0, 5, st));
         CKK(tspws_cu_weight(d_pps, d_pst, 0, (int)F->fr->ncoef, nb, d_rules, d_zout, st));
         CKK(tspws_cu_inverse(&F->acc, d_zout, NULL, 0, nb, d_rules, d_scr, d_tk, d_ts, NULL, st, NULL, NULL, NULL));
         if (d_ref && sim_out) CKK(tspws_cu_simil(d_ts, nb, max, d_ref, d_sim, d_sim + B, st));
@@ -334,7 +334,7 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
         if ((rc = rp_begin(rpp, k, st))) goto done;
         CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, d_sel + (size_t)m0 * mtr, nb, 1, d_S, st));
         CKK(tspws_cu_group_total(d_S, nb, 1, max, d_scale, d_ls, st));
-        CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, 0, st));
+        CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, 0, 5, st));
         if (use_mma)
             CKK(tspws_cu_weight_mixed32((char *)d_ps + (size_t)m0 * ncoef * 2 * sizeof(float), d_pst, (int)F->fr->ncoef, nb,
                                         d_rules, d_zout, st));
