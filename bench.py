@@ -468,6 +468,90 @@ class ShardedStack:
         self.plan = None
 
 
+class PipedStacks:
+    """A stream of independent stacks of one geometry through tspws_b200_pipe_* : the group sums of stack i+1 run
+    while the tail of stack i finishes (depth plans as buffers).  At N > 1 every plan of the pipe gets the peer
+    exchange of ShardedStack (one exchange region per plan)."""
+
+    def __init__(self, ctx, params, n, mtr_local, mtr_total, offset, depth=4):
+        self.ctx, self.n, self.depth = ctx, n, depth
+        B, lib, torch, dist = ctx.B, ctx.lib, ctx.torch, ctx.dist
+        p = B.default_params(**params)
+        lib.tspws_b200_derive_params(C.byref(p), n, 1.0)
+        self.pipe = lib.tspws_b200_pipe_create(C.byref(p), n, mtr_local, mtr_total, offset, depth)
+        self.ok = bool(self.pipe)
+        world = ctx.world
+        self.peer = False
+        if world > 1:
+            ok = self.ok
+            for k in range(depth):
+                plan = lib.tspws_b200_pipe_plan(self.pipe, k) if self.pipe else None
+                h = (C.c_ubyte * 64)()
+                ok = ok and lib.tspws_b200_plan_peer_export(plan, world, h) == 0
+                mine = torch.tensor(list(h), dtype=torch.uint8, device="cuda")
+                allh = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(allh, mine)
+                if ctx.all_ok(ok):
+                    buf = (C.c_ubyte * (64 * world))(*torch.cat(allh).cpu().tolist())
+                    ok = lib.tspws_b200_plan_peer_import(plan, ctx.rank, world, buf) == 0
+                ok = ctx.all_ok(ok)
+                if not ok:
+                    break
+            self.ok = self.peer = ok
+        if self.ok:
+            self.H = torch.cuda.ExternalStream(lib.tspws_b200_pipe_stream(self.pipe, 0))
+            self.T = torch.cuda.ExternalStream(lib.tspws_b200_pipe_stream(self.pipe, 1))
+            self.outs = [(torch.empty(n, device="cuda"), torch.empty(n, device="cuda")) for _ in range(depth)]
+            self.i = 0
+
+    def submit(self, d_x):
+        k = self.i % self.depth
+        rc = self.ctx.lib.tspws_b200_pipe_submit(self.pipe, d_x.data_ptr(), self.outs[k][0].data_ptr(), self.outs[k][1].data_ptr())
+        if rc:
+            raise SystemExit(f"pipe submit failed rc={rc}")
+        self.i += 1
+        return self.outs[k]
+
+    def sync(self):
+        if self.ctx.lib.tspws_b200_pipe_sync(self.pipe):
+            raise SystemExit("pipe sync failed")
+
+    def timed(self, xs, steps):
+        """K stacks (inputs alternating over xs) between an event on the sums stream before the first submit and an
+        event on the tail stream after the last, barrier + synchronize on both sides, max over ranks; ms per stack."""
+        ctx, torch = self.ctx, self.ctx.torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.sync()
+        ctx.barrier()
+        ev0.record(self.H)
+        for j in range(steps):
+            self.submit(xs[j % len(xs)])
+        ev1.record(self.T)
+        self.sync()
+        ctx.barrier()
+        return ctx.max_over_ranks(ev0.elapsed_time(ev1))[0] / steps
+
+    def close(self):
+        ctx, lib = self.ctx, self.ctx.lib
+        if not self.pipe:
+            return
+        ctx.torch.cuda.synchronize()
+        if ctx.world > 1:
+            try:
+                ctx.dist.barrier()
+                for k in range(self.depth):
+                    lib.tspws_b200_plan_peer_close(lib.tspws_b200_pipe_plan(self.pipe, k))
+                ctx.dist.barrier()
+            except Exception:                           # noqa: BLE001
+                pass
+        lib.tspws_b200_pipe_destroy(self.pipe)
+        self.pipe = None
+
+
+def peer_err_check(lib, ps):
+    return ps.peer and any(lib.tspws_b200_plan_peer_error(lib.tspws_b200_pipe_plan(ps.pipe, k)) for k in range(ps.depth))
+
+
 def whole_step_frac(mtr, n, ms_step, hbm_peak):
     return (4.0 * mtr * n / (ms_step * 1e-3) / 1e9) / hbm_peak
 
@@ -573,6 +657,38 @@ def run_stack(args, wl, name):
         k_alone_ms = ev0.elapsed_time(ev1) / steps
         st.step(d_x, d_ls, d_ts)                        # leave complete outputs behind
         torch.cuda.synchronize()
+
+    # (4) two-stage: a stream of independent stacks, software-pipelined (tspws_b200_pipe_*): the HBM-bound group sums of
+    # stack i+1 overlap the latency-bound tail of stack i.  This is the throughput `value` reports; the single-stack
+    # figures above stay in config.  Two input buffers alternate (each 512 MiB > L2).
+    pipelined = None
+    ms_single = ms_step
+    if two_stage and not args.no_pipe:
+        ps = PipedStacks(ctx, wl["params"], n, mtr, mtr * world, rank * mtr, depth=args.pipe_depth)
+        if ps.ok:
+            d_x2 = torch.roll(d_x, 1, 0)
+            xs = [d_x, d_x2]
+            for j in range(2 * ps.depth):
+                o_ls, o_ts = ps.submit(xs[j % 2])
+            ps.sync()
+            ps.i = 0
+            o_ls, o_ts = ps.submit(d_x)                    # parity of the pipelined path against the single-stack step
+            ps.sync()
+            pipe_diff = nerr(o_ts.cpu().numpy(), d_ts.cpu().numpy())
+            ps.i = 0
+            n1 = lib.tspws_b200_kernel_launches()
+            ms_pipe = ps.timed(xs, steps)
+            pipe_launches = lib.tspws_b200_kernel_launches() - n1
+            ms_pipe_sus = ps.timed(xs, sus_steps)
+            pipelined = {"stacks_in_flight": ps.depth, "api": "tspws_b200_pipe_submit / tspws_b200_pipe_sync",
+                         "ms_per_step": ms_pipe, "ms_per_step_sustained": ms_pipe_sus, "sustained_steps": sus_steps,
+                         "tsPWS_vs_single_stack_step": ctx.max_over_ranks(pipe_diff)[0],
+                         "input_buffers": 2, "exchange": ("peer memory over NVLink" if ps.peer else "none")}
+            if peer_err_check(lib, ps):
+                raise SystemExit(f"rank {rank}: a peer wait timed out in the pipelined leg -- the measurement is invalid")
+            ms_step, launches = ms_pipe, pipe_launches
+            del d_x2
+        ps.close()
 
     total_samples = float(mtr) * n * world
     value = total_samples / (ms_step * 1e-3)
@@ -699,7 +815,8 @@ def run_stack(args, wl, name):
                 "kernel_ms_back_to_back": k_alone_ms,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "frac_whole_step": whole_step_frac(mtr, n, ms_step, hbm_peak),
-                "frac_whole_step_sustained": whole_step_frac(mtr, n, ms_sustained, hbm_peak),
+                "frac_whole_step_sustained": whole_step_frac(mtr, n, pipelined["ms_per_step_sustained"] if pipelined else ms_sustained, hbm_peak),
+                "frac_single_stack_step": whole_step_frac(mtr, n, ms_single, hbm_peak),
                 "kernels_ms_per_step": {k: v[1] / steps for k, v in prof.items() if v[0]}}
     roofline["whole_step_frac"] = roofline["frac_whole_step"]
     if not two_stage:
@@ -739,7 +856,12 @@ def run_stack(args, wl, name):
                    f"{'group sums' if two_stage else 'phasor/linear sums'}" if world > 1 else "single GPU",
                    "l2_note": "per-step input 512 MiB per GPU > 126 MB L2 (no flush needed)",
                    "ms_per_step_with_kernel_events": ms_prof,
-                   "ms_per_step_sustained": ms_sustained, "sustained_steps": sus_steps,
+                   "step": ("K independent stacks submitted to a 2-stream software pipeline (pipelined); ms_per_step = elapsed / K"
+                            if pipelined else "K stacks one after the other"),
+                   "pipelined": pipelined,
+                   "single_stack": {"ms_per_step": ms_single, "ms_per_step_sustained": ms_sustained, "sustained_steps": sus_steps,
+                                    "note": "one stack at a time through tspws_b200_plan_stack (latency of a stack)"},
+                   "ms_per_step_sustained": pipelined["ms_per_step_sustained"] if pipelined else ms_sustained, "sustained_steps": sus_steps,
                    "step_replayed_as_cuda_graph": bool(world == 1 or peer or st.graph is not None),
                    "exchange": ("none" if world == 1 else "peer memory over NVLink, fused into the stack's own kernels" if peer
                                 else "NCCL all-reduce")},
@@ -774,6 +896,15 @@ def short_stack_leg(ctx, wlname, steps, hbm_peak, cpu_traces):
     out = {"desc": wl["desc"], "value": float(mtr) * n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
            "frac_whole_step": whole_step_frac(mtr, n, ms, hbm_peak),
            "kernels_ms_per_step": {k: v[1] / steps for k, v in prof.items() if v[0]}}
+    if st.two_stage:
+        ps = PipedStacks(ctx, wl["params"], n, mtr, mtr, 0)
+        if ps.ok:
+            for _ in range(2 * ps.depth):
+                ps.submit(d_x)
+            msp = ps.timed([d_x], steps)
+            out["pipelined"] = {"stacks_in_flight": ps.depth, "ms_per_step": msp, "value": float(mtr) * n / (msp * 1e-3),
+                                "frac_whole_step": whole_step_frac(mtr, n, msp, hbm_peak)}
+        ps.close()
     if not st.two_stage:
         fr = lib.tspws_b200_frame_create(st.p.type, st.p.J, st.p.V, n, st.p.s0, st.p.b0, st.p.w0, st.p.uni)
         f = fr.contents
@@ -957,6 +1088,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extra", action="store_true", help="skip the short legs of the other BASELINE configs (N = 1)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs (N > 1)")
+    ap.add_argument("--no-pipe", action="store_true", help="two-stage: time one stack at a time instead of the stack pipeline")
+    ap.add_argument("--pipe-depth", type=int, default=4, help="stacks in flight in the pipelined leg")
     args = ap.parse_args()
     protect_stdout()
     wl = WORKLOADS[args.workload]

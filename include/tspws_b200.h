@@ -286,6 +286,22 @@ size_t tspws_b200_plan_ncoef(tspws_plan_t *plan);
 long tspws_b200_plan_get_stacks(tspws_plan_t *plan, double *st, double *ps, size_t ncoef);
 unsigned int tspws_b200_plan_K(tspws_plan_t *plan);
 
+/* A stream of independent stacks of one geometry (what a data set run of src/ts_pws1f.c is: one stack per station
+ * pair / component), software-pipelined on the GPU: the HBM-bound group sums of stack i+1 run while the latency-bound
+ * tail (transforms of the group sums, phase stack, inverse) of stack i finishes.  `depth` plans (2-4) are the buffers.
+ * submit enqueues one stack (device pointers; any device pointers, they may change from stack to stack) and
+ * returns at once; sync waits for everything submitted.  Each stack is computed exactly as tspws_b200_plan_stack
+ * computes it.  pipe_stream(p, 0 | 1): the cudaStream_t the sums | tails run on (to order or time work against).
+ * pipe_plan(p, k): plan k, k = (submit index) % depth, for tspws_b200_plan_get_stacks after a sync. */
+typedef struct tspws_pipe tspws_pipe_t;
+tspws_pipe_t *tspws_b200_pipe_create(const t_tsPWS *p, int max, unsigned int mtr_local, unsigned int mtr_total,
+                                     unsigned int trace_offset, int depth);   /* shard arguments as tspws_b200_plan_create */
+int   tspws_b200_pipe_submit(tspws_pipe_t *pipe, float *d_sigall, float *d_ls, float *d_tspws);
+int   tspws_b200_pipe_sync(tspws_pipe_t *pipe);
+void *tspws_b200_pipe_stream(tspws_pipe_t *pipe, int which);
+tspws_plan_t *tspws_b200_pipe_plan(tspws_pipe_t *pipe, int k);
+void  tspws_b200_pipe_destroy(tspws_pipe_t *pipe);
+
 /* ------------------------------------------------------------------------- */
 /* ABI checks against the reference layout (probed with the reference header) */
 /* ------------------------------------------------------------------------- */

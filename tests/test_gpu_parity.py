@@ -320,6 +320,36 @@ def test_full_size_single_stage_w6_vs_oracle(pkg, gpu_lib):
     assert O.nerr(ls, o_ls) <= TOL_STACK and O.nerr(ts, o_ts) <= TOL_STACK
 
 
+@pytest.mark.parametrize("kw,depth", [(dict(Kmax=10, unbiased=1, lrm=1), 3), (dict(Kmax=7), 2), (dict(), 2)],
+                         ids=["two_stage_unbiased_rm", "two_stage_biased", "single_stage"])
+def test_stack_pipeline_matches_one_stack_at_a_time(pkg, gpu_lib, kw, depth):
+    """tspws_b200_pipe_*: 7 different stacks through a software pipeline of `depth` plans (sums of stack i+1 overlap
+    the tail of stack i) -- every stack must equal the same stack through tspws_b200_plan_stack, and the oracle."""
+    import torch
+    lib = gpu_lib
+    mtr, n, nst = 96, 4096, 7
+    xs = [_bench_traces(mtr, n) * np.float32(1 + 0.1 * j) + np.roll(_bench_traces(mtr, n), 3 * j + 1, axis=0) * np.float32(0.05 * j)
+          for j in range(nst)]
+    p = pkg.default_params(**kw)
+    lib.tspws_b200_derive_params(C.byref(p), n, 1.0)
+    pipe = lib.tspws_b200_pipe_create(C.byref(p), n, mtr, mtr, 0, depth)
+    assert pipe
+    try:
+        dxs = [torch.from_numpy(x).cuda() for x in xs]
+        outs = [(torch.empty(n, device="cuda"), torch.empty(n, device="cuda")) for _ in range(nst)]
+        for rep in range(2):                               # second round: replayed graphs with changed pointers
+            for j in range(nst):
+                assert lib.tspws_b200_pipe_submit(pipe, dxs[j].data_ptr(), outs[j][0].data_ptr(), outs[j][1].data_ptr()) == 0
+            assert lib.tspws_b200_pipe_sync(pipe) == 0
+        for j in (0, 3, 6):
+            ls, ts, _ = _plan_stack(pkg, lib, xs[j], **kw)
+            assert O.nerr(outs[j][1].cpu().numpy(), ts) <= 1e-6 and O.nerr(outs[j][0].cpu().numpy(), ls) <= 1e-6
+            o = O.tspws_main(O.Params(**kw), xs[j])
+            assert O.nerr(outs[j][1].cpu().numpy(), o["tsPWS"]) <= TOL_STACK
+    finally:
+        lib.tspws_b200_pipe_destroy(pipe)
+
+
 @pytest.mark.parametrize("kw", [dict(w0=6.0, w0set=4), dict(), dict(type=-3)], ids=["morlet_w6", "morlet_default", "mexhat"])
 def test_tensor_core_octaves_vs_simt_and_oracle(pkg, gpu_lib, kw, monkeypatch):
     """1024 x 16384 single stage: the octaves D >= 16 run as banded / dense tcgen05 GEMMs (tspws_cu_forward_band,

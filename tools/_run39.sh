@@ -1,0 +1,2 @@
+cd /root/repo
+for c in 592 444 296; do echo "CS2_CTAS=$c"; TSPWS_CS2_CTAS=$c timeout 300 python tools/pipe_probe2.py 2>&1 | tail -4; done

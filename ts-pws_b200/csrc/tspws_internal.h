@@ -302,3 +302,5 @@ int  tspws_cu_profile_read(char *buf, int cap);
 }
 #endif
 #endif
+
+void tspws_plan_set_cs2_hint(int ctas);

@@ -1,0 +1,142 @@
+/*
+ * Software pipeline over a stream of independent stacks (device-resident traces).
+ *
+ * One two-stage stack is an HBM-bound pass (the group sums: every trace sample read once) followed by a tail of short,
+ * latency-bound kernels (transforms of the Kmax group sums, phase stack, inverse) that leave HBM idle.  A single stack
+ * cannot overlap the two -- the tail needs all group sums -- but a stream of stacks (one per station pair / component /
+ * resample, the way src/ts_pws1f.c is run over a data set) can: all group-sum passes go back to back on one stream and
+ * the tails follow on a second, higher-priority stream, `depth` plans serving as buffers:
+ *
+ *     H:  sums(0) sums(1) sums(2) sums(3) ...
+ *     T:          tail(0) tail(1) tail(2) ...
+ *
+ * The sums are one direct launch (their input pointer changes from stack to stack); the tail is replayed as a CUDA
+ * graph that writes the two stacks into buffers of the pipe, copied to the caller's pointers right behind it (2 x N
+ * floats, device to device) -- so no graph is ever re-captured because a pointer changed.  Results of stack i are
+ * complete after tspws_b200_pipe_sync (or once the tail stream passes the submit, for callers that order their own
+ * work after tspws_b200_pipe_stream(p, 1)).
+ * Every stack is computed exactly as tspws_b200_plan_stack computes it (same kernels, same order within the stack).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <cuda_runtime.h>
+#include "tspws_b200.h"
+#include "tspws_internal.h"
+
+struct tspws_pipe {
+    int depth, nograph;
+    tspws_plan_t **pl;
+    cudaStream_t H, T;
+    cudaEvent_t *red, *fin;
+    cudaGraphExec_t *g_fin;
+    unsigned long *k_fin;                  /* kernels per replay (launch accounting) */
+    float **out;                           /* [depth] device buffers [2][N]: ls | tsPWS of the plan's last stack */
+    size_t N;
+    unsigned long long n;
+};
+
+void tspws_b200_pipe_destroy(tspws_pipe_t *pp)
+{
+    if (!pp) return;
+    if (pp->H) cudaStreamSynchronize(pp->H);
+    if (pp->T) cudaStreamSynchronize(pp->T);
+    for (int k = 0; k < pp->depth; k++) {
+        if (pp->g_fin && pp->g_fin[k]) cudaGraphExecDestroy(pp->g_fin[k]);
+        if (pp->red && pp->red[k]) cudaEventDestroy(pp->red[k]);
+        if (pp->fin && pp->fin[k]) cudaEventDestroy(pp->fin[k]);
+        if (pp->pl && pp->pl[k]) tspws_b200_plan_destroy(pp->pl[k]);
+        if (pp->out && pp->out[k]) cudaFree(pp->out[k]);
+    }
+    if (pp->H) cudaStreamDestroy(pp->H);
+    if (pp->T) cudaStreamDestroy(pp->T);
+    free(pp->pl); free(pp->red); free(pp->fin); free(pp->g_fin); free(pp->k_fin); free(pp->out);
+    free(pp);
+}
+
+tspws_pipe_t *tspws_b200_pipe_create(const t_tsPWS *p, int max, unsigned int mtr_local, unsigned int mtr_total,
+                                     unsigned int trace_offset, int depth)
+{
+    if (!p || depth < 1 || depth > 8) return NULL;
+    tspws_pipe_t *pp = (tspws_pipe_t *)calloc(1, sizeof *pp);
+    if (!pp) return NULL;
+    pp->depth = depth;
+    { const char *e = getenv("TSPWS_NO_GRAPH"); pp->nograph = e && atoi(e); }
+    pp->pl = calloc(depth, sizeof *pp->pl); pp->red = calloc(depth, sizeof *pp->red); pp->fin = calloc(depth, sizeof *pp->fin);
+    pp->g_fin = calloc(depth, sizeof *pp->g_fin); pp->k_fin = calloc(depth, sizeof *pp->k_fin);
+    pp->out = calloc(depth, sizeof *pp->out);
+    pp->N = (size_t)max;
+    if (!pp->pl || !pp->red || !pp->fin || !pp->g_fin || !pp->k_fin || !pp->out) goto fail;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&pp->H, cudaStreamNonBlocking, lo) != cudaSuccess) goto fail;
+    if (cudaStreamCreateWithPriority(&pp->T, cudaStreamNonBlocking, hi) != cudaSuccess) goto fail;
+    for (int k = 0; k < depth; k++) {
+        /* 2 group-sum CTAs per SM: measured on the headline stack, depth 3: 114.8 us per stack with 296 CTAs, 122.5
+         * with 370, 121.7 with 222, no overlap at all (148-152 us) with 444 or 592 -- the tail needs room beside them */
+        tspws_plan_set_cs2_hint(148 * 2);
+        pp->pl[k] = tspws_b200_plan_create(p, max, mtr_local, mtr_total, trace_offset);
+        tspws_plan_set_cs2_hint(0);
+        if (!pp->pl[k]) goto fail;
+        if (cudaMalloc((void **)&pp->out[k], 2 * pp->N * sizeof(float)) != cudaSuccess) goto fail;
+        if (cudaEventCreateWithFlags(&pp->red[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
+        if (cudaEventCreateWithFlags(&pp->fin[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
+    }
+    return pp;
+fail:
+    tspws_b200_pipe_destroy(pp);
+    return NULL;
+}
+
+/* the tail of plan k's stack on stream s: replayed graph (captured on first use) writing into pp->out[k] */
+static int tail(tspws_pipe_t *pp, int k, cudaStream_t s)
+{
+    float *ls = pp->out[k], *ts = pp->out[k] + pp->N;
+    if (pp->nograph || tspws_cu_profile_enabled()) return tspws_b200_plan_finish(pp->pl[k], ls, ts, s);
+    if (!pp->g_fin[k]) {
+        cudaGraph_t g = NULL;
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); pp->nograph = 1; return tail(pp, k, s); }
+        const unsigned long n0 = tspws_cu_launch_count();
+        const int e = tspws_b200_plan_finish(pp->pl[k], ls, ts, s);
+        const cudaError_t ce = cudaStreamEndCapture(s, &g);
+        pp->k_fin[k] = tspws_cu_launch_count() - n0;
+        tspws_cu_launch_count_add(0ul - pp->k_fin[k]);              /* nothing has run yet */
+        if (e || ce != cudaSuccess || !g || cudaGraphInstantiate(&pp->g_fin[k], g, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (g) cudaGraphDestroy(g);
+            pp->g_fin[k] = NULL;
+            return e ? e : TSPWS_ERR_CUDA;
+        }
+        cudaGraphDestroy(g);
+    }
+    if (cudaGraphLaunch(pp->g_fin[k], s) != cudaSuccess) { cudaGetLastError(); return TSPWS_ERR_CUDA; }
+    tspws_cu_launch_count_add(pp->k_fin[k]);
+    return 0;
+}
+
+int tspws_b200_pipe_submit(tspws_pipe_t *pp, float *d_sigall, float *d_ls, float *d_tspws)
+{
+    if (!pp || !d_sigall || !d_ls || !d_tspws) return TSPWS_ERR_NULL;
+    const int k = (int)(pp->n % (unsigned long long)pp->depth);
+    int e;
+    /* the plan's buffers are free again once the tail of the stack that used them last has run */
+    if (pp->n >= (unsigned long long)pp->depth && cudaStreamWaitEvent(pp->H, pp->fin[k], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if ((e = tspws_b200_plan_reduce(pp->pl[k], d_sigall, pp->H))) return e;
+    if (cudaEventRecord(pp->red[k], pp->H) != cudaSuccess || cudaStreamWaitEvent(pp->T, pp->red[k], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if ((e = tail(pp, k, pp->T))) return e;
+    if (cudaMemcpyAsync(d_ls, pp->out[k], pp->N * sizeof(float), cudaMemcpyDeviceToDevice, pp->T) != cudaSuccess ||
+        cudaMemcpyAsync(d_tspws, pp->out[k] + pp->N, pp->N * sizeof(float), cudaMemcpyDeviceToDevice, pp->T) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (cudaEventRecord(pp->fin[k], pp->T) != cudaSuccess) return TSPWS_ERR_CUDA;
+    pp->n++;
+    return 0;
+}
+
+int tspws_b200_pipe_sync(tspws_pipe_t *pp)
+{
+    if (!pp) return TSPWS_ERR_NULL;
+    if (cudaStreamSynchronize(pp->H) != cudaSuccess || cudaStreamSynchronize(pp->T) != cudaSuccess) return TSPWS_ERR_CUDA;
+    return 0;
+}
+
+void *tspws_b200_pipe_stream(tspws_pipe_t *pp, int which) { return pp ? (void *)(which ? pp->T : pp->H) : NULL; }
+tspws_plan_t *tspws_b200_pipe_plan(tspws_pipe_t *pp, int k) { return (pp && k >= 0 && k < pp->depth) ? pp->pl[k] : NULL; }

@@ -93,6 +93,10 @@ struct tspws_plan {
     fprintf(stderr, "tspws_b200: CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); \
     goto fail; } } while (0)
 
+/* CTA count of the group-sum kernel for plans created by this thread (0: default); see tspws_pipe.c */
+static __thread int g_cs2_ctas_hint = 0;
+void tspws_plan_set_cs2_hint(int ctas) { g_cs2_ctas_hint = ctas; }
+
 static long env_long(const char *name, long dflt)
 {
     const char *v = getenv(name);
@@ -533,10 +537,15 @@ static int twostage_build(tspws_plan_t *pl)
         if (bad) goto done;
     }
 
-    /* ---- single-wave variant: ntiles x nparts CTAs = 148 SMs x 4 resident CTAs, equal rows per part ---- */
+    /* ---- single-wave variant: ntiles x nparts CTAs, all resident at once, equal rows per part ---- */
     pl->cs2 = 0;
     if (pl->N % 4 == 0 && n > 0 && !env_long("TSPWS_NO_CS2", 0)) {
-        int nparts = (int)(env_long("TSPWS_CS2_CTAS", 148 * 4) / ntiles);
+        /* CTAs of the group-sum kernel.  3 per SM by default (measured on the headline stack: 139.8 us against 143.8 with
+         * 4 and 141.3 with 2: enough loads in flight either way, less drain at the end); 2 per SM when the plan is a
+         * buffer of a stack pipeline (tspws_pipe.c: leaves half the register file to the tail of the previous stack).
+         * Handing the parts out through a queue (atomic per chunk, 592-2368 chunks) was tried for the pipeline: 147-160 us
+         * per single stack, no better overlap -- static parts stay. */
+        int nparts = (int)(env_long("TSPWS_CS2_CTAS", g_cs2_ctas_hint > 0 ? g_cs2_ctas_hint : 148 * 3) / ntiles);
         if (nparts > (int)((n + 3) / 4)) nparts = (int)((n + 3) / 4);
         if (nparts < 1) nparts = 1;
         int *pr = (int *)calloc((size_t)nparts * 4, sizeof(int));
