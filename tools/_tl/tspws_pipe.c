@@ -5,7 +5,7 @@
  * latency-bound kernels (transforms of the Kmax group sums, phase stack, inverse) that leave HBM idle.  A single stack
  * cannot overlap the two -- the tail needs all group sums -- but a stream of stacks (one per station pair / component /
  * resample, the way src/ts_pws1f.c is run over a data set) can: all group-sum passes go back to back on one stream and
- * the tails follow on a second, higher-priority stream, `depth` plans serving as buffers:
+ * the tails follow on a second, lower-priority stream, `depth` plans serving as buffers:
  *
  *     H:  sums(0) sums(1) sums(2) sums(3) ...
  *     T:          tail(0) tail(1) tail(2) ...
@@ -27,7 +27,8 @@
 struct tspws_pipe {
     int depth, nograph;
     tspws_plan_t **pl;
-    cudaStream_t H, T;
+    cudaStream_t H, T, T2;                 /* tails alternate over T and T2 when ntail == 2 */
+    int ntail;
     cudaEvent_t *red, *fin;
     cudaGraphExec_t *g_fin;
     unsigned long *k_fin;                  /* kernels per replay (launch accounting) */
@@ -41,6 +42,7 @@ void tspws_b200_pipe_destroy(tspws_pipe_t *pp)
     if (!pp) return;
     if (pp->H) cudaStreamSynchronize(pp->H);
     if (pp->T) cudaStreamSynchronize(pp->T);
+    if (pp->T2) cudaStreamSynchronize(pp->T2);
     for (int k = 0; k < pp->depth; k++) {
         if (pp->g_fin && pp->g_fin[k]) cudaGraphExecDestroy(pp->g_fin[k]);
         if (pp->red && pp->red[k]) cudaEventDestroy(pp->red[k]);
@@ -50,6 +52,7 @@ void tspws_b200_pipe_destroy(tspws_pipe_t *pp)
     }
     if (pp->H) cudaStreamDestroy(pp->H);
     if (pp->T) cudaStreamDestroy(pp->T);
+    if (pp->T2) cudaStreamDestroy(pp->T2);
     free(pp->pl); free(pp->red); free(pp->fin); free(pp->g_fin); free(pp->k_fin); free(pp->out);
     free(pp);
 }
@@ -69,16 +72,18 @@ tspws_pipe_t *tspws_b200_pipe_create(const t_tsPWS *p, int max, unsigned int mtr
     if (!pp->pl || !pp->red || !pp->fin || !pp->g_fin || !pp->k_fin || !pp->out) goto fail;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    /* Tails at the higher priority.  Measured on the headline stack with the per-CTA timeline (tools/pipe_timeline.py,
-     * 8192 x 16384, depth 4): tails high 118 us per stack; equal priorities 118-126; sums high 161 (the next group-sum
-     * kernel then starts only after the whole tail: fully serial); two alternating tail streams 125-130.  What is left
-     * on the table: at every group-sum boundary the ~3400 queued CTAs of the transform kernel take the freed slots and
-     * the next group-sum kernel waits ~25 us for that backlog to drain (HBM idle meanwhile).  TSPWS_PIPE_PRIO=sums|equal. */
+    /* The SUMS get the higher priority: HBM is the resource that bounds the pipeline, so the next group-sum kernel must
+     * take the slots its predecessor frees at once, and the tails fill what is left.  (The other way round -- measured
+     * with the per-CTA timeline, tools/pipe_timeline.py -- the 3400 queued CTAs of the transform kernel starve the sums
+     * for 24 us per stack: 126 us per stack instead of ~100.)  TSPWS_PIPE_PRIO=tail restores that order. */
     { const char *e = getenv("TSPWS_PIPE_PRIO");
-      if (e && !strcmp(e, "sums")) { const int t = lo; lo = hi; hi = t; }
-      if (e && !strcmp(e, "equal")) hi = lo; }
-    if (cudaStreamCreateWithPriority(&pp->H, cudaStreamNonBlocking, lo) != cudaSuccess) goto fail;
-    if (cudaStreamCreateWithPriority(&pp->T, cudaStreamNonBlocking, hi) != cudaSuccess) goto fail;
+      if (e && !strcmp(e, "tail")) { const int t = lo; lo = hi; hi = t; }
+      if (e && !strcmp(e, "equal")) hi = lo;
+      if (e && !strcmp(e, "equalhi")) lo = hi; }
+    if (cudaStreamCreateWithPriority(&pp->H, cudaStreamNonBlocking, hi) != cudaSuccess) goto fail;
+    if (cudaStreamCreateWithPriority(&pp->T, cudaStreamNonBlocking, lo) != cudaSuccess) goto fail;
+    if (cudaStreamCreateWithPriority(&pp->T2, cudaStreamNonBlocking, lo) != cudaSuccess) goto fail;
+    { const char *e = getenv("TSPWS_PIPE_TAILS"); pp->ntail = e && atoi(e) == 2 ? 2 : 1; }
     for (int k = 0; k < depth; k++) {
         /* 2 group-sum CTAs per SM: measured on the headline stack, depth 3: 114.8 us per stack with 296 CTAs, 122.5
          * with 370, 121.7 with 222, no overlap at all (148-152 us) with 444 or 592 -- the tail needs room beside them */
@@ -130,7 +135,7 @@ int tspws_b200_pipe_submit(tspws_pipe_t *pp, float *d_sigall, float *d_ls, float
     /* the plan's buffers are free again once the tail of the stack that used them last has run */
     if (pp->n >= (unsigned long long)pp->depth && cudaStreamWaitEvent(pp->H, pp->fin[k], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
     if ((e = tspws_b200_plan_reduce(pp->pl[k], d_sigall, pp->H))) return e;
-    cudaStream_t T = pp->T;
+    cudaStream_t T = (pp->ntail == 2 && (pp->n & 1)) ? pp->T2 : pp->T;
     if (cudaEventRecord(pp->red[k], pp->H) != cudaSuccess || cudaStreamWaitEvent(T, pp->red[k], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
     if ((e = tail(pp, k, T))) return e;
     if (cudaMemcpyAsync(d_ls, pp->out[k], pp->N * sizeof(float), cudaMemcpyDeviceToDevice, T) != cudaSuccess ||
@@ -143,7 +148,8 @@ int tspws_b200_pipe_submit(tspws_pipe_t *pp, float *d_sigall, float *d_ls, float
 int tspws_b200_pipe_sync(tspws_pipe_t *pp)
 {
     if (!pp) return TSPWS_ERR_NULL;
-    if (cudaStreamSynchronize(pp->H) != cudaSuccess || cudaStreamSynchronize(pp->T) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (cudaStreamSynchronize(pp->H) != cudaSuccess || cudaStreamSynchronize(pp->T) != cudaSuccess ||
+        cudaStreamSynchronize(pp->T2) != cudaSuccess) return TSPWS_ERR_CUDA;
     return 0;
 }
 

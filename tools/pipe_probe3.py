@@ -5,7 +5,7 @@ import torch, importlib.util
 _root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _spec = importlib.util.spec_from_file_location("ts_pws_b200", os.path.join(_root, "ts-pws_b200", "__init__.py"))
 B = importlib.util.module_from_spec(_spec); sys.modules["ts_pws_b200"] = B; _spec.loader.exec_module(B)
-lib = B.load_library()
+lib = B.load_library(os.environ.get('TSPWS_LIB') or None)
 mtr, n = 8192, 16384
 def run(depth, reps=int(os.environ.get('REPS', '60')), **kw):
     p = B.default_params(**kw)
@@ -30,9 +30,12 @@ def run(depth, reps=int(os.environ.get('REPS', '60')), **kw):
         host = (time.perf_counter() - t0) / reps
         end.record(T)
         lib.tspws_b200_pipe_sync(pipe); torch.cuda.synchronize()
-        ts.append(start.elapsed_time(end) / reps)
+        wall = (time.perf_counter() - t0) / reps * 1e3
+        ts.append(max(start.elapsed_time(end) / reps, wall if os.environ.get('TSPWS_PIPE_TAILS') == '2' else 0.0))
     best = min(ts)
     print(f"pipe depth {depth}: best {best*1e3:.1f} median {sorted(ts)[2]*1e3:.1f} us per stack, {mtr*n*4/best/1e6:.0f} GB/s  (host issue {host*1e6:.1f} us per stack)", flush=True)
     lib.tspws_b200_pipe_destroy(pipe)
+kw = dict(Kmax=10, unbiased=1, lrm=1)
+if os.environ.get('MEXHAT'): kw['type'] = -3
 for d in [int(v) for v in os.environ.get('DEPTHS', '1,2,3,4').split(',')]:
-    run(d, Kmax=10, unbiased=1, lrm=1)
+    run(d, **kw)
