@@ -552,6 +552,12 @@ def peer_err_check(lib, ps):
     return ps.peer and any(lib.tspws_b200_plan_peer_error(lib.tspws_b200_pipe_plan(ps.pipe, k)) for k in range(ps.depth))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of colsum2_kernel at 8192 x 16384 (432 CTAs), from the committed
+# ncu --set full capture profiles/r02_colsum2_ncu_raw.csv -- not measured inside a bench run (ncu replays kernels)
+COLSUM2_TRAFFIC = (538.475e6, "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed "
+                   "ncu --set full capture of this kernel at this shape (profiles/r01_colsum2_ncu_raw.csv: 536.76 MB + 1.71 MB)")
+
+
 def whole_step_frac(mtr, n, ms_step, hbm_peak):
     return (4.0 * mtr * n / (ms_step * 1e-3) / 1e9) / hbm_peak
 
@@ -686,7 +692,10 @@ def run_stack(args, wl, name):
                          "input_buffers": 2, "exchange": ("peer memory over NVLink" if ps.peer else "none")}
             if peer_err_check(lib, ps):
                 raise SystemExit(f"rank {rank}: a peer wait timed out in the pipelined leg -- the measurement is invalid")
-            ms_step, launches = ms_pipe, pipe_launches
+            if ms_pipe < ms_step:                          # `value` is the better of the two ways to run K stacks
+                ms_step, launches = ms_pipe, pipe_launches
+            else:
+                pipelined["note"] = "not faster than one stack at a time here: value / ms_per_step are the single-stack figures"
             del d_x2
         ps.close()
 
@@ -798,12 +807,10 @@ def run_stack(args, wl, name):
         kname = "colsum2_kernel" if "colsum2_kernel" in prof else "colsum_kernel"
         kcnt, kms = prof.get(kname, (0, 0.0))
         if kname == "colsum2_kernel" and (mtr, n) == (8192, 16384):
-            traffic = 538.475e6
-            traffic_src = ("NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the "
-                           "committed ncu --set full capture of this kernel at this shape, profiles/r01_colsum2_ncu_raw.csv "
-                           "(536.76 MB + 1.71 MB); the kernel is unchanged since")
+            traffic, traffic_src = COLSUM2_TRAFFIC
     else:
-        parts = {k: v for k, v in prof.items() if k.startswith("fwd2_acc_kernel") or k == "fwd_kernel" or k.startswith("fwd_mma")}
+        parts = {k: v for k, v in prof.items() if k.startswith("fwd2_acc_kernel") or k == "fwd_kernel" or k.startswith("fwd_dense_mma")
+                 or k in ("trace_image_kernel", "tile_sum_kernel", "dense_finish_kernel")}
         kname = "forward transform kernels"
         kcnt = max([v[0] for v in parts.values()] or [0])
         kms = sum(v[1] for v in parts.values())
@@ -815,7 +822,7 @@ def run_stack(args, wl, name):
                 "kernel_ms_back_to_back": k_alone_ms,
                 "traffic": traffic, "traffic_source": traffic_src,
                 "frac_whole_step": whole_step_frac(mtr, n, ms_step, hbm_peak),
-                "frac_whole_step_sustained": whole_step_frac(mtr, n, pipelined["ms_per_step_sustained"] if pipelined else ms_sustained, hbm_peak),
+                "frac_whole_step_sustained": whole_step_frac(mtr, n, min(pipelined["ms_per_step_sustained"], ms_sustained) if pipelined else ms_sustained, hbm_peak),
                 "frac_single_stack_step": whole_step_frac(mtr, n, ms_single, hbm_peak),
                 "kernels_ms_per_step": {k: v[1] / steps for k, v in prof.items() if v[0]}}
     roofline["whole_step_frac"] = roofline["frac_whole_step"]
@@ -857,11 +864,11 @@ def run_stack(args, wl, name):
                    "l2_note": "per-step input 512 MiB per GPU > 126 MB L2 (no flush needed)",
                    "ms_per_step_with_kernel_events": ms_prof,
                    "step": ("K independent stacks submitted to a 2-stream software pipeline (pipelined); ms_per_step = elapsed / K"
-                            if pipelined else "K stacks one after the other"),
+                            if pipelined and ms_step == pipelined["ms_per_step"] else "K stacks one after the other"),
                    "pipelined": pipelined,
                    "single_stack": {"ms_per_step": ms_single, "ms_per_step_sustained": ms_sustained, "sustained_steps": sus_steps,
                                     "note": "one stack at a time through tspws_b200_plan_stack (latency of a stack)"},
-                   "ms_per_step_sustained": pipelined["ms_per_step_sustained"] if pipelined else ms_sustained, "sustained_steps": sus_steps,
+                   "ms_per_step_sustained": min(pipelined["ms_per_step_sustained"], ms_sustained) if pipelined else ms_sustained, "sustained_steps": sus_steps,
                    "step_replayed_as_cuda_graph": bool(world == 1 or peer or st.graph is not None),
                    "exchange": ("none" if world == 1 else "peer memory over NVLink, fused into the stack's own kernels" if peer
                                 else "NCCL all-reduce")},
