@@ -288,10 +288,12 @@ unsigned int tspws_b200_plan_K(tspws_plan_t *plan);
 
 /* A stream of independent stacks of one geometry (what a data set run of src/ts_pws1f.c is: one stack per station
  * pair / component), software-pipelined on the GPU: the HBM-bound group sums of stack i+1 run while the latency-bound
- * tail (transforms of the group sums, phase stack, inverse) of stack i finishes.  `depth` plans (2-4) are the buffers.
+ * tail (transforms of the group sums, phase stack, inverse) of stack i finishes.  `depth` plans (3-4) are the buffers;
+ * depth = 1: no overlap, one stack at a time as tspws_b200_plan_stack runs it (the overlap does not pay for every
+ * frame: +17 % for the 44-scale Morlet headline, a loss for the Mexican hat -- DESIGN.md 4.1b; measure both).
  * submit enqueues one stack (device pointers; any device pointers, they may change from stack to stack) and
  * returns at once; sync waits for everything submitted.  Each stack is computed exactly as tspws_b200_plan_stack
- * computes it.  pipe_stream(p, 0 | 1): the cudaStream_t the sums | tails run on (to order or time work against).
+ * computes it.  pipe_stream(p, 0 | 1): the cudaStream_t the sums run on | the results arrive on (to order or time work against).
  * pipe_plan(p, k): plan k, k = (submit index) % depth, for tspws_b200_plan_get_stacks after a sync. */
 typedef struct tspws_pipe tspws_pipe_t;
 tspws_pipe_t *tspws_b200_pipe_create(const t_tsPWS *p, int max, unsigned int mtr_local, unsigned int mtr_total,

@@ -320,8 +320,9 @@ def test_full_size_single_stage_w6_vs_oracle(pkg, gpu_lib):
     assert O.nerr(ls, o_ls) <= TOL_STACK and O.nerr(ts, o_ts) <= TOL_STACK
 
 
-@pytest.mark.parametrize("kw,depth", [(dict(Kmax=10, unbiased=1, lrm=1), 3), (dict(Kmax=7), 2), (dict(), 2)],
-                         ids=["two_stage_unbiased_rm", "two_stage_biased", "single_stage"])
+@pytest.mark.parametrize("kw,depth", [(dict(Kmax=10, unbiased=1, lrm=1), 3), (dict(Kmax=7), 2), (dict(), 2),
+                                      (dict(Kmax=10, type=-3), 1), (dict(Kmax=10, type=-3), 4)],
+                         ids=["two_stage_unbiased_rm", "two_stage_biased", "single_stage", "mexhat_depth1", "mexhat_depth4"])
 def test_stack_pipeline_matches_one_stack_at_a_time(pkg, gpu_lib, kw, depth):
     """tspws_b200_pipe_*: 7 different stacks through a software pipeline of `depth` plans (sums of stack i+1 overlap
     the tail of stack i) -- every stack must equal the same stack through tspws_b200_plan_stack, and the oracle."""

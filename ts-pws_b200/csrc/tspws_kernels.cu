@@ -220,6 +220,30 @@ template <> struct cplx<double> { typedef double2 type; };
 __device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
 __device__ __forceinline__ float  ld_stream1(const float *p) { return __ldcs(p); }
 
+/* ---- programmatic dependent launch between the short kernels of the two-stage tail: a dependent kernel launched with
+ * LAUNCH_DEP may become resident as soon as every CTA of its predecessor in the stream has started (pdl_trigger) and
+ * waits in pdl_wait until the predecessor has completed and its writes are visible -- the launch gap and the CTA ramp
+ * of every link of the chain disappear under the predecessor's last wave.  Both instructions are no-ops in a kernel
+ * that was launched the ordinary way.  TSPWS_PDL=0 switches the launch attribute off. ---- */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static int pdl_on()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("TSPWS_PDL"); on = e ? atoi(e) != 0 : 1; }
+    return on;
+}
+#define LAUNCH_DEP(kernel, grid_, block_, smem_, stream_, ...)                                            \
+    do {                                                                                             \
+        cudaLaunchConfig_t c_ = {};                                                                  \
+        c_.gridDim = (grid_); c_.blockDim = (block_); c_.dynamicSmemBytes = (smem_); c_.stream = (stream_); \
+        cudaLaunchAttribute a_[1];                                                                   \
+        a_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                               \
+        a_[0].val.programmaticStreamSerializationAllowed = 1;                                        \
+        c_.attrs = a_; c_.numAttrs = pdl_on() ? 1 : 0;                                                \
+        cudaLaunchKernelEx(&c_, kernel, __VA_ARGS__);                                                \
+    } while (0)
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v)
 {
@@ -522,6 +546,8 @@ group_post2_kernel(const double *__restrict__ slots, const double *__restrict__ 
                    const tspws_peer_args pa, const double inv_n, const double inv_k)
 {
     tl_scope tls(1);
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ double s_c[];                      /* [K] group-mean corrections, then [K][world] presence bytes */
     __shared__ double s_m[GP2_LANES][32];
     unsigned char *s_pres = reinterpret_cast<unsigned char *>(s_c + K);
@@ -777,9 +803,8 @@ extern "C" int tspws_cu_group_post2(const double *d_slots, const double *d_slot_
     if (smem > 40 * 1024) return (int)cudaErrorInvalidValue;
     tspws_peer_args pa;
     memset(&pa, 0, sizeof pa);
-    group_post2_kernel<false><<<(N + 31) / 32, 32 * GP2_LANES, smem, (cudaStream_t)st>>>(d_slots, d_slot_tot, d_slot_off, N, K, ntile,
-                                                                                         mode, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean, pa,
-                                                                                         1.0 / (double)N, 1.0 / (double)K);
+    LAUNCH_DEP(group_post2_kernel<false>, dim3((N + 31) / 32), dim3(32 * GP2_LANES), smem, (cudaStream_t)st, d_slots, d_slot_tot, d_slot_off, N, K, ntile,
+               mode, do_rm, do_fold, split, d_gsum, d_gtile, d_out32, d_gmean, pa, 1.0 / (double)N, 1.0 / (double)K);
     TSPWS_LAUNCHED_N("group_post2_kernel", (cudaStream_t)st);
     return 0;
 }
@@ -1671,6 +1696,8 @@ fwd_tail_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restri
                 const tspws_tailfuse_t fz, const int g5)
 {
     tl_scope tls(2);
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(128) float fw_smem[];
     __shared__ double sh64[FW_WARPS][2 * F64_R];
     fwd_tail_cta(scales, g_all, items, nitems, x, N, ypart, ypart_len, smem_per_warp, ntr, long_L, long_row0, w64, items64,
@@ -1756,7 +1783,7 @@ extern "C" int tspws_cu_forward_tail(const tspws_devframe_t *f, const float *d_x
     fz.ps = (float2 *)d_ps; fz.st = (float2 *)d_st; fz.zout = (float2 *)d_zout; fz.ncoef = f->ncoef;
     int g5 = f->fw_lg_begin[5] / FW_WARPS;               /* first item group with D >= 32 items */
     { const char *e = getenv("TSPWS_TAIL_ORDER"); if (e && atoi(e) == 0) g5 = cpt; }   /* 0: fp64 CTAs first, then all groups */
-    fwd_tail_kernel<<<nf64 + ntr * cpt, FW_WARPS * 32, smem, s>>>(f->d_scale, (const float2 *)f->d_g32, f->d_items2, f->nitems2,
+    LAUNCH_DEP(fwd_tail_kernel, dim3(nf64 + ntr * cpt), dim3(FW_WARPS * 32), smem, s, f->d_scale, (const float2 *)f->d_g32, f->d_items2, f->nitems2,
         d_x, f->N, (float2 *)d_ypart, f->ypart_len, f->fw_smem_per_warp, ntr, long_row0 > 0 ? f->f64_maxl : 0x7fffffff, long_row0,
         (const double2 *)f->d_w64, f->d_items_short, f->nitems_short, nshort_cta, (const int2 *)f->d_long, nf64, d_x64,
         (double2 *)d_y64, f->ncoef, fz, g5);
@@ -1810,6 +1837,8 @@ phasor_combine_kernel(const int4 *__restrict__ tiles,
                       float2 *__restrict__ ps, float2 *__restrict__ st, float2 *__restrict__ zout)
 {
     tl_scope tls(3);
+    pdl_trigger();
+    pdl_wait();
     __shared__ float  s_p[4][PC_TILE][2];
     __shared__ double s_s[4][PC_TILE][2];
     /* tile = (offset in a trace's partial-Y block, offset in the coefficient arrays, valid
@@ -1946,7 +1975,7 @@ extern "C" int tspws_cu_phasor_combine(const tspws_devframe_t *f, const void *d_
     if (nseg <= 0 || f->S <= 0) return 0;
     if (f->ntile16 <= 0) return 0;
     dim3 grid(f->ntile16, nseg);
-    phasor_combine_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const int4 *)f->d_tile16, (const float2 *)d_ypart, f->ypart_len,
+    LAUNCH_DEP(phasor_combine_kernel, grid, dim3(256), 0, (cudaStream_t)st, (const int4 *)f->d_tile16, (const float2 *)d_ypart, f->ypart_len,
         f->ncoef, seg, d_rules, (const double2 *)d_ymean, (float2 *)d_ps, (float2 *)d_st, (float2 *)d_zout);
     TSPWS_LAUNCHED_N("phasor_combine_kernel", (cudaStream_t)st);
     return 0;
@@ -2521,6 +2550,8 @@ inv2_kernel(const tspws_scale_t *__restrict__ scales, const float2 *__restrict__
             int smem_per_warp /* bytes */, int qmax)
 {
     tl_scope tls(4);
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char iv_smem[];
     const int widx = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (widx >= nitems) return;
@@ -2615,6 +2646,7 @@ inv_finish_kernel(const float *__restrict__ scratch, int nslots, int nseg, int N
                   float *__restrict__ out_ts, float *__restrict__ out_ls)
 {
     tl_scope tls(6);
+    pdl_wait();
     /* 32 float4 columns x 8 slot lanes: thread (col, sl) adds slots sl, sl+8, ... of its 4 samples in
      * fp64, then the 8 lanes of a column are added in lane order -- 12 loads per thread at 44 scales */
     __shared__ double sh[8][8][33];
@@ -2704,9 +2736,9 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
             cudaFuncSetAttribute(inv2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * spw);
             cudaFuncSetAttribute(inv2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * spw);
         }
-        if (d_st) inv2_kernel<true><<<grid, 128, 4 * spw, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
+        if (d_st) LAUNCH_DEP(inv2_kernel<true>, grid, dim3(128), (size_t)(4 * spw), s, f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
                       f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg, spw, f->inv2_qmax);
-        else      inv2_kernel<false><<<grid, 128, 4 * spw, s>>>(f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
+        else      LAUNCH_DEP(inv2_kernel<false>, grid, dim3(128), (size_t)(4 * spw), s, f->d_scale, (const float2 *)f->d_gi32, (const int4 *)f->d_items_inv2, f->nitems_inv2,
                       f->N, f->ncoef, S, (const float4 *)d_zout, (float *)d_scratch, nseg, spw, f->inv2_qmax);
         TSPWS_LAUNCHED_N("inv2_kernel", s);
     }
@@ -2725,8 +2757,8 @@ extern "C" int tspws_cu_inverse(const tspws_devframe_t *f, const void *d_zout, c
     }
     {
         dim3 grid((f->N + 127) / 128, nseg);
-        if (d_st) inv_finish_kernel<true><<<grid, 256, 0, s>>>((const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
-        else      inv_finish_kernel<false><<<grid, 256, 0, s>>>((const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
+        if (d_st) LAUNCH_DEP(inv_finish_kernel<true>, grid, dim3(256), 0, s, (const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
+        else      LAUNCH_DEP(inv_finish_kernel<false>, grid, dim3(256), 0, s, (const float *)d_scratch, S, nseg, f->N, d_rules, d_out_ts, d_out_ls);
         TSPWS_LAUNCHED_N("inv_finish_kernel", s);
     }
     tl_host_dump(s);

@@ -16,6 +16,12 @@
  * complete after tspws_b200_pipe_sync (or once the tail stream passes the submit, for callers that order their own
  * work after tspws_b200_pipe_stream(p, 1)).
  * Every stack is computed exactly as tspws_b200_plan_stack computes it (same kernels, same order within the stack).
+ *
+ * Whether the overlap pays depends on the frame: the tail kernels slow down beside the streaming kernel (they lose L2
+ * and DRAM pages to it) and slow it down in turn.  Measured at 8192 x 16384: Morlet, 44 scales 141 -> 115-120 us per
+ * stack; Mexican hat, 20 scales (long inverse filters at the fine scales) 133 -> 192 us (inv2 / inv4 take 70-120 us
+ * instead of 10-16, colsum2 179 instead of 84).  depth = 1 runs one stack at a time in the plan_stack configuration
+ * through the same calls; bench.py times both and reports the better one.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -27,8 +33,8 @@
 struct tspws_pipe {
     int depth, nograph;
     tspws_plan_t **pl;
-    cudaStream_t H, T;
-    cudaEvent_t *red, *fin;
+    cudaStream_t H, T, C;                  /* sums, tails, result copies */
+    cudaEvent_t *red, *done, *fin;         /* sums done, tail done, results delivered (plan free again) */
     cudaGraphExec_t *g_fin;
     unsigned long *k_fin;                  /* kernels per replay (launch accounting) */
     float **out;                           /* [depth] device buffers [2][N]: ls | tsPWS of the plan's last stack */
@@ -41,16 +47,19 @@ void tspws_b200_pipe_destroy(tspws_pipe_t *pp)
     if (!pp) return;
     if (pp->H) cudaStreamSynchronize(pp->H);
     if (pp->T) cudaStreamSynchronize(pp->T);
+    if (pp->C) cudaStreamSynchronize(pp->C);
     for (int k = 0; k < pp->depth; k++) {
         if (pp->g_fin && pp->g_fin[k]) cudaGraphExecDestroy(pp->g_fin[k]);
         if (pp->red && pp->red[k]) cudaEventDestroy(pp->red[k]);
+        if (pp->done && pp->done[k]) cudaEventDestroy(pp->done[k]);
         if (pp->fin && pp->fin[k]) cudaEventDestroy(pp->fin[k]);
         if (pp->pl && pp->pl[k]) tspws_b200_plan_destroy(pp->pl[k]);
         if (pp->out && pp->out[k]) cudaFree(pp->out[k]);
     }
     if (pp->H) cudaStreamDestroy(pp->H);
     if (pp->T) cudaStreamDestroy(pp->T);
-    free(pp->pl); free(pp->red); free(pp->fin); free(pp->g_fin); free(pp->k_fin); free(pp->out);
+    if (pp->C) cudaStreamDestroy(pp->C);
+    free(pp->pl); free(pp->red); free(pp->done); free(pp->fin); free(pp->g_fin); free(pp->k_fin); free(pp->out);
     free(pp);
 }
 
@@ -62,11 +71,11 @@ tspws_pipe_t *tspws_b200_pipe_create(const t_tsPWS *p, int max, unsigned int mtr
     if (!pp) return NULL;
     pp->depth = depth;
     { const char *e = getenv("TSPWS_NO_GRAPH"); pp->nograph = e && atoi(e); }
-    pp->pl = calloc(depth, sizeof *pp->pl); pp->red = calloc(depth, sizeof *pp->red); pp->fin = calloc(depth, sizeof *pp->fin);
+    pp->pl = calloc(depth, sizeof *pp->pl); pp->red = calloc(depth, sizeof *pp->red); pp->done = calloc(depth, sizeof *pp->done); pp->fin = calloc(depth, sizeof *pp->fin);
     pp->g_fin = calloc(depth, sizeof *pp->g_fin); pp->k_fin = calloc(depth, sizeof *pp->k_fin);
     pp->out = calloc(depth, sizeof *pp->out);
     pp->N = (size_t)max;
-    if (!pp->pl || !pp->red || !pp->fin || !pp->g_fin || !pp->k_fin || !pp->out) goto fail;
+    if (!pp->pl || !pp->red || !pp->done || !pp->fin || !pp->g_fin || !pp->k_fin || !pp->out) goto fail;
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     /* Tails at the higher priority.  Measured on the headline stack with the per-CTA timeline (tools/pipe_timeline.py,
@@ -79,15 +88,17 @@ tspws_pipe_t *tspws_b200_pipe_create(const t_tsPWS *p, int max, unsigned int mtr
       if (e && !strcmp(e, "equal")) hi = lo; }
     if (cudaStreamCreateWithPriority(&pp->H, cudaStreamNonBlocking, lo) != cudaSuccess) goto fail;
     if (cudaStreamCreateWithPriority(&pp->T, cudaStreamNonBlocking, hi) != cudaSuccess) goto fail;
+    if (cudaStreamCreateWithPriority(&pp->C, cudaStreamNonBlocking, hi) != cudaSuccess) goto fail;
     for (int k = 0; k < depth; k++) {
         /* 2 group-sum CTAs per SM: measured on the headline stack, depth 3: 114.8 us per stack with 296 CTAs, 122.5
          * with 370, 121.7 with 222, no overlap at all (148-152 us) with 444 or 592 -- the tail needs room beside them */
-        tspws_plan_set_cs2_hint(148 * 2);
+        if (depth > 1) tspws_plan_set_cs2_hint(148 * 2);            /* depth 1: one stack at a time, the plan_stack configuration */
         pp->pl[k] = tspws_b200_plan_create(p, max, mtr_local, mtr_total, trace_offset);
         tspws_plan_set_cs2_hint(0);
         if (!pp->pl[k]) goto fail;
         if (cudaMalloc((void **)&pp->out[k], 2 * pp->N * sizeof(float)) != cudaSuccess) goto fail;
         if (cudaEventCreateWithFlags(&pp->red[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
+        if (cudaEventCreateWithFlags(&pp->done[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
         if (cudaEventCreateWithFlags(&pp->fin[k], cudaEventDisableTiming) != cudaSuccess) goto fail;
     }
     return pp;
@@ -130,12 +141,14 @@ int tspws_b200_pipe_submit(tspws_pipe_t *pp, float *d_sigall, float *d_ls, float
     /* the plan's buffers are free again once the tail of the stack that used them last has run */
     if (pp->n >= (unsigned long long)pp->depth && cudaStreamWaitEvent(pp->H, pp->fin[k], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
     if ((e = tspws_b200_plan_reduce(pp->pl[k], d_sigall, pp->H))) return e;
-    cudaStream_t T = pp->T;
+    cudaStream_t T = pp->depth > 1 ? pp->T : pp->H;                 /* depth 1: sums and tail in stream order, no overlap */
     if (cudaEventRecord(pp->red[k], pp->H) != cudaSuccess || cudaStreamWaitEvent(T, pp->red[k], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
     if ((e = tail(pp, k, T))) return e;
-    if (cudaMemcpyAsync(d_ls, pp->out[k], pp->N * sizeof(float), cudaMemcpyDeviceToDevice, T) != cudaSuccess ||
-        cudaMemcpyAsync(d_tspws, pp->out[k] + pp->N, pp->N * sizeof(float), cudaMemcpyDeviceToDevice, T) != cudaSuccess) return TSPWS_ERR_CUDA;
-    if (cudaEventRecord(pp->fin[k], T) != cudaSuccess) return TSPWS_ERR_CUDA;
+    /* the two result copies leave the tail stream (it is the critical path of the pipeline): they run on a third one */
+    if (cudaEventRecord(pp->done[k], T) != cudaSuccess || cudaStreamWaitEvent(pp->C, pp->done[k], 0) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (cudaMemcpyAsync(d_ls, pp->out[k], pp->N * sizeof(float), cudaMemcpyDeviceToDevice, pp->C) != cudaSuccess ||
+        cudaMemcpyAsync(d_tspws, pp->out[k] + pp->N, pp->N * sizeof(float), cudaMemcpyDeviceToDevice, pp->C) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (cudaEventRecord(pp->fin[k], pp->C) != cudaSuccess) return TSPWS_ERR_CUDA;
     pp->n++;
     return 0;
 }
@@ -143,9 +156,11 @@ int tspws_b200_pipe_submit(tspws_pipe_t *pp, float *d_sigall, float *d_ls, float
 int tspws_b200_pipe_sync(tspws_pipe_t *pp)
 {
     if (!pp) return TSPWS_ERR_NULL;
-    if (cudaStreamSynchronize(pp->H) != cudaSuccess || cudaStreamSynchronize(pp->T) != cudaSuccess) return TSPWS_ERR_CUDA;
+    if (cudaStreamSynchronize(pp->H) != cudaSuccess || cudaStreamSynchronize(pp->T) != cudaSuccess ||
+        cudaStreamSynchronize(pp->C) != cudaSuccess) return TSPWS_ERR_CUDA;
     return 0;
 }
 
-void *tspws_b200_pipe_stream(tspws_pipe_t *pp, int which) { return pp ? (void *)(which ? pp->T : pp->H) : NULL; }
+/* 0: the stream of the sums (work may be ordered BEFORE a submit through it); 1: the stream the results arrive on */
+void *tspws_b200_pipe_stream(tspws_pipe_t *pp, int which) { return pp ? (void *)(which ? pp->C : pp->H) : NULL; }
 tspws_plan_t *tspws_b200_pipe_plan(tspws_pipe_t *pp, int k) { return (pp && k >= 0 && k < pp->depth) ? pp->pl[k] : NULL; }
