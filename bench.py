@@ -315,7 +315,7 @@ class Ctx:
         import torch.distributed as dist
         self.torch, self.dist, self.args = torch, dist, args
         self.B = load_pkg()
-        self.lib = self.B.load_library()
+        self.lib = self.B.load_library(os.environ.get("TSPWS_LIB") or None)     # TSPWS_LIB: diagnostics builds (tools/pipe_timeline_mg.py)
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))

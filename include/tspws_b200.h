@@ -155,6 +155,12 @@ tspws_frame_t *tspws_b200_frame_create(int type, unsigned int J, unsigned int V,
                                        double s0, double b0, double w0, int uni);
 void tspws_b200_frame_destroy(tspws_frame_t *f);
 
+/* Geometry of the banded tensor-core transform of the middle octaves, host only: one record of 28 ints
+ * per octave = { tile_base, nj, ncols, rows_per_group, qmin, ngroups, nv, Pn, U, E, Ns, D, coef_rel[8], s_of[8] }
+ * (csrc/tspws_internal.h: tspws_band_t).  For the CPU tests, which rebuild the B tiles in numpy and compare the banded
+ * product with the oracle's analysis.  Returns the number of records. */
+int tspws_b200_band_layout(const tspws_frame_t *fr, long dense_D, long band_D, int *out, int max, int *s_first);
+
 /* Resampling plans (host, integer work).
  * tspws_b200_subsampling_plan: reference SubsamplingPlan (src/ts_pws1f_lib.c:355-383), uses rand().
  * tspws_b200_jackknife_plans : reference JackknifePlans  (src/ts_pws1f_lib.c:385-430). */

@@ -307,3 +307,75 @@ def test_frame_equals_the_compiled_reference_on_a_random_grid(pkg, lib):
             assert np.max(np.abs(d["w"] - wr)) <= 1e-13 * np.max(np.abs(wr)), (typ, J, V, N, s0, b0, w0, uni)
         finally:
             rf.close()
+
+
+@pytest.mark.parametrize("kw,N,dense_D,band_D", [
+    (dict(w0=6.0, w0set=4), 16384, 256, 16),      # BASELINE configs[1] frame: octaves D = 16 .. 128, 5 voices
+    (dict(), 16384, 256, 16),                     # default Morlet, 4 voices
+    (dict(type=-3), 16384, 256, 16),              # Mexican hat, 2 voices (real filters)
+    (dict(), 32768, 256, 32),                     # configs[3] length
+    (dict(w0=6.0, w0set=4), 4096, 128, 8),        # short traces: few row blocks, octaves dropped when the window would wrap
+], ids=["morlet_w6", "morlet_default", "mexhat", "n32768", "n4096"])
+def test_banded_gemm_geometry_reproduces_the_transform(pkg, lib, kw, N, dense_D, band_D):
+    """The banded tensor-core transform (csrc/tspws_mma.cu, fwd_dense_mma_kernel<true>) is an index rearrangement of
+    src/FWTa/wavelet_v7.c:43-64: coefficient m = U P + u of a voice is sum_q row[P E + q] . B_q[u] over 64-sample
+    row blocks.  This test takes the geometry from the C side (tspws_b200_band_layout = what the plan uploads),
+    rebuilds the B tiles exactly as band_w_image_kernel does, multiplies in numpy and compares every covered
+    coefficient with the oracle's analysis -- the layout logic is checked without a GPU."""
+    p = pkg.default_params(**kw)
+    assert lib.tspws_b200_derive_params(C.byref(p), N, 1.0) == 0
+    fr = lib.tspws_b200_frame_create(p.type, p.J, p.V, N, p.s0, p.b0, p.w0, p.uni)
+    assert fr
+    try:
+        rec = (C.c_int * (28 * 16))()
+        s_first = C.c_int(-1)
+        nb = lib.tspws_b200_band_layout(fr, dense_D, band_D, rec, 16, C.byref(s_first))
+    finally:
+        lib.tspws_b200_frame_destroy(fr)
+    assert nb >= 1
+    fo = O.frame_from_params(O.derive_params(O.Params(**kw), N, 1.0), N)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(N)
+    Y = O.analysis(fo, x)
+    off = fo.coef_off
+    rows = x.reshape(N // 64, 64)
+    kblocks = N // 64
+    covered = np.zeros(fo.ncoef, dtype=bool)
+    tiles = 0
+    for i in range(nb):
+        tile_base, nj, ncols, rpg, qmin, ngroups, nv, Pn, U, E, Ns, D = rec[28 * i:28 * i + 12]
+        coef_rel = rec[28 * i + 12:28 * i + 20]
+        s_of = rec[28 * i + 20:28 * i + 28]
+        assert tile_base == tiles and ncols % 16 == 0 and nv * Pn * U * 2 <= ncols <= 128 and nj <= kblocks
+        assert all(fo.D[s_of[v]] == D for v in range(nv)) and Ns == fo.Ns[s_of[0]]
+        tiles += nj
+        B = np.zeros((nj, ncols, 64))
+        for col in range(ncols):
+            t2 = col >> 1; u = t2 % U; t3 = t2 // U; pp = t3 % Pn; vi = t3 // Pn
+            if vi >= nv:
+                continue
+            s = s_of[vi]
+            w, L, c = fo.w[s], int(fo.L[s]), int(fo.center[s])
+            for jj in range(nj):
+                l = 64 * (jj + qmin - E * pp) + np.arange(64) - u * D + c
+                ok = (l >= 0) & (l < L)
+                v = (-w.imag if col & 1 else w.real)[np.clip(l, 0, L - 1)]
+                B[jj, col] = np.where(ok, v, 0.0)
+        for g in range(ngroups):
+            row0 = (g * rpg + qmin) % kblocks
+            acc = np.zeros(ncols)
+            for jj in range(nj):
+                acc += B[jj] @ rows[(row0 + jj) % kblocks]
+            for col in range(ncols):
+                t2 = col >> 1; u = t2 % U; t3 = t2 // U; pp = t3 % Pn; vi = t3 // Pn
+                m = (g * Pn + pp) * U + u
+                if vi < nv and m < Ns:
+                    ci = off[s_first.value] + coef_rel[vi] + m
+                    assert ci == off[s_of[vi]] + m
+                    ref = Y[ci].imag if col & 1 else Y[ci].real
+                    assert abs(acc[col] - ref) <= 1e-11 * (1 + np.abs(Y).max())
+                    if not (col & 1):
+                        covered[ci] = True
+    # every coefficient of the covered octaves is produced exactly once, nothing outside them
+    lo, hi = off[s_first.value], off[max(rec[20:20 + rec[6]]) + 1]                 # record 0 is the coarsest octave
+    assert covered[lo:hi].all() and not covered[:lo].any() and not covered[hi:].any()

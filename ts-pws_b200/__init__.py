@@ -120,6 +120,8 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_main_batch.argtypes = [C.POINTER(TsPWS), C.POINTER(TsPWSOut), C.POINTER(Data), C.c_uint]
     lib.tspws_b200_derive_params.restype = C.c_int
     lib.tspws_b200_derive_params.argtypes = [C.POINTER(TsPWS), C.c_uint, C.c_float]
+    lib.tspws_b200_band_layout.restype = C.c_int
+    lib.tspws_b200_band_layout.argtypes = [C.POINTER(Frame), C.c_long, C.c_long, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
     lib.tspws_b200_frame_create.restype = C.POINTER(Frame)
     lib.tspws_b200_frame_create.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint,
                                             C.c_double, C.c_double, C.c_double, C.c_int]
@@ -212,7 +214,7 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
 
 
 EXPORTS = [
-    "tspws_main", "tspws_b200_main_batch", "tspws_b200_derive_params", "tspws_b200_frame_create", "tspws_b200_frame_destroy",
+    "tspws_main", "tspws_b200_main_batch", "tspws_b200_derive_params", "tspws_b200_frame_create", "tspws_b200_frame_destroy", "tspws_b200_band_layout",
     "tspws_b200_subsampling_plan", "tspws_b200_jackknife_plans", "tspws_b200_get_coherence",
     "tspws_b200_get_stacks", "tspws_b200_set_selection", "tspws_b200_set_option",
     "tspws_b200_get_option", "tspws_b200_device_count", "tspws_b200_shutdown", "tspws_b200_version",

@@ -610,21 +610,20 @@ void tspws_b200_plan_destroy(tspws_plan_t *pl)
 
 static int floor_div(int a, int b) { int q = a / b; if ((a % b) && ((a < 0) != (b < 0))) q--; return q; }
 
-/* Middle octaves of a single-stage plan as banded GEMMs: walks down from the first dense scale, one descriptor per
- * run of scales with equal decimation D >= TSPWS_BAND_D (default 16 -- measured at 8192 x 16384, w0 = 6: 9.11 ms with 32,
- * 8.55 with 16, 8.66 with 8; 0 = off).  Updates td_* and dense_items. */
-static int band_plan(tspws_plan_t *pl, int N)
+/* Geometry of the banded GEMMs (host only, no GPU): walks down from scale s_dense (the first scale the dense GEMM
+ * covers), one descriptor per run of scales with equal decimation D >= band_D.  all_polyphase: every scale with
+ * D = 2^lg < 32 is on its polyphase list (the whole list is then skipped by the SIMT launch).  Returns the number of
+ * descriptors; *s_first = first scale covered, coef_rel relative to coef_off[*s_first]; *tiles / *groups = B tiles and
+ * CTA groups in total.  Exported for the CPU tests as tspws_b200_band_layout. */
+static int band_layout(const tspws_frame_t *fr, int N, int s_dense, long band_D, int all_polyphase,
+                       tspws_band_t *bands, int maxb, int *tiles_out, int *groups_out, int *s_first)
 {
-    const tspws_frame_t *fr = pl->fr;
-    const long bD = env_long("TSPWS_BAND_D", 16);
-    if (bD <= 0) return 0;
-    tspws_band_t bands[16];
-    int nb = 0, tiles = 0, groups = 0, sb = pl->dense_s0;
+    int nb = 0, tiles = 0, groups = 0, sb = s_dense;
     const int kblocks = N / 64;
-    while (sb > 0 && nb < 16) {
+    while (band_D > 0 && sb > 0 && nb < maxb) {
         const int D = (int)fr->D[sb - 1];
-        if (D < bD || D < 2 || (N % D)) break;
-        if (D < 32 && pl->dev.nitems_gen) break;         /* D = 2^lg < 32: its whole polyphase list is skipped, so every scale must be on it */
+        if (D < band_D || D < 2 || (N % D)) break;
+        if (D < 32 && !all_polyphase) break;
         if (D <= 64 ? (64 % D) : (D % 64)) break;
         int sa = sb - 1;
         while (sa > 0 && (int)fr->D[sa - 1] == D) sa--;
@@ -651,8 +650,38 @@ static int band_plan(tspws_plan_t *pl, int N)
         tiles += b->nj; groups += b->ngroups; nb++;
         sb = sa;
     }
-    if (!nb) return 0;
     const int ci0 = (int)fr->coef_off[sb];
+    for (int i = 0; i < nb; i++)
+        for (int v = 0; v < bands[i].nv; v++) bands[i].coef_rel[v] -= ci0;
+    if (tiles_out) *tiles_out = tiles;
+    if (groups_out) *groups_out = groups;
+    if (s_first) *s_first = sb;
+    return nb;
+}
+
+/* host-only view of the above for tests: descriptors as int[28] records; dense_D / band_D as the environment knobs */
+int tspws_b200_band_layout(const tspws_frame_t *fr, long dense_D, long band_D, int *out /* [max][28] */, int max, int *s_first)
+{
+    if (!fr || !out || max <= 0 || fr->N % 64) return TSPWS_ERR_ARG;
+    int s0 = -1;
+    for (unsigned int s = 0; s < fr->S; s++)
+        if ((long)fr->D[s] >= dense_D && fr->D[s] >= 32 && fr->D[s] <= fr->N) { s0 = (int)s; break; }
+    if (s0 < 0) return 0;
+    tspws_band_t bands[16];
+    const int nb = band_layout(fr, (int)fr->N, s0, band_D, 1, bands, max < 16 ? max : 16, NULL, NULL, s_first);
+    for (int i = 0; i < nb; i++) memcpy(out + 28 * i, &bands[i], sizeof(tspws_band_t));
+    return nb;
+}
+
+/* Middle octaves of a single-stage plan as banded GEMMs (TSPWS_BAND_D, default 16 -- measured at 8192 x 16384, w0 = 6:
+ * 9.11 ms with 32, 8.55 with 16, 8.66 with 8; 0 = off).  Updates td_* and dense_items. */
+static int band_plan(tspws_plan_t *pl, int N)
+{
+    const tspws_frame_t *fr = pl->fr;
+    tspws_band_t bands[16];
+    int tiles = 0, groups = 0, sb = pl->dense_s0;
+    const int nb = band_layout(fr, N, pl->dense_s0, env_long("TSPWS_BAND_D", 16), pl->dev.nitems_gen == 0, bands, 16, &tiles, &groups, &sb);
+    if (!nb) return 0;
     int items = 0;
     int lg_end = 5;
     for (unsigned int s = (unsigned int)sb; s < fr->S; s++) {
@@ -660,14 +689,12 @@ static int band_plan(tspws_plan_t *pl, int N)
         else { int lg = 0; while ((1u << lg) < fr->D[s]) lg++; if (lg < lg_end) lg_end = lg; }   /* whole list of D = 2^lg skipped */
     }
     pl->simt_lg_end = lg_end;
-    for (int i = 0; i < nb; i++)
-        for (int v = 0; v < bands[i].nv; v++) bands[i].coef_rel[v] -= ci0;
     if (cudaMalloc((void **)&pl->d_bands, nb * sizeof(tspws_band_t)) != cudaSuccess) return 1;
     if (cudaMemcpy(pl->d_bands, bands, nb * sizeof(tspws_band_t), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
     if (cudaMalloc(&pl->d_bimg, (size_t)tiles * 3 * 16384) != cudaSuccess) return 1;
     if (tspws_cu_band_wimage(&pl->dev, pl->d_bands, nb, tiles, pl->d_bimg, NULL)) return 1;
     pl->band_n = nb; pl->band_groups = groups;
-    pl->td_s0 = sb; pl->td_ci0 = ci0; pl->td_ncd = (int)(fr->ncoef - (size_t)ci0);
+    pl->td_s0 = sb; pl->td_ci0 = (int)fr->coef_off[sb]; pl->td_ncd = (int)(fr->ncoef - fr->coef_off[sb]);
     pl->dense_items = items;
     return 0;
 }
