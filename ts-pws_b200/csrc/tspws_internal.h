@@ -204,6 +204,10 @@ typedef struct {
     int coef_rel[TSPWS_BAND_MAXV];   /* coefficient offset of voice v relative to the first band coefficient */
     int s_of[TSPWS_BAND_MAXV];       /* scale index of voice v                                          */
 } tspws_band_t;
+int tspws_cu_forward_image(const float *d_x, int ntr, int N, void *d_ximg, float *d_tsum, float *d_sumtrace, tspws_stream_t st);
+int tspws_cu_forward_mma_all(const void *d_ximg, int ntr, int N, const void *d_wimg, int ncd_dense, const void *d_bimg,
+                             const tspws_band_t *d_bands, int nbands, int ngroups_total, float *d_part, int ld_part,
+                             int col0_dense, tspws_stream_t st);
 int tspws_cu_band_wimage(const tspws_devframe_t *f, const tspws_band_t *d_bands, int nbands, int ntiles, void *d_img, tspws_stream_t st);
 int tspws_cu_forward_band(const void *d_ximg, int ntr, int N, const void *d_bimg, const tspws_band_t *d_bands, int nbands,
                           int ngroups_total, float *d_part, int ld_part, tspws_stream_t st);

@@ -557,6 +557,179 @@ fwd_dense_mma_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat1
     if (warp == 2) m_tmem_dealloc(tmem, TMEM_COLS);
 }
 
+/* ---- persistent variant: ONE launch for all dense and banded jobs of a stack ------------------------------------
+ * One CTA per SM walks the job list j = blockIdx.x, + gridDim.x, ...; jobs are ordered M tile by M tile (the CTAs that
+ * run at the same time share their A tiles through L2), within an M tile the dense column tiles (256 row blocks each)
+ * come first, then the (octave, group) items of the banded GEMMs.  The three roles keep running counters of row blocks
+ * and chunks across jobs, so the smem ring and the two TMEM accumulators never drain between jobs: while the epilogue
+ * warps turn the last chunk of job i into phasors and column sums, the producer and the MMA thread are already two
+ * chunks into job i + 1.  (The one-job-per-CTA launches spent half of the band's time outside the tensor pipe.) */
+struct fd_job {
+    int mt, kblocks, row0, ncols, ob, grp, nt;
+    size_t wtile0;                      /* first B tile (3-term triple) of the job in its image */
+    bool band;
+};
+__device__ __forceinline__ fd_job fd_get_job(int j, int jobs_per_mt, int ndense, int kblocks_total, const tspws_band_t *__restrict__ bands)
+{
+    fd_job q;
+    q.mt = j / jobs_per_mt;
+    int r = j - q.mt * jobs_per_mt;
+    q.band = r >= ndense;
+    q.ob = 0; q.grp = 0; q.nt = 0;
+    if (!q.band) {
+        q.nt = r; q.kblocks = kblocks_total; q.row0 = 0; q.ncols = MMA_TILE_MN;
+        q.wtile0 = (size_t)r * kblocks_total;
+    } else {
+        r -= ndense;
+        while (r >= bands[q.ob].ngroups) { r -= bands[q.ob].ngroups; q.ob++; }
+        q.grp = r;
+        q.kblocks = bands[q.ob].nj; q.ncols = bands[q.ob].ncols; q.wtile0 = (size_t)bands[q.ob].tile_base;
+        q.row0 = (r * bands[q.ob].rows_per_group + bands[q.ob].qmin) % kblocks_total;
+        if (q.row0 < 0) q.row0 += kblocks_total;
+    }
+    return q;
+}
+
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+fwd_mma_persistent_kernel(const __nv_bfloat16 *__restrict__ x_img, const __nv_bfloat16 *__restrict__ w_img /* dense */,
+                          const __nv_bfloat16 *__restrict__ b_img /* band */, int kblocks_total, int ncol_dense, int ndense,
+                          int nband_groups, int mtiles, float *__restrict__ part /* [mtiles][ld_part] */, int ld_part, int col0_dense,
+                          int term_mask, const tspws_band_t *__restrict__ bands)
+{
+    extern __shared__ __align__(1024) unsigned char mma_smem[];
+    unsigned char *tiles = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(mma_smem) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full   = reinterpret_cast<uint64_t *>(tiles + (size_t)FD_STAGES * FD_STAGE_BYTES);
+    uint64_t *empty  = full + FD_STAGES;
+    uint64_t *tfull  = empty + FD_STAGES;
+    uint64_t *tempty = tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+    float (*colsum)[MMA_TILE_MN] = reinterpret_cast<float (*)[MMA_TILE_MN]>(tmem_slot + 4);     /* [4 warps][128 columns], its own 2 KiB */
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr unsigned TMEM_COLS = 2 * MMA_TILE_MN;
+    const int jobs_per_mt = ndense + nband_groups, njobs = jobs_per_mt * mtiles;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < FD_STAGES; s++) { m_mbar_init(full + s, 1); m_mbar_init(empty + s, 1); }
+        for (int s = 0; s < 2; s++) { m_mbar_init(tfull + s, 1); m_mbar_init(tempty + s, 4); }
+        m_fence_barrier_init();
+    } else if (warp == 2) {
+        m_tmem_alloc(tmem_slot, TMEM_COLS);
+    }
+    m_tc_fence_before();
+    __syncthreads();
+    m_tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        /* ---- producer ---- */
+        unsigned kc = 0;
+        for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
+            const fd_job q = fd_get_job(j, jobs_per_mt, ndense, kblocks_total, bands);
+            const __nv_bfloat16 *wsrc = q.band ? b_img : w_img;
+            const unsigned bbytes = q.band ? (unsigned)q.ncols * 128u : (unsigned)MMA_TILE_BYTES;
+            for (int kb = 0; kb < q.kblocks; kb++, kc++) {
+                const unsigned s = kc % FD_STAGES;
+                if (kc >= FD_STAGES) m_mbar_wait(empty + s, ((kc / FD_STAGES) & 1) ^ 1);
+                unsigned char *st = tiles + (size_t)s * FD_STAGE_BYTES;
+                m_mbar_expect_tx(full + s, FD_NT * MMA_TILE_BYTES + FD_NT * bbytes);
+                int ka = q.row0 + kb;
+                if (ka >= kblocks_total) ka -= kblocks_total;
+                m_bulk_g2s(st, x_img + ((size_t)q.mt * kblocks_total + ka) * FD_NT * (MMA_TILE_MN * MMA_TILE_K), FD_NT * MMA_TILE_BYTES, full + s);
+                for (int t = 0; t < FD_NT; t++)
+                    m_bulk_g2s(st + (FD_NT + t) * MMA_TILE_BYTES, wsrc + ((q.wtile0 + kb) * FD_NT + t) * (MMA_TILE_MN * MMA_TILE_K), bbytes, full + s);
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        /* ---- MMA issuer ---- */
+        unsigned kc = 0, cc = 0;
+        for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
+            const fd_job q = fd_get_job(j, jobs_per_mt, ndense, kblocks_total, bands);
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(q.ncols >> 3) << 17) | ((uint32_t)(MMA_TILE_MN >> 4) << 24);
+            const int nchunk = (q.kblocks + FD_CHUNK - 1) / FD_CHUNK;
+            for (int c = 0; c < nchunk; c++, cc++) {
+                const unsigned buf = cc & 1;
+                if (cc >= 2) { m_mbar_wait(tempty + buf, ((cc >> 1) & 1) ^ 1); m_tc_fence_after(); }
+                const uint32_t acc = tmem + buf * MMA_TILE_MN;
+                const int kb1 = min(q.kblocks, (c + 1) * FD_CHUNK);
+                for (int kb = c * FD_CHUNK; kb < kb1; kb++, kc++) {
+                    const unsigned s = kc % FD_STAGES;
+                    m_mbar_wait(full + s, (kc / FD_STAGES) & 1);
+                    m_tc_fence_after();
+                    const unsigned char *st = tiles + (size_t)s * FD_STAGE_BYTES;
+                    const unsigned char *a = st, *b = st + FD_NT * MMA_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < MMA_TILE_K / MMA_UMMA_K; k++) {
+                        const unsigned kby = k * MMA_UMMA_K * 2;
+                        bool first = (kb == c * FD_CHUNK) && k == 0;
+#define FD_MMA(I, J) do { if (term_mask & (1 << (I + J))) { m_umma_bf16(acc, m_smem_desc(a + (I) * MMA_TILE_BYTES, kby), m_smem_desc(b + (J) * MMA_TILE_BYTES, kby), idesc, !first); first = false; } } while (0)
+                        FD_MMA(2, 0); FD_MMA(0, 2); FD_MMA(1, 1); FD_MMA(1, 0); FD_MMA(0, 1); FD_MMA(0, 0);
+#undef FD_MMA
+                    }
+                    m_umma_commit(empty + s);
+                }
+                m_umma_commit(tfull + buf);
+            }
+        }
+    } else if (warp >= 2) {
+        /* ---- epilogue warps: thread = trace (TMEM lane) ---- */
+        const int q4 = warp & 3, e = threadIdx.x - 64;          /* e: 0..127 over the four epilogue warps */
+        unsigned cc = 0;
+        for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
+            const fd_job q = fd_get_job(j, jobs_per_mt, ndense, kblocks_total, bands);
+            const int nchunk = (q.kblocks + FD_CHUNK - 1) / FD_CHUNK;
+            float y[MMA_TILE_MN];
+#pragma unroll
+            for (int i = 0; i < MMA_TILE_MN; i++) y[i] = 0.f;
+            for (int c = 0; c < nchunk; c++, cc++) {
+                const unsigned buf = cc & 1;
+                m_mbar_wait(tfull + buf, (cc >> 1) & 1);
+                m_tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < MMA_TILE_MN; c0 += 32) {
+                    if (c0 >= q.ncols) break;
+                    uint32_t v[32];
+                    m_tmem_ld32(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * MMA_TILE_MN + c0), v);
+#pragma unroll
+                    for (int i = 0; i < 32; i++) y[c0 + i] += __uint_as_float(v[i]);
+                }
+                m_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(m_smem_u32(tempty + buf)) : "memory");
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < MMA_TILE_MN; c0 += 32) {
+                if (c0 >= q.ncols) break;
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) fd_phasor(y[c0 + i], y[c0 + i + 1], f[i], f[i + 1]);
+                fd_transpose_stage<16>(f, lane); fd_transpose_stage<8>(f, lane); fd_transpose_stage<4>(f, lane);
+                fd_transpose_stage<2>(f, lane);  fd_transpose_stage<1>(f, lane);
+                colsum[q4][c0 + lane] = f[0];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (e < q.ncols) {
+                const float sum = ((colsum[2][e] + colsum[3][e]) + colsum[0][e]) + colsum[1][e];
+                if (q.band) {
+                    const tspws_band_t *bd = bands + q.ob;
+                    const int t2 = e >> 1, U = bd->U, Pn = bd->Pn;
+                    const int u = t2 % U, t3 = t2 / U, pp = t3 % Pn, v = t3 / Pn;
+                    const int m = (q.grp * Pn + pp) * U + u;
+                    if (v < bd->nv && m < bd->Ns)
+                        part[(size_t)q.mt * ld_part + 2 * (bd->coef_rel[v] + m) + (e & 1)] = sum;
+                } else {
+                    const int col = q.nt * MMA_TILE_MN + e;
+                    if (col < ncol_dense) part[(size_t)q.mt * ld_part + col0_dense + col] = sum;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");       /* colsum is free for the next job */
+        }
+    }
+    m_tc_fence_before();
+    __syncthreads();
+    if (warp == 2) m_tmem_dealloc(tmem, TMEM_COLS);
+}
+
 /* traces x [ntr][N] fp32 -> A image [mtiles][kblocks][hi | lo], rows beyond ntr zero; and per M tile the column sums
  * of its traces (the linear stack of the coarse scales is the transform of the summed trace, by linearity) */
 __global__ void __launch_bounds__(256)
@@ -648,6 +821,48 @@ extern "C" int tspws_cu_forward_dense(const float *d_x, int ntr, int N, const vo
                                                                          nullptr);
     tspws_cu_profile_launched("fwd_dense_mma_kernel<dense>", st);
     tspws_cu_launch_count_add(3);
+    return (int)cudaGetLastError();
+}
+
+/* dense + banded jobs in one persistent launch (d_ximg built by tspws_cu_forward_image); nbands may be 0 */
+extern "C" int tspws_cu_forward_mma_all(const void *d_ximg, int ntr, int N, const void *d_wimg, int ncd_dense, const void *d_bimg,
+                                        const tspws_band_t *d_bands, int nbands, int ngroups_total, float *d_part, int ld_part,
+                                        int col0_dense, tspws_stream_t st)
+{
+    if (ntr <= 0) return 0;
+    if (N % MMA_TILE_K) return (int)cudaErrorInvalidValue;
+    const int mtiles = (ntr + MMA_TILE_MN - 1) / MMA_TILE_MN, ncol = 2 * ncd_dense;
+    const int ndense = (ncol + MMA_TILE_MN - 1) / MMA_TILE_MN;
+    if (nbands <= 0) ngroups_total = 0;
+    if (ndense + ngroups_total <= 0) return 0;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { cudaGetLastError(); sms = 148; } }
+    const size_t smem = (size_t)FD_STAGES * FD_STAGE_BYTES + 1024 + (2 * FD_STAGES + 4) * 8 + 16 + 4 * MMA_TILE_MN * sizeof(float) + 16;
+    cudaError_t e = cudaFuncSetAttribute(fwd_mma_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long njobs = (long long)(ndense + ngroups_total) * mtiles;
+    const int grid = (int)(njobs < sms ? njobs : sms);
+    fwd_mma_persistent_kernel<<<grid, MMA_THREADS, smem, (cudaStream_t)st>>>((const __nv_bfloat16 *)d_ximg, (const __nv_bfloat16 *)d_wimg,
+        (const __nv_bfloat16 *)d_bimg, N / MMA_TILE_K, ncol, ndense, ngroups_total, mtiles, d_part, ld_part, col0_dense,
+        getenv("TSPWS_DENSE_TERMS") ? atoi(getenv("TSPWS_DENSE_TERMS")) : 7, d_bands);
+    tspws_cu_profile_launched("fwd_mma_persistent_kernel", st);
+    tspws_cu_launch_count_add(1);
+    return (int)cudaGetLastError();
+}
+
+/* the trace image + summed trace alone (first half of tspws_cu_forward_dense) */
+extern "C" int tspws_cu_forward_image(const float *d_x, int ntr, int N, void *d_ximg, float *d_tsum, float *d_sumtrace, tspws_stream_t st)
+{
+    if (ntr <= 0) return 0;
+    if (N % MMA_TILE_K) return (int)cudaErrorInvalidValue;
+    cudaStream_t s = (cudaStream_t)st;
+    const int mtiles = (ntr + MMA_TILE_MN - 1) / MMA_TILE_MN, kblocks = N / MMA_TILE_K;
+    cudaFuncSetAttribute(trace_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_NT * MMA_TILE_BYTES);
+    trace_image_kernel<<<dim3(kblocks, mtiles), 256, FD_NT * MMA_TILE_BYTES, s>>>(d_x, ntr, N, kblocks, (__nv_bfloat16 *)d_ximg, d_tsum);
+    tspws_cu_profile_launched("trace_image_kernel", st);
+    tile_sum_kernel<<<(N + 255) / 256, 256, 0, s>>>(d_tsum, mtiles, N, d_sumtrace);
+    tspws_cu_profile_launched("tile_sum_kernel", st);
+    tspws_cu_launch_count_add(2);
     return (int)cudaGetLastError();
 }
 

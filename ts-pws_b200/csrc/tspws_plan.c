@@ -858,12 +858,19 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
     if (pl->acc64) {
         if ((e = tspws_cu_forward(&pl->dev, d_sigall, 0, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
     } else {
+        if (pl->dense_on && env_long("TSPWS_MMA_PERSIST", 1)) {
+            /* trace image, then every dense and banded job of the stack in one persistent launch */
+            if ((e = tspws_cu_forward_image(d_sigall, pl->ntr_fwd, pl->N, pl->d_ximg, pl->d_tsum, pl->d_sumtrace, stream))) return TSPWS_ERR_CUDA;
+            if ((e = tspws_cu_forward_mma_all(pl->d_ximg, pl->ntr_fwd, pl->N, pl->d_wimg, pl->dense_ncd, pl->d_bimg, pl->d_bands, pl->band_n,
+                                              pl->band_groups, pl->d_dpart, 2 * pl->td_ncd, 2 * (pl->dense_ci0 - pl->td_ci0), stream))) return TSPWS_ERR_CUDA;
+        } else {
         if (pl->dense_on &&
             (e = tspws_cu_forward_dense(d_sigall, pl->ntr_fwd, pl->N, pl->d_wimg, pl->dense_ncd, pl->d_ximg, pl->d_tsum, pl->d_sumtrace,
                                         pl->d_dpart, 2 * pl->td_ncd, 2 * (pl->dense_ci0 - pl->td_ci0), stream))) return TSPWS_ERR_CUDA;
         if (pl->band_n &&
             (e = tspws_cu_forward_band(pl->d_ximg, pl->ntr_fwd, pl->N, pl->d_bimg, pl->d_bands, pl->band_n, pl->band_groups,
                                        pl->d_dpart, 2 * pl->td_ncd, stream))) return TSPWS_ERR_CUDA;
+        }
         if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst,
                                        pl->dense_on ? pl->dense_items : 0, pl->dense_on ? pl->simt_lg_end : 5, stream))) return TSPWS_ERR_CUDA;
         if (pl->dense_on) {
