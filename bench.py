@@ -554,8 +554,8 @@ def peer_err_check(lib, ps):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of colsum2_kernel at 8192 x 16384 (432 CTAs), from the committed
 # ncu --set full capture profiles/r02_colsum2_ncu_raw.csv -- not measured inside a bench run (ncu replays kernels)
-COLSUM2_TRAFFIC = (538.475e6, "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed "
-                   "ncu --set full capture of this kernel at this shape (profiles/r01_colsum2_ncu_raw.csv: 536.76 MB + 1.71 MB)")
+COLSUM2_TRAFFIC = (537.754e6, "NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed "
+                   "ncu --set full capture of this kernel at this shape and grid (profiles/r02_colsum2_ncu_raw.csv: 536.76 MB + 0.99 MB)")
 
 
 def whole_step_frac(mtr, n, ms_step, hbm_peak):
@@ -949,9 +949,14 @@ def resample_leg(ctx, M, two_stage, cpu_M=0, rows=None):
         kw.update(Kmax=10, unbiased=1)
     lib.tspws_b200_set_selection(mysel.ctypes.data_as(C.c_char_p), Mloc, mtr)
     try:
-        B.call_tspws_main(lib, x, B.default_params(**dict(wl["params"], **({"Kmax": 10, "unbiased": 1} if two_stage else {}))))   # warm-up: plan, buffers
-        r = B.call_tspws_main(lib, x, B.default_params(**kw))
-        dt = r["seconds"]                               # the tspws_main call itself (outputs allocated and touched before)
+        # warm-up: the same call once (plan, device buffers, pinned result staging), then the better of two timed calls --
+        # the call is host-heavy (pageable H2D of 262 MB, scatter of 2 x M rows) and its time moves with the host's state
+        B.call_tspws_main(lib, x, B.default_params(**kw))
+        r, dt = None, None
+        for _ in range(2):
+            ri = B.call_tspws_main(lib, x, B.default_params(**kw))
+            if dt is None or ri["seconds"] < dt:
+                r, dt = ri, ri["seconds"]               # the tspws_main call itself (outputs allocated and touched before)
     finally:
         lib.tspws_b200_set_selection(None, 0, 0)
     assert r["rc"] == 0, r["rc"]

@@ -30,7 +30,7 @@ $T ncu --set full --import-source on --clock-control none --cache-control none \
     -k regex:"group_post2|fwd_tail|phasor_combine|inv2|inv4|inv_finish" --launch-skip 12 --launch-count 6 \
     -o "$OUT/${R}_tail_full" python tools/quick_bench.py ts > /dev/null 2>&1
 # the tcgen05 kernels of the single-stage forward transform (dense + banded GEMM)
-$T ncu --set full --import-source on --clock-control none -k regex:fwd_dense_mma --launch-skip 2 --launch-count 2 \
+$T ncu --set full --import-source on --clock-control none -k regex:"fwd_mma_persistent|fwd_dense_mma" --launch-skip 1 --launch-count 1 \
     -o "$OUT/${R}_fwd_band_mma" python tools/quick_bench.py c2 > /dev/null 2>&1
 
 if [ -n "${EXTRA_PROBES:-}" ]; then
