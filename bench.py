@@ -474,7 +474,7 @@ class PipedStacks:
     exchange of ShardedStack (one exchange region per plan)."""
 
     def __init__(self, ctx, params, n, mtr_local, mtr_total, offset, depth=4):
-        self.ctx, self.n, self.depth = ctx, n, depth
+        self.ctx, self.n, self.depth = ctx, n, (depth or 4)          # depth 0 = AUTO (the library measures both ways)
         B, lib, torch, dist = ctx.B, ctx.lib, ctx.torch, ctx.dist
         p = B.default_params(**params)
         lib.tspws_b200_derive_params(C.byref(p), n, 1.0)
@@ -484,7 +484,7 @@ class PipedStacks:
         self.peer = False
         if world > 1:
             ok = self.ok
-            for k in range(depth):
+            for k in range(self.depth):
                 plan = lib.tspws_b200_pipe_plan(self.pipe, k) if self.pipe else None
                 h = (C.c_ubyte * 64)()
                 ok = ok and lib.tspws_b200_plan_peer_export(plan, world, h) == 0
@@ -501,7 +501,7 @@ class PipedStacks:
         if self.ok:
             self.H = torch.cuda.ExternalStream(lib.tspws_b200_pipe_stream(self.pipe, 0))
             self.T = torch.cuda.ExternalStream(lib.tspws_b200_pipe_stream(self.pipe, 1))
-            self.outs = [(torch.empty(n, device="cuda"), torch.empty(n, device="cuda")) for _ in range(depth)]
+            self.outs = [(torch.empty(n, device="cuda"), torch.empty(n, device="cuda")) for _ in range(self.depth)]
             self.i = 0
 
     def submit(self, d_x):
@@ -904,13 +904,20 @@ def short_stack_leg(ctx, wlname, steps, hbm_peak, cpu_traces):
            "frac_whole_step": whole_step_frac(mtr, n, ms, hbm_peak),
            "kernels_ms_per_step": {k: v[1] / steps for k, v in prof.items() if v[0]}}
     if st.two_stage:
-        ps = PipedStacks(ctx, wl["params"], n, mtr, mtr, 0)
+        # the stream-of-stacks API in AUTO mode: it measures pipelined against one-at-a-time on its first 16 stacks
+        ps = PipedStacks(ctx, wl["params"], n, mtr, mtr, 0, depth=0)
         if ps.ok:
-            for _ in range(2 * ps.depth):
+            for _ in range(24):
                 ps.submit(d_x)
+            ps.sync()
+            ps.submit(d_x)
+            cal = (C.c_float * 2)()
+            mode = lib.tspws_b200_pipe_mode(ps.pipe, cal)
             msp = ps.timed([d_x], steps)
-            out["pipelined"] = {"stacks_in_flight": ps.depth, "ms_per_step": msp, "value": float(mtr) * n / (msp * 1e-3),
-                                "frac_whole_step": whole_step_frac(mtr, n, msp, hbm_peak)}
+            out["stream_of_stacks_auto"] = {"api": "tspws_b200_pipe_create(depth = 0)", "chosen": {0: "undecided", 1: "pipelined", 2: "one at a time"}.get(mode, mode),
+                                            "calibration_ms_per_stack": {"pipelined": cal[0], "one_at_a_time": cal[1]},
+                                            "ms_per_step": msp, "value": float(mtr) * n / (msp * 1e-3),
+                                            "frac_whole_step": whole_step_frac(mtr, n, msp, hbm_peak)}
         ps.close()
     if not st.two_stage:
         fr = lib.tspws_b200_frame_create(st.p.type, st.p.J, st.p.V, n, st.p.s0, st.p.b0, st.p.w0, st.p.uni)

@@ -296,7 +296,10 @@ unsigned int tspws_b200_plan_K(tspws_plan_t *plan);
  * pair / component), software-pipelined on the GPU: the HBM-bound group sums of stack i+1 run while the latency-bound
  * tail (transforms of the group sums, phase stack, inverse) of stack i finishes.  `depth` plans (3-4) are the buffers;
  * depth = 1: no overlap, one stack at a time as tspws_b200_plan_stack runs it (the overlap does not pay for every
- * frame: +17 % for the 44-scale Morlet headline, a loss for the Mexican hat -- DESIGN.md 4.1b; measure both).
+ * frame: +20 % for the 44-scale Morlet headline, a loss for the Mexican hat -- DESIGN.md 4.1b).
+ * depth = 0: AUTO (unsharded stacks only): the first 8 stacks run pipelined (4 plans), the next 8 one at a time, both
+ * timed on the device, and the faster way serves the rest; tspws_b200_pipe_mode tells which (0 = still measuring,
+ * 1 = pipelined, 2 = one at a time; ms[0], ms[1] = the two measurements in ms per stack).
  * submit enqueues one stack (device pointers; any device pointers, they may change from stack to stack) and
  * returns at once; sync waits for everything submitted.  Each stack is computed exactly as tspws_b200_plan_stack
  * computes it.  pipe_stream(p, 0 | 1): the cudaStream_t the sums run on | the results arrive on (to order or time work against).
@@ -308,6 +311,7 @@ int   tspws_b200_pipe_submit(tspws_pipe_t *pipe, float *d_sigall, float *d_ls, f
 int   tspws_b200_pipe_sync(tspws_pipe_t *pipe);
 void *tspws_b200_pipe_stream(tspws_pipe_t *pipe, int which);
 tspws_plan_t *tspws_b200_pipe_plan(tspws_pipe_t *pipe, int k);
+int   tspws_b200_pipe_mode(tspws_pipe_t *pipe, float *ms);
 void  tspws_b200_pipe_destroy(tspws_pipe_t *pipe);
 
 /* ------------------------------------------------------------------------- */

@@ -321,8 +321,8 @@ def test_full_size_single_stage_w6_vs_oracle(pkg, gpu_lib):
 
 
 @pytest.mark.parametrize("kw,depth", [(dict(Kmax=10, unbiased=1, lrm=1), 3), (dict(Kmax=7), 2), (dict(), 2),
-                                      (dict(Kmax=10, type=-3), 1), (dict(Kmax=10, type=-3), 4)],
-                         ids=["two_stage_unbiased_rm", "two_stage_biased", "single_stage", "mexhat_depth1", "mexhat_depth4"])
+                                      (dict(Kmax=10, type=-3), 1), (dict(Kmax=10, type=-3), 4), (dict(Kmax=10, unbiased=1), 0)],
+                         ids=["two_stage_unbiased_rm", "two_stage_biased", "single_stage", "mexhat_depth1", "mexhat_depth4", "auto"])
 def test_stack_pipeline_matches_one_stack_at_a_time(pkg, gpu_lib, kw, depth):
     """tspws_b200_pipe_*: 7 different stacks through a software pipeline of `depth` plans (sums of stack i+1 overlap
     the tail of stack i) -- every stack must equal the same stack through tspws_b200_plan_stack, and the oracle."""
@@ -338,10 +338,13 @@ def test_stack_pipeline_matches_one_stack_at_a_time(pkg, gpu_lib, kw, depth):
     try:
         dxs = [torch.from_numpy(x).cuda() for x in xs]
         outs = [(torch.empty(n, device="cuda"), torch.empty(n, device="cuda")) for _ in range(nst)]
-        for rep in range(2):                               # second round: replayed graphs with changed pointers
-            for j in range(nst):
+        for rep in range(2 if depth else 5):               # later rounds: replayed graphs with changed pointers; depth 0 (AUTO):
+            for j in range(nst):                           # 35 stacks take it through both measurement phases and the decision
                 assert lib.tspws_b200_pipe_submit(pipe, dxs[j].data_ptr(), outs[j][0].data_ptr(), outs[j][1].data_ptr()) == 0
             assert lib.tspws_b200_pipe_sync(pipe) == 0
+        ms = (C.c_float * 2)()
+        mode = lib.tspws_b200_pipe_mode(pipe, ms)
+        assert mode == (1 if depth > 1 else 2) if depth else (mode in (1, 2) and ms[0] > 0 and ms[1] > 0)
         for j in (0, 3, 6):
             ls, ts, _ = _plan_stack(pkg, lib, xs[j], **kw)
             assert O.nerr(outs[j][1].cpu().numpy(), ts) <= 1e-6 and O.nerr(outs[j][0].cpu().numpy(), ls) <= 1e-6

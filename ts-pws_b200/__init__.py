@@ -198,6 +198,8 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_pipe_stream.argtypes = [C.c_void_p, C.c_int]
     lib.tspws_b200_pipe_plan.restype = C.c_void_p
     lib.tspws_b200_pipe_plan.argtypes = [C.c_void_p, C.c_int]
+    lib.tspws_b200_pipe_mode.restype = C.c_int
+    lib.tspws_b200_pipe_mode.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     lib.tspws_b200_pipe_destroy.restype = None
     lib.tspws_b200_pipe_destroy.argtypes = [C.c_void_p]
     lib.tspws_b200_plan_stacks_ptr.restype = C.c_int
@@ -224,7 +226,7 @@ EXPORTS = [
     "tspws_b200_read_sac", "tspws_b200_free_data",
     "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_peer_export", "tspws_b200_plan_peer_import", "tspws_b200_plan_peer_region", "tspws_b200_plan_peer_import_ptrs", "tspws_b200_plan_peer_error", "tspws_b200_plan_peer_close", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
     "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",
-    "tspws_b200_pipe_create", "tspws_b200_pipe_submit", "tspws_b200_pipe_sync", "tspws_b200_pipe_stream", "tspws_b200_pipe_plan", "tspws_b200_pipe_destroy",
+    "tspws_b200_pipe_create", "tspws_b200_pipe_submit", "tspws_b200_pipe_sync", "tspws_b200_pipe_stream", "tspws_b200_pipe_plan", "tspws_b200_pipe_mode", "tspws_b200_pipe_destroy",
 ]
 
 
