@@ -138,15 +138,17 @@ def test_repeated_calls_and_plan_cache(pkg, gpu_lib):
 
 
 def test_writeback_option_mutates_input_like_reference(pkg, gpu_lib):
-    x = O.synthetic_traces(12, 600, seed=9)
-    ref = x.copy()
-    O.fold_inplace(ref)
-    O.remove_mean_inplace(ref)
     gpu_lib.tspws_b200_set_option(pkg.OPT_WRITEBACK, 1)
     try:
-        for kmax in (0, 4):
-            r = gpu_run(pkg, gpu_lib, x, lrm=1, fold=1, Kmax=kmax)
-            np.testing.assert_array_equal(r["sigall"], ref)    # bit-exact fp32 mutation
+        for n, fold in ((600, 1), (600, 0), (602, 0), (16384, 0)):     # rm alone, N % 4 == 0: the one-pass register kernel
+            x = O.synthetic_traces(12, n, seed=9) + np.float32(3.25)   # a DC offset worth removing
+            ref = x.copy()
+            if fold:
+                O.fold_inplace(ref)
+            O.remove_mean_inplace(ref)
+            for kmax in (0, 4):
+                r = gpu_run(pkg, gpu_lib, x, lrm=1, fold=fold, Kmax=kmax)
+                np.testing.assert_array_equal(r["sigall"], ref)    # bit-exact fp32 mutation
     finally:
         gpu_lib.tspws_b200_set_option(pkg.OPT_WRITEBACK, 0)
 
