@@ -3,7 +3,7 @@
  *
  * Kernel                       replaces (reference file:line)                            bound
  * ---------------------------  --------------------------------------------------------  ---------
- * prep_kernel                  fold src/ts_pws1f_lib.c:76-86, mean removal :160-168      HBM
+ * prep_kernel, prep_rm_kernel  fold src/ts_pws1f_lib.c:76-86, mean removal :160-168      HBM
  * colsum2_kernel (colsum_kernel when N % 4 != 0)
  *                              partial_linear_stacks src/ts_pws1f_lib.c:866-881          HBM (headline)
  * group_post2_kernel<PEER>     slot sums + mean removal / fold (:76-86, :160-168 applied
@@ -29,6 +29,12 @@
  *                              src/ts_pws1f_lib.c:501-831                                 HBM / L2
  * prefix_weight, simil, lsconv kernels
  *                              convergence curves src/ts_pws1f_lib.c:247-314, :433-462    L2
+ * peer_publish_f32 / peer_collect_f32 kernels
+ *                              single-stage PS | ST sums across the ranks of a node        NVLink
+ *
+ * The tcgen05 / TMEM kernels are in tspws_mma.cu: the octaves with D >= 16 of the single-stage forward transform
+ * (fwd_mma_persistent_kernel: dense and banded GEMMs) and the resampling contraction (resample_mma_kernel).
+ * The links of the two-stage tail are launched with programmatic dependent launch (LAUNCH_DEP / pdl_wait).
  *
  * Everything is written from the mathematics in SURVEY.md Appendix A.
  */

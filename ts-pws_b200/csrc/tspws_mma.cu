@@ -1,5 +1,9 @@
 /*
- * tspws_mma.cu -- the resampling contraction on the 5th-generation tensor cores (sm_100a only).
+ * tspws_mma.cu -- the tcgen05 / TMEM kernels (sm_100a only):
+ *   1. the resampling contraction (resample_mma_kernel), described right below;
+ *   2. the octaves with decimation D >= 16 of the single-stage forward transform as dense (D >= 256) and banded
+ *      (16 <= D < 256) GEMMs with a phasor epilogue -- second half of the file (fwd_dense_mma_kernel<BAND>,
+ *      fwd_mma_persistent_kernel, trace_image_kernel, w_image_kernel, band_w_image_kernel).
  *
  * Single-stage bootstrap / sub-sampling / jackknife (reference src/ts_pws1f_lib.c:528-565): for every
  * realisation m the phase stack is  PS_m[i] = sum_t c[m][t] * phasor_t[i]  with c the selection (0/1) or
