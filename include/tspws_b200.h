@@ -278,6 +278,14 @@ int tspws_b200_plan_peer_error(tspws_plan_t *plan);
 /* Teardown order (CUDA IPC rule: never free an exported allocation that another process still maps):
  * every rank calls plan_peer_close, the ranks synchronise (barrier), then every rank calls plan_destroy. */
 int tspws_b200_plan_peer_close(tspws_plan_t *plan);
+/* The reduce step of an fp32 single-stage plan in PARTS of the shard, for callers that are still copying the traces to
+ * the device: transform the part that has arrived while the next one is on the bus (tspws_main does exactly that).
+ * plan_part_align: parts start at multiples of this many traces and all but the last are a multiple of it long
+ * (0: the plan does not take parts -- two-stage or fp64 plans).  d_part = address of trace t0.  After the last part:
+ * plan_reduce_done, then the exchange (if any) and plan_finish as usual.  plan_reduce == one part + done. */
+unsigned int tspws_b200_plan_part_align(tspws_plan_t *plan);
+int tspws_b200_plan_reduce_part(tspws_plan_t *plan, float *d_part, unsigned int t0, unsigned int nt, void *stream);
+int tspws_b200_plan_reduce_done(tspws_plan_t *plan, void *stream);
 int tspws_b200_plan_finish(tspws_plan_t *plan, float *d_ls, float *d_tspws, void *stream);
 /* A+B on one GPU. */
 int tspws_b200_plan_stack(tspws_plan_t *plan, float *d_sigall, float *d_ls, float *d_tspws,

@@ -91,6 +91,54 @@ def _plan_stack(pkg, lib, x, mtr_total=None, offset=0, **params):
         lib.tspws_b200_plan_destroy(plan)
 
 
+@pytest.mark.parametrize("mtr,n,kw", [(700, 2048, dict(lrm=1)), (1280, 4096, dict(lrm=1, fold=1)), (2560, 4096, dict(w0=6.0, w0set=4))],
+                         ids=["simt_700", "tensor_core_1280", "tensor_core_2560_w6"])
+def test_single_stage_reduce_in_parts_equals_whole(pkg, gpu_lib, mtr, n, kw):
+    """tspws_b200_plan_reduce_part / _done (what tspws_main uses to transform the traces while they are still arriving):
+    any split into aligned parts gives bit-identical stacks to the one-call reduce, and both match the oracle."""
+    import torch
+    lib = gpu_lib
+    x = O.synthetic_traces(mtr, n, seed=77) + np.float32(0.5)
+    p = pkg.default_params(**kw)
+    lib.tspws_b200_derive_params(C.byref(p), n, 1.0)
+    stream = torch.cuda.current_stream().cuda_stream
+    plan = lib.tspws_b200_plan_create(C.byref(p), n, mtr, mtr, 0)
+    assert plan
+    try:
+        al = lib.tspws_b200_plan_part_align(plan)
+        assert al > 0 and (mtr < 1024 or al % 128 == 0)
+        res = []
+        for nparts in (1, 2, 3):
+            dx = torch.from_numpy(x).cuda()              # prep works in place: a fresh copy per run
+            ls, ts = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+            step = -(-(-(-mtr // nparts)) // al) * al    # ceil(ceil(mtr / nparts) / al) * al
+            t0 = 0
+            while t0 < mtr:
+                nt = min(step, mtr - t0)
+                assert lib.tspws_b200_plan_reduce_part(plan, dx[t0].data_ptr(), t0, nt, stream) == 0
+                t0 += nt
+            assert lib.tspws_b200_plan_reduce_done(plan, stream) == 0
+            assert lib.tspws_b200_plan_finish(plan, ls.data_ptr(), ts.data_ptr(), stream) == 0
+            torch.cuda.synchronize()
+            res.append((ls.cpu().numpy(), ts.cpu().numpy()))
+        for ls, ts in res[1:]:
+            np.testing.assert_array_equal(ls, res[0][0])
+            np.testing.assert_array_equal(ts, res[0][1])
+        # misaligned parts are refused, two-stage plans do not take parts
+        assert lib.tspws_b200_plan_reduce_part(plan, torch.from_numpy(x).cuda().data_ptr(), 1, al, stream) == 5    # TSPWS_ERR_ARG
+        o = O.tspws_main(O.Params(**kw), x)
+        assert O.nerr(res[0][1], o["tsPWS"]) <= TOL_STACK and O.nerr(res[0][0], o["ls"]) <= TOL_STACK
+    finally:
+        lib.tspws_b200_plan_destroy(plan)
+    p2 = pkg.default_params(Kmax=10)
+    lib.tspws_b200_derive_params(C.byref(p2), n, 1.0)
+    plan2 = lib.tspws_b200_plan_create(C.byref(p2), n, mtr, mtr, 0)
+    try:
+        assert lib.tspws_b200_plan_part_align(plan2) == 0
+    finally:
+        lib.tspws_b200_plan_destroy(plan2)
+
+
 @pytest.mark.parametrize("kw", [dict(Kmax=10, unbiased=1, lrm=1, fold=1), dict(Kmax=10, unbiased=1, lrm=1),
                                 dict(type=-3, Kmax=8, fold=1), dict(lrm=1, fold=1)])
 def test_device_plan_api_fused_mean_and_fold(pkg, gpu_lib, kw):

@@ -186,6 +186,12 @@ def _declare(lib: C.CDLL, full: bool) -> C.CDLL:
     lib.tspws_b200_plan_peer_close.argtypes = [C.c_void_p]
     lib.tspws_b200_plan_finish.restype = C.c_int
     lib.tspws_b200_plan_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tspws_b200_plan_part_align.restype = C.c_uint
+    lib.tspws_b200_plan_part_align.argtypes = [C.c_void_p]
+    lib.tspws_b200_plan_reduce_part.restype = C.c_int
+    lib.tspws_b200_plan_reduce_part.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p]
+    lib.tspws_b200_plan_reduce_done.restype = C.c_int
+    lib.tspws_b200_plan_reduce_done.argtypes = [C.c_void_p, C.c_void_p]
     lib.tspws_b200_plan_stack.restype = C.c_int
     lib.tspws_b200_plan_stack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tspws_b200_pipe_create.restype = C.c_void_p
@@ -224,7 +230,7 @@ EXPORTS = [
     "tspws_b200_plan_reduce", "tspws_b200_plan_exchange_ptr", "tspws_b200_plan_exchange_bytes",
     "tspws_b200_load_sac_list", "tspws_b200_load_bin", "tspws_b200_save_bin", "tspws_b200_save_rows_bin", "tspws_b200_write_sac",
     "tspws_b200_read_sac", "tspws_b200_free_data",
-    "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_peer_export", "tspws_b200_plan_peer_import", "tspws_b200_plan_peer_region", "tspws_b200_plan_peer_import_ptrs", "tspws_b200_plan_peer_error", "tspws_b200_plan_peer_close", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
+    "tspws_b200_plan_exchange_is_f64", "tspws_b200_plan_bind_exchange", "tspws_b200_plan_mark_exchanged", "tspws_b200_plan_peer_export", "tspws_b200_plan_peer_import", "tspws_b200_plan_peer_region", "tspws_b200_plan_peer_import_ptrs", "tspws_b200_plan_peer_error", "tspws_b200_plan_peer_close", "tspws_b200_plan_part_align", "tspws_b200_plan_reduce_part", "tspws_b200_plan_reduce_done", "tspws_b200_plan_finish", "tspws_b200_plan_stack",
     "tspws_b200_plan_stacks_ptr", "tspws_b200_plan_ncoef", "tspws_b200_plan_get_stacks", "tspws_b200_plan_K",
     "tspws_b200_pipe_create", "tspws_b200_pipe_submit", "tspws_b200_pipe_sync", "tspws_b200_pipe_stream", "tspws_b200_pipe_plan", "tspws_b200_pipe_mode", "tspws_b200_pipe_destroy",
 ]

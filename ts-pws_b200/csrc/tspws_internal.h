@@ -205,6 +205,7 @@ typedef struct {
     int s_of[TSPWS_BAND_MAXV];       /* scale index of voice v                                          */
 } tspws_band_t;
 int tspws_cu_forward_image(const float *d_x, int ntr, int N, void *d_ximg, float *d_tsum, float *d_sumtrace, tspws_stream_t st);
+int tspws_cu_tile_sum(const float *d_tsum, int ntr, int N, float *d_sumtrace, tspws_stream_t st);
 int tspws_cu_forward_mma_all(const void *d_ximg, int ntr, int N, const void *d_wimg, int ncd_dense, const void *d_bimg,
                              const tspws_band_t *d_bands, int nbands, int ngroups_total, float *d_part, int ld_part,
                              int col0_dense, tspws_stream_t st);

@@ -27,10 +27,12 @@ int tspws_convergence_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, 
                           unsigned int mtr, int max, cudaStream_t stream);
 void tspws_resample_release(void);
 
+#define TSPWS_MAIN_PARTS 8
 static struct {
     long          opt_writeback, opt_fp64_tail, opt_device, opt_ss_jackknife;
     int           cuda_state;              /* 0 unknown, 1 ok, -1 unusable */
-    cudaStream_t  stream;
+    cudaStream_t  stream, copy_stream;     /* copy_stream: the traces of a single-stage stack arrive in parts (see tspws_main_locked) */
+    cudaEvent_t   part_ev[TSPWS_MAIN_PARTS];
     /* cached plan of the last main stack */
     tspws_plan_t *plan;
     t_tsPWS       plan_key;
@@ -148,6 +150,8 @@ static void release_device_state(void)
     if (G.d_x)   { cudaFree(G.d_x);   G.d_x = NULL;   G.d_x_cap = 0; }
     if (G.d_out) { cudaFree(G.d_out); G.d_out = NULL; G.d_out_cap = 0; }
     if (G.stream) { cudaStreamDestroy(G.stream); G.stream = NULL; }
+    if (G.copy_stream) { cudaStreamDestroy(G.copy_stream); G.copy_stream = NULL; }
+    for (int i = 0; i < TSPWS_MAIN_PARTS; i++) if (G.part_ev[i]) { cudaEventDestroy(G.part_ev[i]); G.part_ev[i] = NULL; }
     for (int i = 0; i < TSPWS_NSLOT; i++) {
         if (S[i].plan)  tspws_b200_plan_destroy(S[i].plan);
         if (S[i].d_x)   cudaFree(S[i].d_x);
@@ -279,8 +283,6 @@ static int tspws_main_locked(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
         fprintf(stderr, "tspws_b200: out of device memory\n");
         return TSPWS_ERR_ALLOC;
     }
-    if (cudaMemcpyAsync(G.d_x, in->sigall, nelem * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) goto cuda_fail;
-
     const int resampling  = (tspws->subsmpl_N > 0 && tspws->subsmpl_p > 0) || (tspws->jackknife_n > 0 && tspws->jackknife_d > 0);
     const int two_stage   = tspws->Kmax && tspws->Kmax <= mtr;
     /* The host path always cleans the traces themselves, bit-faithfully to the reference's fp32
@@ -293,10 +295,7 @@ static int tspws_main_locked(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
     const int exact_prep  = two_stage && (tspws->fold || tspws->lrm) &&
                             (G.opt_writeback || resampling || tspws->convergence);
     t_tsPWS pp = *tspws;
-    if (exact_prep) {
-        if (tspws_cu_prep(G.d_x, (int)mtr, max, tspws->fold, tspws->lrm, st)) goto cuda_fail;
-        pp.fold = 0; pp.lrm = 0;
-    }
+    if (exact_prep) { pp.fold = 0; pp.lrm = 0; }
 
     /* ---- main stack ---- */
     if (!G.plan || !same_plan_key(&G.plan_key, &pp) || G.plan_max != max || G.plan_mtr != mtr ||
@@ -306,7 +305,38 @@ static int tspws_main_locked(t_tsPWS *tspws, t_tsPWS_out *out, t_data *in)
         if (!G.plan) { fprintf(stderr, "tspws_b200: cannot create the stacking plan\n"); return TSPWS_ERR_ALLOC; }
         G.plan_key = pp; G.plan_max = max; G.plan_mtr = mtr; G.plan_fp64 = G.opt_fp64_tail;
     }
-    if ((nerr = tspws_b200_plan_stack(G.plan, G.d_x, G.d_out, G.d_out + max, st))) goto cuda_fail;
+    /* Single-stage stacks are compute-bound (8 ms of transforms behind a 10 ms copy at 8192 x 16384): the traces go
+     * to the device in up to TSPWS_MAIN_PARTS parts on a copy stream and every part is transformed as soon as it has
+     * arrived, while the next one is on the bus.  Two-stage stacks read every sample once (0.14 ms behind the same
+     * copy): one copy, one graph replay. */
+    const unsigned int al = tspws_b200_plan_part_align(G.plan);
+    unsigned int part = 0;
+    if (al && mtr >= 4 * al && !getenv("TSPWS_MAIN_NO_PARTS")) {
+        int np = 6;            /* measured at 8192 x 16384 (w0 = 6): e2e 18.0 ms in one piece, 14.1 / 12.9 / 12.8 / 12.2 / 13.9 ms in 2 / 3 / 4 / 6 / 8 parts */
+        { const char *e = getenv("TSPWS_MAIN_PARTS"); if (e && atoi(e) >= 1 && atoi(e) <= TSPWS_MAIN_PARTS) np = atoi(e); }
+        part = (mtr + np - 1) / np;
+        part = (part + al - 1) / al * al;
+        if (!G.copy_stream && cudaStreamCreateWithFlags(&G.copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); part = 0; }
+        for (int i = 0; part && i < TSPWS_MAIN_PARTS; i++)
+            if (!G.part_ev[i] && cudaEventCreateWithFlags(&G.part_ev[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); part = 0; }
+    }
+    if (part) {
+        int i = 0;
+        for (unsigned int t0 = 0; t0 < mtr; t0 += part, i++) {
+            const unsigned int nt = t0 + part < mtr ? part : mtr - t0;
+            float *d_p = G.d_x + (size_t)t0 * (size_t)max;
+            if (cudaMemcpyAsync(d_p, in->sigall + (size_t)t0 * (size_t)max, (size_t)nt * (size_t)max * sizeof(float),
+                                cudaMemcpyHostToDevice, G.copy_stream) != cudaSuccess) goto cuda_fail;
+            if (cudaEventRecord(G.part_ev[i], G.copy_stream) != cudaSuccess || cudaStreamWaitEvent(st, G.part_ev[i], 0) != cudaSuccess) goto cuda_fail;
+            if ((nerr = tspws_b200_plan_reduce_part(G.plan, d_p, t0, nt, st))) goto cuda_fail;
+        }
+        if ((nerr = tspws_b200_plan_reduce_done(G.plan, st))) goto cuda_fail;
+        if ((nerr = tspws_b200_plan_finish(G.plan, G.d_out, G.d_out + max, st))) goto cuda_fail;
+    } else {
+        if (cudaMemcpyAsync(G.d_x, in->sigall, nelem * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess) goto cuda_fail;
+        if (exact_prep && tspws_cu_prep(G.d_x, (int)mtr, max, tspws->fold, tspws->lrm, st)) goto cuda_fail;
+        if ((nerr = tspws_b200_plan_stack(G.plan, G.d_x, G.d_out, G.d_out + max, st))) goto cuda_fail;
+    }
     if (cudaMemcpyAsync(out->ls, G.d_out, (size_t)max * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) goto cuda_fail;
     if (cudaMemcpyAsync(out->tsPWS, G.d_out + max, (size_t)max * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess) goto cuda_fail;
     if (G.opt_writeback && (tspws->fold || tspws->lrm))

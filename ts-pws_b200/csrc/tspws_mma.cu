@@ -864,9 +864,21 @@ extern "C" int tspws_cu_forward_image(const float *d_x, int ntr, int N, void *d_
     cudaFuncSetAttribute(trace_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FD_NT * MMA_TILE_BYTES);
     trace_image_kernel<<<dim3(kblocks, mtiles), 256, FD_NT * MMA_TILE_BYTES, s>>>(d_x, ntr, N, kblocks, (__nv_bfloat16 *)d_ximg, d_tsum);
     tspws_cu_profile_launched("trace_image_kernel", st);
-    tile_sum_kernel<<<(N + 255) / 256, 256, 0, s>>>(d_tsum, mtiles, N, d_sumtrace);
+    tspws_cu_launch_count_add(1);
+    if (d_sumtrace) {                                   /* NULL: the caller sums the tiles later (tspws_cu_tile_sum), e.g. after several parts */
+        tile_sum_kernel<<<(N + 255) / 256, 256, 0, s>>>(d_tsum, mtiles, N, d_sumtrace);
+        tspws_cu_profile_launched("tile_sum_kernel", st);
+        tspws_cu_launch_count_add(1);
+    }
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tspws_cu_tile_sum(const float *d_tsum, int ntr, int N, float *d_sumtrace, tspws_stream_t st)
+{
+    if (ntr <= 0) return 0;
+    tile_sum_kernel<<<(N + 255) / 256, 256, 0, (cudaStream_t)st>>>(d_tsum, (ntr + MMA_TILE_MN - 1) / MMA_TILE_MN, N, d_sumtrace);
     tspws_cu_profile_launched("tile_sum_kernel", st);
-    tspws_cu_launch_count_add(2);
+    tspws_cu_launch_count_add(1);
     return (int)cudaGetLastError();
 }
 

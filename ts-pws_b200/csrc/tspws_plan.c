@@ -819,6 +819,8 @@ fail:
 static void *plan_ps(tspws_plan_t *pl) { return pl->d_exch; }
 static void *plan_st(tspws_plan_t *pl) { return (char *)pl->d_exch + (size_t)pl->fr->ncoef * pl->csz; }
 
+static int single_stage_close(tspws_plan_t *pl, void *stream);
+
 int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
 {
     if (!pl || (!d_sigall && pl->mtr_local)) return TSPWS_ERR_NULL;
@@ -854,23 +856,21 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
                                  pl->d_gsum, pl->d_gtile, stream))) return TSPWS_ERR_CUDA;
         return 0;
     }
+    if (tspws_b200_plan_part_align(pl)) {
+        /* fp32 single-stage: the whole shard as one part, then the closing step */
+        if ((e = tspws_b200_plan_reduce_part(pl, d_sigall, 0, pl->mtr_local, stream))) return e;
+        return tspws_b200_plan_reduce_done(pl, stream);
+    }
     if ((e = tspws_cu_prep(d_sigall, (int)pl->mtr_local, pl->N, pl->p.fold, pl->p.lrm, stream))) return TSPWS_ERR_CUDA;
     if (pl->acc64) {
         if ((e = tspws_cu_forward(&pl->dev, d_sigall, 0, 1, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
     } else {
-        if (pl->dense_on && env_long("TSPWS_MMA_PERSIST", 1)) {
-            /* trace image, then every dense and banded job of the stack in one persistent launch */
-            if ((e = tspws_cu_forward_image(d_sigall, pl->ntr_fwd, pl->N, pl->d_ximg, pl->d_tsum, pl->d_sumtrace, stream))) return TSPWS_ERR_CUDA;
-            if ((e = tspws_cu_forward_mma_all(pl->d_ximg, pl->ntr_fwd, pl->N, pl->d_wimg, pl->dense_ncd, pl->d_bimg, pl->d_bands, pl->band_n,
-                                              pl->band_groups, pl->d_dpart, 2 * pl->td_ncd, 2 * (pl->dense_ci0 - pl->td_ci0), stream))) return TSPWS_ERR_CUDA;
-        } else {
         if (pl->dense_on &&
             (e = tspws_cu_forward_dense(d_sigall, pl->ntr_fwd, pl->N, pl->d_wimg, pl->dense_ncd, pl->d_ximg, pl->d_tsum, pl->d_sumtrace,
                                         pl->d_dpart, 2 * pl->td_ncd, 2 * (pl->dense_ci0 - pl->td_ci0), stream))) return TSPWS_ERR_CUDA;
         if (pl->band_n &&
             (e = tspws_cu_forward_band(pl->d_ximg, pl->ntr_fwd, pl->N, pl->d_bimg, pl->d_bands, pl->band_n, pl->band_groups,
                                        pl->d_dpart, 2 * pl->td_ncd, stream))) return TSPWS_ERR_CUDA;
-        }
         if ((e = tspws_cu_forward_fast(&pl->dev, d_sigall, pl->ntr_fwd, pl->chunk, pl->d_pps, pl->d_pst,
                                        pl->dense_on ? pl->dense_items : 0, pl->dense_on ? pl->simt_lg_end : 5, stream))) return TSPWS_ERR_CUDA;
         if (pl->dense_on) {
@@ -879,6 +879,13 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
             if ((e = tspws_cu_dense_finish(pl->d_dpart, pl->ntr_fwd, pl->td_ncd, pl->d_ysum_st, pl->td_ci0, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
         }
     }
+    return single_stage_close(pl, stream);
+}
+
+/* reduce_weight + the push of the sums to the peers: the end of the reduce step of a single-stage plan */
+static int single_stage_close(tspws_plan_t *pl, void *stream)
+{
+    int e;
     if ((e = tspws_cu_reduce_weight(pl->d_pps, pl->d_pst, pl->acc64, pl->dev.ncoef, 1, pl->nchunk, pl->d_rule,
                                     plan_ps(pl), plan_st(pl), pl->d_zout, stream))) return TSPWS_ERR_CUDA;
     if (pl->peer_on && !pl->acc64) {
@@ -891,6 +898,58 @@ int tspws_b200_plan_reduce(tspws_plan_t *pl, float *d_sigall, void *stream)
         pl->peer_pending = 1;
     }
     return 0;
+}
+
+/* ---- the reduce step of an fp32 single-stage plan in PARTS of the shard: lets a caller that still copies the traces to
+ * the device transform the part that has arrived while the next one is on the bus (tspws_main does).  Parts start at
+ * multiples of tspws_b200_plan_part_align() traces (0: the plan does not take parts -- two-stage, fp64, non-persistent
+ * tensor-core path) and every part but the last is a multiple of it long; after the last part call ..._reduce_done. ---- */
+unsigned int tspws_b200_plan_part_align(tspws_plan_t *pl)
+{
+    if (!pl || pl->two_stage || pl->acc64 || pl->dev.per_trace) return 0;
+    if (pl->dense_on && !env_long("TSPWS_MMA_PERSIST", 1)) return 0;
+    unsigned int a = (unsigned int)pl->chunk;
+    if (pl->dense_on) { unsigned int x = a, y = 128; while (y) { const unsigned int t = x % y; x = y; y = t; } a = a / x * 128; }   /* lcm(chunk, 128) */
+    return a;
+}
+
+int tspws_b200_plan_reduce_part(tspws_plan_t *pl, float *d_part, unsigned int t0, unsigned int nt, void *stream)
+{
+    const unsigned int al = tspws_b200_plan_part_align(pl);
+    if (!pl || (!d_part && nt)) return TSPWS_ERR_NULL;
+    if (!al || t0 % al || t0 + nt > pl->mtr_local || ((nt % al) && t0 + nt != pl->mtr_local)) return TSPWS_ERR_ARG;
+    if (!nt) return 0;
+    int e;
+    if (t0 == 0) { pl->summed_across_ranks = 0; pl->peer_pending = 0; tspws_cu_profile_mark(stream); }
+    const size_t ncoef = pl->fr->ncoef;
+    if ((e = tspws_cu_prep(d_part, (int)nt, pl->N, pl->p.fold, pl->p.lrm, stream))) return TSPWS_ERR_CUDA;
+    if (pl->dense_on) {
+        const size_t mt0 = t0 / 128;
+        char *ximg = (char *)pl->d_ximg + mt0 * tspws_cu_dense_ximg_bytes(128, pl->N);
+        if ((e = tspws_cu_forward_image(d_part, (int)nt, pl->N, ximg, pl->d_tsum + mt0 * pl->N, NULL, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_forward_mma_all(ximg, (int)nt, pl->N, pl->d_wimg, pl->dense_ncd, pl->d_bimg, pl->d_bands, pl->band_n,
+                                          pl->band_groups, pl->d_dpart + mt0 * 2 * (size_t)pl->td_ncd, 2 * pl->td_ncd,
+                                          2 * (pl->dense_ci0 - pl->td_ci0), stream))) return TSPWS_ERR_CUDA;
+    }
+    const size_t c0 = t0 / (unsigned int)pl->chunk;
+    if ((e = tspws_cu_forward_fast(&pl->dev, d_part, (int)nt, pl->chunk, (char *)pl->d_pps + c0 * ncoef * pl->csz,
+                                   (char *)pl->d_pst + c0 * ncoef * pl->csz, pl->dense_on ? pl->dense_items : 0,
+                                   pl->dense_on ? pl->simt_lg_end : 5, stream))) return TSPWS_ERR_CUDA;
+    return 0;
+}
+
+int tspws_b200_plan_reduce_done(tspws_plan_t *pl, void *stream)
+{
+    if (!pl) return TSPWS_ERR_NULL;
+    if (!tspws_b200_plan_part_align(pl)) return TSPWS_ERR_ARG;
+    int e;
+    if (pl->dense_on) {
+        /* linear stack of the tensor-core coefficients = transform of the summed trace (generic kernel, one trace) */
+        if ((e = tspws_cu_tile_sum(pl->d_tsum, pl->ntr_fwd, pl->N, pl->d_sumtrace, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_forward_one(&pl->dev, pl->d_sumtrace, pl->dev.h_item_first[pl->td_s0], pl->d_ysum_ps, pl->d_ysum_st, stream))) return TSPWS_ERR_CUDA;
+        if ((e = tspws_cu_dense_finish(pl->d_dpart, pl->ntr_fwd, pl->td_ncd, pl->d_ysum_st, pl->td_ci0, pl->d_pps, pl->d_pst, stream))) return TSPWS_ERR_CUDA;
+    }
+    return single_stage_close(pl, stream);
 }
 
 void *tspws_b200_plan_exchange_ptr(tspws_plan_t *pl)
