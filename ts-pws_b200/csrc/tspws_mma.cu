@@ -251,6 +251,7 @@ extern "C" int tspws_cu_resample_mma(const void *d_a_img, const void *d_b_img, i
         resample_mma_kernel<3><<<grid, MMA_THREADS, smem, (cudaStream_t)st>>>((const __nv_bfloat16 *)d_a_img, (const __nv_bfloat16 *)d_b_img,
                                                                                mtiles, kblocks, M, N, d_out, ld_out);
     }
+    tspws_cu_profile_launched("resample_mma_kernel", st);
     tspws_cu_launch_count_add(1);
     return (int)cudaGetLastError();
 }
@@ -278,6 +279,7 @@ extern "C" int tspws_cu_count_image(const signed char *d_cnt, int ld, int M, int
     if (M <= 0 || T <= 0) return 0;
     const int mtiles = (M + MMA_TILE_MN - 1) / MMA_TILE_MN, kblocks = (T + MMA_TILE_K - 1) / MMA_TILE_K;
     count_image_kernel<<<dim3(kblocks, mtiles), 256, 0, (cudaStream_t)st>>>(d_cnt, ld, M, T, kblocks, (__nv_bfloat16 *)d_img);
+    tspws_cu_profile_launched("count_image_kernel", st);
     tspws_cu_launch_count_add(1);
     return (int)cudaGetLastError();
 }
@@ -322,6 +324,7 @@ extern "C" int tspws_cu_phasor_image(const void *d_P, int ncoef, int nt, int t0,
     dim3 grid(kbl, ntiles);
     if (nterm == 2) phasor_image_kernel<2><<<grid, 256, 0, (cudaStream_t)st>>>((const float2 *)d_P, ncoef, nt, t0, kblocks_total, (__nv_bfloat16 *)d_img);
     else            phasor_image_kernel<3><<<grid, 256, 0, (cudaStream_t)st>>>((const float2 *)d_P, ncoef, nt, t0, kblocks_total, (__nv_bfloat16 *)d_img);
+    tspws_cu_profile_launched("phasor_image_kernel", st);
     tspws_cu_launch_count_add(1);
     return (int)cudaGetLastError();
 }

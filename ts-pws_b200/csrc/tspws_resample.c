@@ -57,6 +57,20 @@ static void frames_close(rs_frames_t *F)
     memset(F, 0, sizeof(*F));
 }
 
+/* The frames of the sub-sampling driver are kept between calls: building them (filters on the host, the polyphase
+ * tables, the uploads) took ~25 ms of every call at 32768 samples.  Key = everything frame_create depends on. */
+static struct { rs_frames_t F; int valid, type, uni, max, need_pt; unsigned int J, V; double s0, b0, w0; } g_fc;
+static rs_frames_t *frames_cached(const t_tsPWS *p, int max, int need_pt, int *rc)
+{
+    if (g_fc.valid && g_fc.type == p->type && g_fc.uni == (int)p->uni && g_fc.max == max && g_fc.J == p->J && g_fc.V == p->V &&
+        g_fc.s0 == p->s0 && g_fc.b0 == p->b0 && g_fc.w0 == p->w0 && (g_fc.need_pt || !need_pt)) return &g_fc.F;
+    if (g_fc.valid) { frames_close(&g_fc.F); g_fc.valid = 0; }
+    if ((*rc = frames_open(&g_fc.F, p, max, need_pt))) { frames_close(&g_fc.F); return NULL; }
+    g_fc.valid = 1; g_fc.type = p->type; g_fc.uni = (int)p->uni; g_fc.max = max; g_fc.need_pt = need_pt;
+    g_fc.J = p->J; g_fc.V = p->V; g_fc.s0 = p->s0; g_fc.b0 = p->b0; g_fc.w0 = p->w0;
+    return &g_fc.F;
+}
+
 /* group of the r-th selected trace out of K: src/ts_pws1f_lib.c:648 (unsigned product, double division) */
 static int rank_group(unsigned int r, unsigned int Kmax, unsigned int K)
 {
@@ -118,7 +132,29 @@ static int rp_acquire(rowpipe_t **out, int B, size_t N)
     *out = &g_rp;
     return 0;
 }
-void tspws_resample_release(void) { if (g_rp.cst) rp_close(&g_rp); }
+/* Device scratch of the two sub-sampling drivers, kept between calls: at BASELINE configs[3] (2.5 GB in 15 buffers) the
+ * cudaMalloc / cudaFree round of every call cost ~30 ms of its 140.  Slot = one buffer of one driver; grows on demand. */
+#define RS_SLOTS 28
+static struct { void *p; size_t cap; } g_scr[RS_SLOTS];
+static cudaError_t rs_scratch(int slot, void **p, size_t bytes)
+{
+    if (g_scr[slot].cap < bytes) {
+        if (g_scr[slot].p) cudaFree(g_scr[slot].p);
+        g_scr[slot].p = NULL; g_scr[slot].cap = 0;
+        const cudaError_t e = cudaMalloc(&g_scr[slot].p, bytes);
+        if (e != cudaSuccess) return e;
+        g_scr[slot].cap = bytes;
+    }
+    *p = g_scr[slot].p;
+    return cudaSuccess;
+}
+
+void tspws_resample_release(void)
+{
+    if (g_rp.cst) rp_close(&g_rp);
+    for (int i = 0; i < RS_SLOTS; i++) { if (g_scr[i].p) cudaFree(g_scr[i].p); g_scr[i].p = NULL; g_scr[i].cap = 0; }
+    if (g_fc.valid) { frames_close(&g_fc.F); g_fc.valid = 0; }
+}
 
 /* batch k is about to be computed into buffers k & 1: the copy of batch k - 2 out of them must have finished */
 static int rp_begin(rowpipe_t *rp, int k, cudaStream_t st)
@@ -174,6 +210,8 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     unsigned int *d_tk = NULL, *Ks = NULL;
     const int ntk = (max + 255) / 256;
     rowpipe_t *rpp = NULL;
+    signed char *h_cnt = NULL, *d_cnt = NULL;
+    void *d_ximg = NULL, *d_aimg = NULL;
 
     if (Kmax > 32767) { fprintf(stderr, "tspws_b200: two-stage resampling supports Kmax <= 32767\n"); return TSPWS_ERR_ARG; }
     for (size_t i = 0; i < (size_t)nres * mtr; i++)
@@ -187,16 +225,35 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     Ks      = (unsigned int *)malloc(B * sizeof(unsigned int));
     if (!h_gid || !h_scale || !h_rules || !Ks) { rc = TSPWS_ERR_ALLOC; goto done; }
     if ((rc = rp_acquire(&rpp, B, N))) goto done;
-    CKR(cudaMalloc((void **)&d_gid, (size_t)B * mtr * sizeof(short)));
-    CKR(cudaMalloc((void **)&d_gs, (size_t)B * Kmax * N * sizeof(float)));
-    CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
-    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.inv_slots ? F->acc.inv_slots : 1) * B * N * sizeof(float)));
-    CKR(cudaMalloc((void **)&d_scale, B * sizeof(double)));
-    CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
-    CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
+    CKR(rs_scratch(0, (void **)&d_gid, (size_t)B * mtr * sizeof(short)));
+    CKR(rs_scratch(1, (void **)&d_gs, (size_t)B * Kmax * N * sizeof(float)));
+    CKR(rs_scratch(2, (void **)&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(rs_scratch(3, (void **)&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(rs_scratch(4, (void **)&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
+    CKR(rs_scratch(5, (void **)&d_scr, (size_t)2 * (F->acc.inv_slots ? F->acc.inv_slots : 1) * B * N * sizeof(float)));
+    CKR(rs_scratch(6, (void **)&d_scale, B * sizeof(double)));
+    CKR(rs_scratch(7, (void **)&d_rules, B * sizeof(tspws_weight_t)));
+    CKR(rs_scratch(8, (void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
     CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
+    /* The Kmax group sums of a batch of realisations are a 0/1 matrix times the traces: G[(b, g)][n] = sum_t [trace t is in
+     * group g of realisation b] x_t[n] -- on the tensor cores like the single-stage sums (traces as three bf16 terms,
+     * fp32-faithful; indicator exact): 0.4 ms per batch of 64 x 10 groups at 2000 x 32768 instead of the 3 ms of
+     * regroup_kernel.  TSPWS_RS_REGROUP=1 / odd lengths / very large Kmax keep the SIMT kernel. */
+    const int kblocks = ((int)mtr + 63) / 64;
+    const int sums_mma = (max % 2 == 0) && (size_t)B * Kmax <= 8192 && !(getenv("TSPWS_RS_REGROUP") && atoi(getenv("TSPWS_RS_REGROUP"))) &&
+                         !(getenv("TSPWS_NO_MMA") && atoi(getenv("TSPWS_NO_MMA")));
+    if (sums_mma) {
+        h_cnt = (signed char *)malloc((size_t)B * Kmax * mtr);
+        if (!h_cnt) { rc = TSPWS_ERR_ALLOC; goto done; }
+        CKR(rs_scratch(24, &d_ximg, tspws_cu_mma_b_image_bytes(max, (int)mtr, 3)));
+        CKR(rs_scratch(26, (void **)&d_cnt, (size_t)B * Kmax * mtr));
+        CKR(rs_scratch(27, &d_aimg, tspws_cu_mma_a_image_bytes(B * (int)Kmax, (int)mtr)));
+        CKR(cudaMemsetAsync(d_ximg, 0, tspws_cu_mma_b_image_bytes(max, (int)mtr, 3), st));
+        for (unsigned int t0 = 0; t0 < mtr; t0 += 4096) {
+            const int nt = (int)((mtr - t0 < 4096) ? mtr - t0 : 4096);
+            CKK(tspws_cu_phasor_image(d_x + (size_t)t0 * N, max / 2, nt, (int)t0, kblocks, 3, d_ximg, st));
+        }
+    }
 
     int k = 0;
     for (unsigned int m0 = 0; m0 < nres; m0 += B, k++) {
@@ -211,6 +268,11 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
             unsigned int r = 0;
             for (unsigned int t = 0; t < mtr; t++)
                 h_gid[(size_t)b * mtr + t] = (row[t] == 1) ? (short)rank_group(r++, Kmax, K) : (short)-1;
+            if (sums_mma) {
+                memset(h_cnt + (size_t)b * Kmax * mtr, 0, (size_t)Kmax * mtr);
+                for (unsigned int t = 0; t < mtr; t++)
+                    if (h_gid[(size_t)b * mtr + t] >= 0) h_cnt[((size_t)b * Kmax + (size_t)h_gid[(size_t)b * mtr + t]) * mtr + t] = 1;
+            }
             Ks[b] = K;
             h_scale[b] = K ? 1.0 / (double)K : 0.0;                                   /* W/K with W = 1 (:672,:686) */
             h_rules[b] = tspws_weight_rule(p->wu, p->unbiased, Kmax, K ? K : 1);
@@ -220,7 +282,13 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
         CKR(cudaMemcpyAsync(d_scale, h_scale, nb * sizeof(double), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_rules, h_rules, nb * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
         if ((rc = rp_begin(rpp, k, st))) goto done;
-        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, NULL, nb, (int)Kmax, d_gs, st));
+        if (sums_mma) {
+            CKR(cudaMemcpyAsync(d_cnt, h_cnt, (size_t)nb * Kmax * mtr, cudaMemcpyHostToDevice, st));
+            CKK(tspws_cu_count_image(d_cnt, (int)mtr, nb * (int)Kmax, (int)mtr, d_aimg, st));
+            CKK(tspws_cu_resample_mma(d_aimg, d_ximg, 3, nb * (int)Kmax, max, kblocks, d_gs, N, st));
+        } else {
+            CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid, NULL, nb, (int)Kmax, d_gs, st));
+        }
         if (ls_rows) CKK(tspws_cu_group_total(d_gs, nb, (int)Kmax, max, d_scale, d_ls, st));
         CKK(tspws_cu_forward_fast(&F->acc, d_gs, nb * (int)Kmax, (int)Kmax, d_pps, d_pst, 0, 5, st));
         CKK(tspws_cu_weight(d_pps, d_pst, 0, (int)F->fr->ncoef, nb, d_rules, d_zout, st));
@@ -232,9 +300,8 @@ static int two_stage_rows(const t_tsPWS *p, rs_frames_t *F, const float *d_x, un
     if (k > 0) rc = rp_collect(rpp, k - 1, ls_rows, ts_rows, sim_out, mis_out);
 done:
     cudaStreamSynchronize(st);
-    free(h_gid); free(h_scale); free(h_rules); free(Ks);
-    cudaFree(d_gid); cudaFree(d_gs); cudaFree(d_pps); cudaFree(d_pst);
-    cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale); cudaFree(d_rules); cudaFree(d_tk);
+    free(h_gid); free(h_scale); free(h_rules); free(Ks); free(h_cnt);
+    /* the device scratch stays cached (rs_scratch) */
     if (rpp) cudaStreamSynchronize(rpp->cst);
     return rc;
 }
@@ -257,12 +324,14 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     const int use_mma = !getenv("TSPWS_NO_MMA") || atoi(getenv("TSPWS_NO_MMA")) == 0;
     const int nterm = (getenv("TSPWS_MMA_TERMS") && atoi(getenv("TSPWS_MMA_TERMS")) == 3) ? 3 : 2;
     const int kblocks = ((int)mtr + 63) / 64;
+    const int pertrace_path = F->have_pt && getenv("TSPWS_RS_PERTRACE") && atoi(getenv("TSPWS_RS_PERTRACE"));   /* the previous transform path (A/B) */
     short *h_gid = NULL, *d_gid = NULL;
     signed char *d_sel = NULL;
     float *d_S = NULL;
     void *d_ypart = NULL, *d_P = NULL, *d_ps = NULL, *d_pps = NULL, *d_pst = NULL, *d_zout = NULL, *d_scr = NULL;
     rowpipe_t *rpp = NULL;
-    void *d_aimg = NULL, *d_bimg = NULL;
+    void *d_aimg = NULL, *d_bimg = NULL, *d_ximg = NULL;
+    float *d_Sall = NULL;                  /* [M][N] time-domain sums of all realisations (tensor-core path) */
     double *d_scale = NULL, *h_scale = NULL;
     tspws_weight_t *d_rules = NULL, *h_rules = NULL;
     unsigned int *d_tk = NULL, *km_all = NULL;
@@ -281,26 +350,28 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
             if (c > 0) km_all[m] += (unsigned int)c;
         }
 
-    CKR(cudaMalloc((void **)&d_gid, (size_t)M * mtr * sizeof(short)));
-    CKR(cudaMalloc((void **)&d_sel, (size_t)M * mtr));
-    CKR(cudaMalloc((void **)&d_S, (size_t)B * N * sizeof(float)));
-    CKR(cudaMalloc(&d_ypart, (size_t)TR_BATCH * (F->pt.ypart_len ? F->pt.ypart_len : 1) * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_P, (size_t)TR_BATCH * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_ps, (size_t)M * ncoef * 2 * (use_mma ? sizeof(float) : sizeof(double))));
-    CKR(cudaMalloc(&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
-    CKR(cudaMalloc(&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
-    CKR(cudaMalloc(&d_scr, (size_t)2 * (F->acc.inv_slots ? F->acc.inv_slots : 1) * B * N * sizeof(float)));
-    CKR(cudaMalloc((void **)&d_scale, B * sizeof(double)));
-    CKR(cudaMalloc((void **)&d_rules, B * sizeof(tspws_weight_t)));
-    CKR(cudaMalloc((void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
+    CKR(rs_scratch(9, (void **)&d_gid, (size_t)M * mtr * sizeof(short)));
+    CKR(rs_scratch(10, (void **)&d_sel, (size_t)M * mtr));
+    CKR(rs_scratch(11, (void **)&d_S, (size_t)B * N * sizeof(float)));
+    CKR(rs_scratch(12, (void **)&d_ypart, (size_t)TR_BATCH * ((F->have_pt && (size_t)F->pt.ypart_len > ncoef) ? (size_t)F->pt.ypart_len : ncoef) * 2 * sizeof(float)));
+    CKR(rs_scratch(13, (void **)&d_P, (size_t)TR_BATCH * ncoef * 2 * sizeof(float)));
+    CKR(rs_scratch(14, (void **)&d_ps, (size_t)M * ncoef * 2 * (use_mma ? sizeof(float) : sizeof(double))));
+    CKR(rs_scratch(15, (void **)&d_pps, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(rs_scratch(16, (void **)&d_pst, (size_t)B * ncoef * 2 * sizeof(float)));
+    CKR(rs_scratch(17, (void **)&d_zout, (size_t)B * ncoef * 4 * sizeof(float)));
+    CKR(rs_scratch(18, (void **)&d_scr, (size_t)2 * (F->acc.inv_slots ? F->acc.inv_slots : 1) * B * N * sizeof(float)));
+    CKR(rs_scratch(19, (void **)&d_scale, B * sizeof(double)));
+    CKR(rs_scratch(20, (void **)&d_rules, B * sizeof(tspws_weight_t)));
+    CKR(rs_scratch(21, (void **)&d_tk, (size_t)B * ntk * sizeof(unsigned int)));
     CKR(cudaMemsetAsync(d_tk, 0, (size_t)B * ntk * sizeof(unsigned int), st));
     CKR(cudaMemcpyAsync(d_gid, h_gid, (size_t)M * mtr * sizeof(short), cudaMemcpyHostToDevice, st));
     CKR(cudaMemcpyAsync(d_sel, sel, (size_t)M * mtr, cudaMemcpyHostToDevice, st));
     if (use_mma) {
         /* tile images: counts (A) once, unit phasors (B) batch by batch as the traces are transformed */
-        CKR(cudaMalloc(&d_aimg, tspws_cu_mma_a_image_bytes((int)M, (int)mtr)));
-        CKR(cudaMalloc(&d_bimg, tspws_cu_mma_b_image_bytes(2 * (int)F->fr->ncoef, (int)mtr, nterm)));
+        CKR(rs_scratch(22, (void **)&d_aimg, tspws_cu_mma_a_image_bytes((int)M, (int)mtr)));
+        CKR(rs_scratch(23, (void **)&d_bimg, tspws_cu_mma_b_image_bytes(2 * (int)F->fr->ncoef, (int)mtr, nterm)));
+        /* cached buffers: no stale (possibly non-finite) bits in the padding of the phasor image */
+        CKR(cudaMemsetAsync(d_bimg, 0, tspws_cu_mma_b_image_bytes(2 * (int)F->fr->ncoef, (int)mtr, nterm), st));
         CKK(tspws_cu_count_image(d_sel, (int)mtr, (int)M, (int)mtr, d_aimg, st));
     } else {
         CKR(cudaMemsetAsync(d_ps, 0, (size_t)M * ncoef * 2 * sizeof(double), st));
@@ -309,13 +380,36 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
     /* every trace is transformed once: per-trace coefficients -> unit phasors -> image (or the SIMT contraction) */
     for (unsigned int t0 = 0; t0 < mtr; t0 += TR_BATCH) {
         const int nt = (int)((mtr - t0 < TR_BATCH) ? mtr - t0 : TR_BATCH);
-        CKK(tspws_cu_forward_pertrace(&F->pt, d_x + (size_t)t0 * N, nt, 0, d_ypart, st));
-        CKK(tspws_cu_coef_matrix(&F->pt, d_ypart, nt, NULL, d_P, st));
+        if (pertrace_path) {
+            CKK(tspws_cu_forward_pertrace(&F->pt, d_x + (size_t)t0 * N, nt, 0, d_ypart, st));
+            CKK(tspws_cu_coef_matrix(&F->pt, d_ypart, nt, NULL, d_P, st));
+        } else {
+            /* the chunk-accumulating kernels with chunks of ONE trace: the "partial phase stack" of a chunk is then the
+             * trace's unit phasors (d_P), its "partial linear stack" the coefficients themselves (scratch, unused).
+             * The per-trace kernels are built for the ~10 traces of a two-stage tail (phase splits, a combine pass): at
+             * 2000 x 32768 they took 55 ms of the call's 130 ms of kernels. */
+            CKK(tspws_cu_forward_fast(&F->acc, d_x + (size_t)t0 * N, nt, 1, d_P, d_ypart, 0, 5, st));
+        }
         if (use_mma) CKK(tspws_cu_phasor_image(d_P, (int)F->fr->ncoef, nt, (int)t0, kblocks, nterm, d_bimg, st));
         else         CKK(tspws_cu_select_sum(d_P, nt, (int)F->fr->ncoef, d_sel, (int)mtr, (int)t0, (int)M, d_ps, st));
     }
     if (use_mma)
         CKK(tspws_cu_resample_mma(d_aimg, d_bimg, nterm, (int)M, 2 * (int)F->fr->ncoef, kblocks, (float *)d_ps, 2 * ncoef, st));
+    /* The time-domain sums S_m = sum_t sel[m][t] x_t (ls, and ST by linearity) are the same contraction with the traces
+     * in place of the phasors: [M x T] . [T x N], traces as three bf16 terms (fp32-faithful), counts exact -- one launch
+     * for all realisations instead of a 1.9 ms regroup launch per batch of 64 (30 of the call's 130 ms at configs[3]).
+     * Needs an even trace length (the image builder takes the samples in pairs). */
+    const int sums_mma = use_mma && (max % 2 == 0) && !(getenv("TSPWS_RS_REGROUP") && atoi(getenv("TSPWS_RS_REGROUP")));
+    if (sums_mma) {
+        CKR(rs_scratch(24, &d_ximg, tspws_cu_mma_b_image_bytes(max, (int)mtr, 3)));
+        CKR(rs_scratch(25, (void **)&d_Sall, (size_t)M * N * sizeof(float)));
+        CKR(cudaMemsetAsync(d_ximg, 0, tspws_cu_mma_b_image_bytes(max, (int)mtr, 3), st));
+        for (unsigned int t0 = 0; t0 < mtr; t0 += 4096) {          /* the builder's grid.x is a count of 64-trace blocks */
+            const int nt = (int)((mtr - t0 < 4096) ? mtr - t0 : 4096);
+            CKK(tspws_cu_phasor_image(d_x + (size_t)t0 * N, max / 2, nt, (int)t0, kblocks, 3, d_ximg, st));
+        }
+        CKK(tspws_cu_resample_mma(d_aimg, d_ximg, 3, (int)M, max, kblocks, d_Sall, N, st));
+    }
 
     /* per batch of realisations: time-domain sums -> ls, ST by linearity, weights, inverse */
     int k = 0;
@@ -332,7 +426,8 @@ static int single_stage_subsample(const t_tsPWS *p, rs_frames_t *F, const float 
         CKR(cudaMemcpyAsync(d_scale, h_scale, B * sizeof(double), cudaMemcpyHostToDevice, st));
         CKR(cudaMemcpyAsync(d_rules, h_rules, B * sizeof(tspws_weight_t), cudaMemcpyHostToDevice, st));
         if ((rc = rp_begin(rpp, k, st))) goto done;
-        CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, d_sel + (size_t)m0 * mtr, nb, 1, d_S, st));
+        if (sums_mma) d_S = d_Sall + (size_t)m0 * N;
+        else CKK(tspws_cu_regroup(d_x, max, (int)mtr, d_gid + (size_t)m0 * mtr, d_sel + (size_t)m0 * mtr, nb, 1, d_S, st));
         CKK(tspws_cu_group_total(d_S, nb, 1, max, d_scale, d_ls, st));
         CKK(tspws_cu_forward_fast(&F->acc, d_S, nb, 1, d_pps, d_pst, 0, 5, st));
         if (use_mma)
@@ -350,9 +445,7 @@ done:
     cudaStreamSynchronize(st);
     if (rpp) cudaStreamSynchronize(rpp->cst);
     free(h_gid); free(h_scale); free(h_rules); free(km_all);
-    cudaFree(d_gid); cudaFree(d_sel); cudaFree(d_S); cudaFree(d_ypart); cudaFree(d_P);
-    cudaFree(d_ps); cudaFree(d_pps); cudaFree(d_pst); cudaFree(d_zout); cudaFree(d_scr); cudaFree(d_scale);
-    cudaFree(d_rules); cudaFree(d_tk); cudaFree(d_aimg); cudaFree(d_bimg);
+    /* the device scratch stays cached (rs_scratch) */
     return rc;
 }
 
@@ -363,10 +456,13 @@ int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, flo
 {
     int rc = 0;
     const int two_stage = p->Kmax && p->Kmax <= mtr;
-    rs_frames_t F;
     char *sel = NULL;
     if (!out->ls_subsmpl || !out->tsPWS_subsmpl) { printf("tspws_main: NULL resampling outputs\n"); return -1; }
-    if ((rc = frames_open(&F, p, max, !two_stage))) { frames_close(&F); return rc; }
+    /* the per-trace frame is only needed by the previous single-stage transform path (TSPWS_RS_PERTRACE=1) */
+    const int need_pt = !two_stage && getenv("TSPWS_RS_PERTRACE") && atoi(getenv("TSPWS_RS_PERTRACE"));
+    rs_frames_t *Fp = frames_cached(p, max, need_pt, &rc);
+    if (!Fp) return rc;
+#define F (*Fp)
 
     /* ---- random sub-sampling (src/ts_pws1f_lib.c:324-333) ---- */
     if (p->subsmpl_N > 0 && p->subsmpl_p > 0) {
@@ -407,7 +503,7 @@ int tspws_resample_run(const t_tsPWS *p, t_tsPWS_out *out, const t_data *in, flo
     }
 done:
     free(sel);
-    frames_close(&F);
+#undef F
     return rc;
 }
 
