@@ -15,8 +15,15 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 TOL = 1e-4
 
 
+@pytest.mark.parametrize("simt", [False, True], ids=["tensor_core_sums", "simt_fallbacks"])
 @pytest.mark.parametrize("name", sorted(CS.RESAMPLE_CASES))
-def test_resampling_matches_reference(pkg, gpu_lib, name):
+def test_resampling_matches_reference(pkg, gpu_lib, name, simt, monkeypatch):
+    """Default: phase stacks, time-domain sums and group sums as tcgen05 contractions, per-trace phasors from the
+    chunk-of-one transform kernels.  simt_fallbacks: the kernels they replaced (regroup_kernel, the per-trace transform),
+    which odd trace lengths and very large Kmax still use."""
+    if simt:
+        monkeypatch.setenv("TSPWS_RS_REGROUP", "1")
+        monkeypatch.setenv("TSPWS_RS_PERTRACE", "1")
     case = CS.RESAMPLE_CASES[name]
     g = np.load(os.path.join(GOLD, name + ".npz"))
     x = CS.make_input(case)
