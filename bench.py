@@ -692,10 +692,12 @@ def run_stack(args, wl, name):
                          "input_buffers": 2, "exchange": ("peer memory over NVLink" if ps.peer else "none")}
             if peer_err_check(lib, ps):
                 raise SystemExit(f"rank {rank}: a peer wait timed out in the pipelined leg -- the measurement is invalid")
-            if ms_pipe < ms_step:                          # `value` is the better of the two ways to run K stacks
+            # `value` is the better of the two ways to run K stacks; the pipeline only counts when it also wins over the
+            # long run (beside the peer exchange at N > 1 it is erratic: a lucky K-step figure must not become the headline)
+            if ms_pipe < ms_step and ms_pipe_sus < ms_sustained:
                 ms_step, launches = ms_pipe, pipe_launches
             else:
-                pipelined["note"] = "not faster than one stack at a time here: value / ms_per_step are the single-stack figures"
+                pipelined["note"] = "not faster than one stack at a time here (K steps and sustained): value / ms_per_step are the single-stack figures"
             del d_x2
         ps.close()
 
