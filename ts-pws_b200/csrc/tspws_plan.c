@@ -746,11 +746,11 @@ tspws_plan_t *tspws_b200_plan_create(const t_tsPWS *p, int max, unsigned int mtr
         CK(cudaMalloc(&pl->d_pps, (size_t)pl->nchunk * ncoef * pl->csz));
         CK(cudaMalloc(&pl->d_pst, (size_t)pl->nchunk * ncoef * pl->csz));
         /* Dense tensor-core transform of the coarse scales (D >= TSPWS_DENSE_D, default 256; 0 = off): single-stage fp32
-         * stacks of at least TSPWS_DENSE_MIN traces (default 1024: the products are fp32-faithful, but the phase of a near-zero
-         * coefficient of a single trace weighs 1/mtr in the coherence -- measured 1.1e-5 at 256 traces, 2e-6 from 1024 on) whose length is a multiple of 64.  The scales must be
+         * stacks of at least TSPWS_DENSE_MIN traces (default 500 = the station-pair geometry of BASELINE configs[4]: the products are fp32-faithful, but the phase of a near-zero
+         * coefficient of a single trace weighs 1/mtr in the coherence -- measured 1.1e-5 at 256 traces, 2.7-3.3e-6 at 500 (three seeds), 2e-6 from 1024 on) whose length is a multiple of 64.  The scales must be
          * polyphase (D >= 32) items so that the SIMT launch can skip them by item index. */
         const long dD = env_long("TSPWS_DENSE_D", 256);
-        if (!pl->two_stage && !pl->acc64 && dD > 0 && max % 64 == 0 && (long)mtr_local >= env_long("TSPWS_DENSE_MIN", 1024)) {
+        if (!pl->two_stage && !pl->acc64 && dD > 0 && max % 64 == 0 && (long)mtr_local >= env_long("TSPWS_DENSE_MIN", 500)) {
             int s0 = -1;
             for (unsigned int s = 0; s < pl->fr->S; s++)
                 if ((long)pl->fr->D[s] >= dD && pl->fr->D[s] >= 32 && pl->fr->D[s] <= (unsigned int)max) { s0 = (int)s; break; }
