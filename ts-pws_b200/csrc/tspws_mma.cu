@@ -382,7 +382,7 @@ out:
 /*   D = x0 W0 + x0 W1 + x1 W0 + x1 W1 + x0 W2 + x2 W0   (everything above 2^-25), fp32 in TMEM  */
 /* Two terms (2^-17) are NOT enough: a trace whose coefficient happens to be ~1e-4 of the typical     */
 /* magnitude has an ill-conditioned phase, and one such (trace, coefficient) pair in 150 000 moved   */
-/* the coherence by 1.2e-4 (tools/_dense_check2.py); fp32-faithful products keep it at the SIMT      */
+/* the coherence by 1.2e-4 (tools/dense_check2.py); fp32-faithful products keep it at the SIMT      */
 /* path's 2e-6.                                                                                    */
 /* and the epilogue is the phasor accumulate of src/ts_pws1f_lib.c:486-494: unit phasor of     */
 /* every (trace, coefficient), summed over the 128 traces of the M tile (warp transpose-reduce   */
@@ -417,7 +417,7 @@ __device__ __forceinline__ void fd_transpose_stage(float (&f)[32], const int lan
 }
 
 /* The tensor core adds into its fp32 accumulator with truncation, not round-to-nearest: measured on B200
- * (tools/_mma_acc_check.py) the result of a K = 16384 accumulation is biased by -1.7e-5 relative, linearly in K
+ * (tools/mma_acc_check.py) the result of a K = 16384 accumulation is biased by -1.7e-5 relative, linearly in K
  * -- 8e-5 on the coherence of the coarse scales.  So the K loop is cut into chunks of FD_CHUNK k blocks (512 samples:
  * bias < 1e-6): every chunk accumulates into one of TWO TMEM accumulators, and the epilogue warps drain the finished
  * one into fp32 registers (round-to-nearest adds) while the next chunk's MMAs run -- the promotion trick of FP8 GEMMs. */
